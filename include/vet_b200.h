@@ -1,0 +1,165 @@
+/*
+ * vet_b200.h -- C ABI of the B200-native viewport-entropy hot path.
+ *
+ * The reference (IamArmanNikkhah/viewport-entropy-toolkit) is pure Python and has
+ * no FFI of its own; its boundary for this path is the Python API.  Each entry
+ * point below names the reference interface it replaces.  Paths are relative to
+ * src/viewport_entropy_toolkit/ in the reference:
+ *   EU = utilities/entropy_utils.py   DU = utilities/data_utils.py
+ *   DT = data_types.py   CFG = config.py
+ *   SA = analyzers/spatial_entropy.py   TA = analyzers/transition_entropy.py
+ *
+ * Conventions
+ *   - every function returns a vet_status (0 = ok, negative = error) and never
+ *     throws; vet_last_error() returns a thread-local message for the last error;
+ *   - the caller owns every buffer; the library owns only the per-configuration
+ *     device tables behind the opaque handle (lattices, cell->tile LUTs, FOV weight
+ *     tables, scratch) -- one handle per (device, configuration);
+ *   - "dev" pointers are device pointers on the handle's device, "host" pointers
+ *     are host pointers; `stream` is a cudaStream_t passed as void* (NULL = the
+ *     legacy default stream).  Calls taking a stream are asynchronous;
+ *   - packed input is [F, U, 3] = (time, 2dmu, 2dmv), frame-major, float32 or
+ *     float64 (VET_F32 / VET_F64).  A NaN in 2dmu or 2dmv marks a missing sample
+ *     (== a row dropped by dropna at DU:314 / a None cell at SA:131-135);
+ *   - tile index outputs use VET_MISSING (0xFFFF) for missing samples;
+ *   - data-dependent error conditions that the reference reports by raising
+ *     (value outside [0,1]: DU:256-257; frame without users: EU:168-169; frame
+ *     pair without a common user: ZeroDivisionError at EU:326) are collected in
+ *     a sticky device flag word, read with vet_poll_flags().
+ */
+#ifndef VET_B200_H
+#define VET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vet_handle vet_handle;
+
+typedef enum {
+  VET_OK = 0,
+  VET_ERR_INVALID_ARG = -1, /* ValueError / ValidationError of CFG:62-67, EU:35-38, DU:236-240 */
+  VET_ERR_CUDA = -2,        /* CUDA runtime failure (message in vet_last_error) */
+  VET_ERR_UNSUPPORTED = -3, /* configuration outside what the tables can hold */
+  VET_ERR_NOMEM = -4
+} vet_status;
+
+enum { VET_F32 = 0, VET_F64 = 1 };
+enum { VET_TRANSITION_LITERAL = 0, VET_TRANSITION_TEXTBOOK = 1 };
+enum { VET_MISSING = 0xFFFF };
+
+/* bits of the sticky flag word (vet_poll_flags) */
+enum {
+  VET_FLAG_OUT_OF_RANGE = 1,  /* a non-missing 2dmu/2dmv outside [0,1]      (DU:256-257) */
+  VET_FLAG_EMPTY_FRAME = 2,   /* a frame with no present user               (EU:168-169) */
+  VET_FLAG_NO_COMMON_USER = 4 /* a frame pair without a common user         (EU:326)     */
+};
+
+/* AnalyzerConfig (CFG:39-58) + EntropyConfig (EU:20-31), flattened. */
+typedef struct {
+  int32_t device;                  /* CUDA device ordinal */
+  int32_t video_width;             /* CFG:53, must be even (DU:239) */
+  int32_t video_height;            /* CFG:54 */
+  int32_t num_tile_counts;         /* len(tile_counts), CFG:55 */
+  const int32_t* tile_counts;      /* host; tile_count n gives T = 2*int(n/2)+1 tiles (DU:43-45) */
+  double fov_angle;                /* EU:29, degrees, 0 < fov <= 360 */
+  double power_factor;             /* EU:31, > 0 */
+  int32_t use_weight_distribution; /* EU:30 */
+  /* Optional host-supplied tables.  NULL => the library derives them itself
+   * with libm, following DU:40-54 / DU:283-284,390-397 / DT:204-216.  The
+   * Python host passes numpy-made tables so that results follow numpy's
+   * arcsin/sin/cos bit for bit (numpy's arcsin differs from libm by 1 ulp on
+   * some inputs). */
+  const double* const* centres; /* [K] pointers to [T_k,3] lattice centres (generate_fibonacci_lattice, DU:25-56) */
+  const double* lon_by_px;      /* [W+1] degrees, after round(.,1) and the wrap quirk (DU:390-395) */
+  const double* lat_by_py;      /* [H+1] degrees, after round(.,1) and the wrap quirk (DU:391-397) */
+} vet_config;
+
+const char* vet_last_error(void);
+const char* vet_version(void);
+
+/* Replaces SpatialEntropyAnalyzer.__init__ / TransitionEntropyAnalyzer.__init__
+ * (SA:53-66, TA:53-66): validates the configuration, builds the Fibonacci
+ * lattices, the per-cell direction table, the cell->nearest-tile LUT of every
+ * tile count (with the brute-force fp64 kernel) and, when weighting is on, the
+ * FOV weight tables. */
+int vet_create(vet_handle** out, const vet_config* cfg);
+int vet_destroy(vet_handle* h);
+
+/* len(generate_fibonacci_lattice(tile_counts[k]))  (DU:43-45). */
+int vet_num_tiles(const vet_handle* h, int k);
+/* Number of reachable cells (video_height+1)*(video_width+1). */
+int64_t vet_num_cells(const vet_handle* h);
+
+/* generate_fibonacci_lattice(tile_counts[k]) -> centres_host[T_k,3]  (DU:25-56). */
+int vet_lattice(const vet_handle* h, int k, double* centres_host);
+/* Nearest tile of every cell (row-major py*(W+1)+px) for tile count k -> lut_host[cells]. */
+int vet_cell_lut(const vet_handle* h, int k, uint16_t* lut_host);
+
+/* Stage 1.  normalize_to_pixel + pixel_to_spherical + round/wrap + Vector.from_spherical
+ * (DU:243-286, DU:390-404, DT:183-216) for n samples: packed_dev[n,3] -> vec_dev[n,3]
+ * (float64; NaN for missing / out-of-range samples).  cell_dev (optional, may be
+ * NULL) receives py*(W+1)+px, or -1 for missing samples. */
+int vet_decode(vet_handle* h, const void* packed_dev, int dtype, int64_t n, double* vec_dev,
+               int32_t* cell_dev, void* stream);
+
+/* Stage 2.  find_nearest_tile (EU:89-106) for n arbitrary vectors against the
+ * lattice of tile count k: vec_dev[n,3] float64 -> idx_dev[n].  fp64 dot of the
+ * re-normalised operands (EU:58-61), lowest index among equal maxima (== first
+ * minimum of arccos, EU:104). */
+int vet_nearest_tile(vet_handle* h, int k, const double* vec_dev, int64_t n, int32_t* idx_dev,
+                     void* stream);
+
+/* calculate_tile_weights (EU:108-144) for n arbitrary vectors, dense rows:
+ * w_dev[n,T_k] float64 (0 where the reference's dict has no entry). */
+int vet_tile_weights(vet_handle* h, int k, const double* vec_dev, int64_t n, double* w_dev,
+                     void* stream);
+
+/* Stages 1-3 fused.  SpatialEntropyAnalyzer.compute_entropy (SA:107-164) on
+ * packed_dev[F,U,3]:
+ *   entropy_dev[F]       mean over tile counts of compute_spatial_entropy (EU:147-211)
+ *   per_k_dev[K,F]       (optional) entropy per tile count
+ *   hist0_dev[F,T_0]     (optional) tile weights of tile_counts[0] (SA:152-154), dense
+ *   assign0_dev[F,U]     (optional) nearest tile of tile_counts[0] per user (uint16) */
+int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U,
+                double* entropy_dev, double* per_k_dev, double* hist0_dev, uint16_t* assign0_dev,
+                void* stream);
+
+/* Stage 4.  TransitionEntropyAnalyzer.compute_entropy (TA:107-175) on
+ * packed_dev[F,U,3]; row r describes frames (r, r+1):
+ *   entropy_dev[F-1]        mean over tile counts of compute_transition_entropy (EU:213-332)
+ *   per_k_dev[K,F-1]        (optional)
+ *   prev_count0_dev[F-1,T_0](optional) users per previous tile, tile_counts[0] (EU:289-292)
+ *   pairs0_dev[F-1,U,2]     (optional) (prev,cur) tile per user, tile_counts[0] (EU:276)
+ * mode: VET_TRANSITION_LITERAL reproduces the reference's order-dependent
+ * bookkeeping (EU:278-318); VET_TRANSITION_TEXTBOOK is an opt-in conditional
+ * entropy that the reference does NOT compute. */
+int vet_transition(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U,
+                   double* entropy_dev, double* per_k_dev, int32_t* prev_count0_dev,
+                   uint16_t* pairs0_dev, int mode, void* stream);
+
+/* Host-buffer variants (the reference-facing call: numpy in, numpy out).  The
+ * packed tensor is streamed to the device in frame batches through pinned
+ * staging buffers, copies overlapped with the kernels; results are copied
+ * back.  Synchronous.  Optional outputs may be NULL. */
+int vet_spatial_host(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U,
+                     double* entropy_host, double* per_k_host, double* hist0_host,
+                     uint16_t* assign0_host);
+int vet_transition_host(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U,
+                        double* entropy_host, double* per_k_host, int32_t* prev_count0_host,
+                        uint16_t* pairs0_host, int mode);
+
+/* Synchronises `stream`, returns the sticky VET_FLAG_* word in *flags and
+ * clears it. */
+int vet_poll_flags(vet_handle* h, void* stream, uint32_t* flags);
+
+/* Number of kernel launches issued through this handle since creation
+ * (bench.py's gpu_launches). */
+int64_t vet_launch_count(const vet_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VET_B200_H */

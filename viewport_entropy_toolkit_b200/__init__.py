@@ -1,0 +1,21 @@
+"""viewport_entropy_toolkit_b200 -- B200-native SpatialEntropyAnalyzer /
+TransitionEntropyAnalyzer hot path of viewport-entropy-toolkit.
+
+Same public names as the reference package for the accelerated path; compute runs
+in hand-written sm_100a CUDA kernels behind a C ABI (include/vet_b200.h).  Importing
+the package does not need a GPU; computing anything does.
+"""
+from .data_types import Point, RadialPoint, Vector, ValidationError, SpatialError
+from .config import (AnalyzerConfig, EntropyConfig, VisualizationConfig, DEFAULT_VIDEO_DIMENSIONS,
+                     DEFAULT_TILE_COUNTS, DEFAULT_OUTPUT_FORMATS)
+from .engine import Engine, SpatialResult, TransitionResult, UnsupportedConfigurationError, get_engine
+from .analyzers import SpatialEntropyAnalyzer, TransitionEntropyAnalyzer
+
+__version__ = "0.1.0"
+__all__ = [
+    "Point", "RadialPoint", "Vector", "ValidationError", "SpatialError",
+    "AnalyzerConfig", "EntropyConfig", "VisualizationConfig",
+    "DEFAULT_VIDEO_DIMENSIONS", "DEFAULT_TILE_COUNTS", "DEFAULT_OUTPUT_FORMATS",
+    "Engine", "SpatialResult", "TransitionResult", "UnsupportedConfigurationError", "get_engine",
+    "SpatialEntropyAnalyzer", "TransitionEntropyAnalyzer",
+]

@@ -1,0 +1,190 @@
+"""Analyzer facades with the reference's class API, backed by the device engine.
+
+SpatialEntropyAnalyzer   <-> analyzers/spatial_entropy.py    (SA:40-253)
+TransitionEntropyAnalyzer <-> analyzers/transition_entropy.py (TA:40-264)
+
+`process_directory` / `compute_entropy` / `create_visualization` / `run_analysis`
+keep their names, arguments, return types and error behaviour; the frame loops of
+SA:129-161 and TA:129-172 run as CUDA kernels over the packed tensor.  The tensor
+level entry points (`compute_entropy_packed`) are the ones to use at scale: they
+return tensors instead of per-frame Python dicts.
+"""
+from __future__ import annotations
+
+import logging
+from datetime import datetime
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _tables
+from .config import AnalyzerConfig, DEFAULT_OUTPUT_FORMATS
+from .data_types import ValidationError, Vector
+from .engine import Engine, SpatialResult, TransitionResult, get_engine
+from .ingest import load_directory
+
+logger = logging.getLogger(__name__)
+
+
+def _lattice_vectors(tile_count: int) -> List[Vector]:
+    return [Vector(float(x), float(y), float(z)) for x, y, z in _tables.fibonacci_lattice(tile_count)]
+
+
+class _AnalyzerBase:
+    def __init__(self, config: Optional[AnalyzerConfig] = None, device: Optional[torch.device] = None):
+        self.config = config or AnalyzerConfig()
+        self._device = device
+        self._data_cache: Dict = {}
+        self._entropy_results: Optional[pd.DataFrame] = None
+        self._fibonacci_vectors = {count: _lattice_vectors(count) for count in self.config.tile_counts}
+        self._engine: Optional[Engine] = None
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            c = self.config
+            self._engine = get_engine(c.video_width, c.video_height, c.tile_counts, c.entropy_config, self._device)
+        return self._engine
+
+    def process_directory(self, directory: Path, order: Optional[Sequence[str]] = None) -> None:
+        """Reads every *.csv of `directory` into the packed tensor.  `order`
+        optionally pins the user order (file stems); the default is glob order."""
+        directory = Path(directory)
+        if not directory.exists():
+            raise FileNotFoundError(f"Directory not found: {directory}")
+        try:
+            packed, times, identifiers = load_directory(directory, order)
+            self._data_cache = {"packed": packed, "times": times, "identifiers": identifiers}
+        except Exception as e:
+            logger.error(f"Error processing directory {directory}: {str(e)}")
+            raise ValidationError(f"Failed to process directory: {str(e)}")
+
+    def load_packed(self, packed: np.ndarray, identifiers: Optional[Sequence[str]] = None) -> None:
+        """Uses an in-memory packed[F,U,3] array instead of a directory."""
+        packed = np.asarray(packed)
+        if packed.ndim != 3 or packed.shape[-1] != 3:
+            raise ValidationError("packed must be [F, U, 3]")
+        ids = list(identifiers) if identifiers is not None else [f"user{u}" for u in range(packed.shape[1])]
+        self._data_cache = {"packed": packed, "times": packed[:, 0, 0].astype(np.float64), "identifiers": ids}
+
+    def _device_packed(self) -> torch.Tensor:
+        if not self._data_cache:
+            raise ValidationError("No data available. Call process_directory first.")
+        return torch.from_numpy(np.ascontiguousarray(self._data_cache["packed"])).to(self.engine.device)
+
+    def _save_csv(self, base_name: str) -> Path:
+        path = self.config.get_output_path(base_name, DEFAULT_OUTPUT_FORMATS["data"])
+        self._entropy_results[["time", "entropy"]].to_csv(path, index=False)
+        return path
+
+    def create_visualization(self, base_name: str) -> None:
+        """Writes the [time, entropy] CSV (SA:211-219).  The matplotlib graph and the
+        ffmpeg animation of the reference are outside the accelerated path; the graph
+        is drawn when matplotlib is importable and skipped (with a log line) otherwise."""
+        if self._entropy_results is None:
+            raise ValidationError("No entropy results. Call compute_entropy first.")
+        try:
+            self._save_csv(base_name)
+            try:
+                import matplotlib
+                matplotlib.use("Agg")
+                import matplotlib.pyplot as plt
+            except Exception:
+                logger.info("matplotlib not available: skipping the entropy graph")
+                return
+            vc = self.config.visualization_config
+            fig, ax = plt.subplots(figsize=vc.figure_size)
+            ax.plot(self._entropy_results["time"], self._entropy_results["entropy"])
+            ax.set_xlabel("Time (s)")
+            ax.set_ylabel("Entropy")
+            fig.savefig(self.config.get_output_path(f"{base_name}_graph", DEFAULT_OUTPUT_FORMATS["plot"]), dpi=vc.dpi)
+            plt.close(fig)
+        except Exception as e:
+            logger.error(f"Error creating visualization: {str(e)}")
+            raise RuntimeError(f"Failed to create visualization: {str(e)}")
+
+    def run_analysis(self, directory: Path, output_prefix: str = "") -> None:
+        """process_directory -> compute_entropy -> create_visualization (SA:225-253)."""
+        try:
+            directory = Path(directory)
+            self.process_directory(directory)
+            self.compute_entropy()
+            timestamp = datetime.now().strftime("%Y%m%d_%H%M%S")
+            base_name = f"{directory.stem}_{output_prefix}_{timestamp}"
+            self.create_visualization(base_name)
+            logger.info(f"Analysis completed successfully: {base_name}")
+        except Exception as e:
+            logger.error(f"Analysis failed: {str(e)}")
+            raise
+
+
+class SpatialEntropyAnalyzer(_AnalyzerBase):
+    """Per-frame normalised Shannon entropy of the (FOV-weighted) tile histogram,
+    averaged over `config.tile_counts` (SA:107-164)."""
+
+    def compute_entropy_packed(self, packed: torch.Tensor, **kw) -> SpatialResult:
+        """Tensor-level entry point: packed[F,U,3] on the device -> SpatialResult.
+        Raises what the reference raises for bad data (out-of-range coordinate,
+        frame without users)."""
+        res = self.engine.spatial(packed, **kw)
+        self.engine.raise_for_flags()
+        return res
+
+    def compute_entropy(self) -> pd.DataFrame:
+        if not self._data_cache:
+            raise ValidationError("No data available. Call process_directory first.")
+        res = self.compute_entropy_packed(self._device_packed())
+        ent = res.entropy.cpu().numpy()
+        hist0 = res.hist0.cpu().numpy()
+        assign0 = res.assign0.cpu().numpy()
+        centres = self._fibonacci_vectors[self.config.tile_counts[0]]
+        ids = self._data_cache["identifiers"]
+        rows = {"time": [], "entropy": [], "tile_weights": [], "tile_assignments": []}
+        for f, t in enumerate(self._data_cache["times"]):
+            nz = np.flatnonzero(hist0[f])
+            rows["time"].append(t)
+            rows["entropy"].append(ent[f])
+            rows["tile_weights"].append({centres[i]: float(hist0[f, i]) for i in nz})
+            rows["tile_assignments"].append({ids[u]: int(a) for u, a in enumerate(assign0[f]) if a != 0xFFFF})
+        self._entropy_results = pd.DataFrame(rows)
+        return self._entropy_results
+
+
+class TransitionEntropyAnalyzer(_AnalyzerBase):
+    """Per-frame-pair transition entropy with the reference's literal bookkeeping
+    (TA:107-175, EU:213-332).  The first frame yields no row; row time is the
+    CURRENT frame's time (TA:130,162)."""
+
+    def __init__(self, config: Optional[AnalyzerConfig] = None, device: Optional[torch.device] = None,
+                 mode: str = "literal"):
+        super().__init__(config, device)
+        self.mode = mode
+
+    def compute_entropy_packed(self, packed: torch.Tensor, **kw) -> TransitionResult:
+        res = self.engine.transition(packed, mode=self.mode, **kw)
+        self.engine.raise_for_flags()
+        return res
+
+    def compute_entropy(self) -> pd.DataFrame:
+        if not self._data_cache:
+            raise ValidationError("No data available. Call process_directory first.")
+        res = self.compute_entropy_packed(self._device_packed())
+        ent = res.entropy.cpu().numpy()
+        counts = res.prev_count0.cpu().numpy()
+        pairs = res.pairs0.cpu().numpy()
+        centres = self._fibonacci_vectors[self.config.tile_counts[0]]
+        ids = self._data_cache["identifiers"]
+        times = self._data_cache["times"]
+        rows = {"time": [], "entropy": [], "tile_weights": [], "tile_assignments": []}
+        for r in range(len(ent)):
+            nz = np.flatnonzero(counts[r])
+            rows["time"].append(times[r + 1])
+            rows["entropy"].append(ent[r])
+            rows["tile_weights"].append({centres[i]: int(counts[r, i]) for i in nz})
+            rows["tile_assignments"].append(
+                {ids[u]: (int(p), int(c)) for u, (p, c) in enumerate(pairs[r]) if p != 0xFFFF})
+        self._entropy_results = pd.DataFrame(rows)
+        return self._entropy_results

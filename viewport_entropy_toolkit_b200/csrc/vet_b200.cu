@@ -1,0 +1,772 @@
+// libvet_b200.so -- C ABI (include/vet_b200.h) over the sm_100a kernels.
+// Host side: configuration validation, table construction (lattice, per-axis
+// direction tables, cell->tile LUTs, FOV weight columns), scratch management and
+// kernel launches.  No CPU compute path: every stage runs on the device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "vet_b200.h"
+#include "vet_common.cuh"
+#include "vet_stream.cuh"
+#include "vet_tables.cuh"
+#include "vet_transition.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define VET_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(VET_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct TileSet {
+  int n = 0;  // tile_count as configured
+  int T = 0;  // number of lattice points
+  std::vector<double> h_centres;  // [T,3]
+  double* d_unit = nullptr;       // [T,3] centres / ||centre||
+  uint16_t* d_lut = nullptr;      // [C]
+  std::vector<uint16_t> h_lut;
+  uint32_t* d_col_ptr = nullptr;  // [T+1]
+  uint32_t* d_cell_idx = nullptr;
+  double* d_w_val = nullptr;
+  uint64_t nnz = 0;
+};
+
+}  // namespace
+
+struct vet_handle {
+  int device = 0;
+  int W = 0, H = 0;
+  int64_t C = 0;
+  int K = 0;
+  double fov = 120.0, pf = 2.0, max_d = 0.0;
+  int use_weight = 1;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  int maxT = 0;
+  std::vector<TileSet> ts;
+  double *d_cosT = nullptr, *d_sinT = nullptr, *d_sinP = nullptr, *d_cosP = nullptr;
+  double* d_cellvec = nullptr;  // [C,3]
+  uint32_t* d_flags = nullptr;
+  // scratch (grown on demand)
+  uint32_t* d_cnt = nullptr;
+  size_t cnt_bytes = 0;
+  void* d_cells = nullptr;
+  size_t cells_bytes = 0;
+  uint32_t* d_tables = nullptr;
+  size_t tables_words = 0;
+  // host-buffer path
+  void* d_in[2] = {nullptr, nullptr};
+  size_t in_bytes = 0;
+  cudaStream_t s_copy = nullptr, s_exec = nullptr;
+  int64_t launches = 0;
+};
+
+namespace {
+
+// ---- host-side table construction (libm; used when the caller passes no tables) ----
+
+// numpy's remainder for doubles (npy_divmod): result takes the sign of the divisor.
+double np_mod(double a, double b) {
+  double m = std::fmod(a, b);
+  if (m != 0.0) {
+    if ((b < 0) != (m < 0)) m += b;
+  } else {
+    m = std::copysign(0.0, b);
+  }
+  return m;
+}
+double np_radians(double x) { return x * (M_PI / 180.0); }
+double np_round6(double v) { return std::rint(v * 1e6) / 1e6; }
+// CPython round(x, 1): correctly rounded decimal (round-half-even on the exact
+// binary value) -- glibc's printf does exactly that.
+double py_round1(double x) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.1f", x);
+  return strtod(buf, nullptr);
+}
+
+// Vector.from_spherical, DT:204-216.
+void from_spherical(double lon, double lat, double* out) {
+  const double theta = np_radians(lon), phi = np_radians(90 - lat);
+  out[0] = np_round6(std::sin(phi) * std::cos(theta));
+  out[1] = np_round6(std::sin(phi) * std::sin(theta));
+  out[2] = np_round6(std::cos(phi));
+}
+
+// generate_fibonacci_lattice, DU:40-54.
+std::vector<double> make_lattice(int n) {
+  const double phi = (1 + std::sqrt(5.0)) / 2;
+  const int N = n / 2;
+  std::vector<double> c((size_t)(2 * N + 1) * 3);
+  for (int i = -N; i <= N; ++i) {
+    const double lat = std::asin(2.0 * i / (2 * N + 1)) * 180 / M_PI;
+    double lon = np_mod((double)i, phi) * 360 / phi;
+    lon = np_mod(lon + 180, 360.0) - 180;
+    from_spherical(lon, lat, &c[(size_t)(i + N) * 3]);
+  }
+  return c;
+}
+
+// pixel_to_spherical + rounding + wrap quirk, DU:283-284, 390-397.
+void make_axis_tables(int W, int H, std::vector<double>& lon, std::vector<double>& lat) {
+  lon.resize(W + 1);
+  lat.resize(H + 1);
+  for (int px = 0; px <= W; ++px) {
+    double v = ((double)px / W) * 360 - 180;
+    v = py_round1(v);
+    if (v <= -180) v = np_mod(v + 360, 360.0) - 180;
+    lon[px] = v;
+  }
+  for (int py = 0; py <= H; ++py) {
+    double v = 90 - ((double)py / H) * 180;
+    v = py_round1(v);
+    if (v <= -90) v = np_mod(v + 180, 180.0) - 90;
+    lat[py] = v;
+  }
+}
+
+template <typename T>
+int upload(T** dptr, const T* host, size_t count) {
+  VET_CUDA(cudaMalloc((void**)dptr, std::max<size_t>(count, 1) * sizeof(T)));
+  if (count) VET_CUDA(cudaMemcpy(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  return VET_OK;
+}
+
+int grow(void** ptr, size_t* have, size_t want) {
+  if (*have >= want) return VET_OK;
+  if (*ptr) VET_CUDA(cudaFree(*ptr));
+  *ptr = nullptr;
+  *have = 0;
+  VET_CUDA(cudaMalloc(ptr, want));
+  *have = want;
+  return VET_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+constexpr size_t kStaticSmemSlack = 1024;
+constexpr int kMaxT = 16384;
+
+int build_tile_set(vet_handle* h, TileSet& t) {
+  const int T = t.T;
+  std::vector<double> unit((size_t)T * 3);
+  for (int i = 0; i < T; ++i) {
+    const double x = t.h_centres[3 * i], y = t.h_centres[3 * i + 1], z = t.h_centres[3 * i + 2];
+    // np.linalg.norm == sqrt(dot(x,x)), ddot as an FMA chain
+    const double nrm = std::sqrt(std::fma(z, z, std::fma(y, y, x * x)));
+    if (!(nrm > 0)) return fail(VET_ERR_INVALID_ARG, "Vector cannot have zero length (tile %d)", i);
+    unit[3 * i] = x / nrm;
+    unit[3 * i + 1] = y / nrm;
+    unit[3 * i + 2] = z / nrm;
+  }
+  if (int rc = upload(&t.d_unit, unit.data(), unit.size())) return rc;
+  VET_CUDA(cudaMalloc((void**)&t.d_lut, (size_t)h->C * sizeof(uint16_t)));
+  const size_t smem = (size_t)T * 3 * sizeof(double);
+  VET_CUDA(cudaFuncSetAttribute(vet::k_nearest<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = 256;
+  const int64_t rounds = (h->C + threads / 4 - 1) / (threads / 4);
+  const int blocks = (int)std::min<int64_t>(rounds, (int64_t)h->sm_count * 8);
+  vet::k_nearest<uint16_t><<<blocks, threads, smem>>>(h->d_cellvec, h->C, t.d_unit, T, t.d_lut);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  t.h_lut.resize(h->C);
+  VET_CUDA(cudaMemcpy(t.h_lut.data(), t.d_lut, (size_t)h->C * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  if (h->use_weight) {
+    uint32_t* d_count = nullptr;
+    VET_CUDA(cudaMalloc((void**)&d_count, (size_t)T * sizeof(uint32_t)));
+    vet::k_weight_columns<false><<<T, 256>>>(h->d_cellvec, (int)h->C, t.d_unit, T, h->max_d, h->pf, d_count, nullptr,
+                                             nullptr, nullptr);
+    h->launches++;
+    VET_CUDA(cudaGetLastError());
+    std::vector<uint32_t> count(T), ptr(T + 1, 0);
+    VET_CUDA(cudaMemcpy(count.data(), d_count, (size_t)T * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    VET_CUDA(cudaFree(d_count));
+    uint64_t nnz = 0;
+    for (int i = 0; i < T; ++i) {
+      ptr[i] = (uint32_t)nnz;
+      nnz += count[i];
+    }
+    if (nnz >= 0xFFFFFFFFull) return fail(VET_ERR_UNSUPPORTED, "weight table too large (%llu entries)", (unsigned long long)nnz);
+    ptr[T] = (uint32_t)nnz;
+    t.nnz = nnz;
+    if (int rc = upload(&t.d_col_ptr, ptr.data(), ptr.size())) return rc;
+    VET_CUDA(cudaMalloc((void**)&t.d_cell_idx, std::max<uint64_t>(nnz, 1) * sizeof(uint32_t)));
+    VET_CUDA(cudaMalloc((void**)&t.d_w_val, std::max<uint64_t>(nnz, 1) * sizeof(double)));
+    vet::k_weight_columns<true><<<T, 256>>>(h->d_cellvec, (int)h->C, t.d_unit, T, h->max_d, h->pf, nullptr, t.d_col_ptr,
+                                            t.d_cell_idx, t.d_w_val);
+    h->launches++;
+    VET_CUDA(cudaGetLastError());
+  }
+  return VET_OK;
+}
+
+void free_tile_set(TileSet& t) {
+  cudaFree(t.d_unit);
+  cudaFree(t.d_lut);
+  cudaFree(t.d_col_ptr);
+  cudaFree(t.d_cell_idx);
+  cudaFree(t.d_w_val);
+}
+
+size_t stream_smem_bytes(const vet_handle* h) { return (size_t)h->C * 4 + (size_t)h->C * 2 + 16; }
+size_t epilogue_smem_bytes(const vet_handle* h) {
+  return (((size_t)h->C * 4 + 15) & ~(size_t)15) + (size_t)h->maxT * 8 + (size_t)h->maxT * 4 + 16;
+}
+
+// frames per batch so that the per-frame cell histogram scratch stays bounded
+int64_t frames_per_batch(const vet_handle* h, int64_t F, int64_t U, bool need_cells) {
+  const size_t budget = (size_t)1 << 30;  // 1 GiB of scratch
+  size_t per_frame = (size_t)h->C * 4;
+  if (need_cells) per_frame += (size_t)U * (h->C <= 65535 ? 2 : 4);
+  int64_t fb = (int64_t)std::max<size_t>(2, budget / std::max<size_t>(per_frame, 1));
+  return std::min<int64_t>(F, fb);
+}
+
+int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64_t U, uint16_t* assign0, bool cells,
+                  cudaStream_t st) {
+  vet::StreamArgs a{};
+  a.packed = packed;
+  a.F = F;
+  a.U = U;
+  a.W = h->W;
+  a.H = h->H;
+  a.C = (int)h->C;
+  a.lut0 = h->ts[0].d_lut;
+  a.assign0 = assign0;
+  a.cell16 = (cells && h->C <= 65535) ? (uint16_t*)h->d_cells : nullptr;
+  a.cell32 = (cells && h->C > 65535) ? (int32_t*)h->d_cells : nullptr;
+  a.cnt = h->d_cnt;
+  a.flags = h->d_flags;
+  // enough work items to balance the SMs, chunks no smaller than 32k users
+  const int64_t want_items = (int64_t)h->sm_count * 24;
+  int64_t cpf = std::min<int64_t>((U + 32767) / 32768, (want_items + F - 1) / F);
+  cpf = std::max<int64_t>(cpf, 1);
+  a.chunk_users = (U + cpf - 1) / cpf;
+  a.chunks_per_frame = (int)((U + a.chunk_users - 1) / std::max<int64_t>(a.chunk_users, 1));
+  if (a.chunks_per_frame < 1) a.chunks_per_frame = 1;
+  if (a.chunks_per_frame > 1) VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->C * 4, st));
+  const int64_t items = F * a.chunks_per_frame;
+  const int blocks = (int)std::min<int64_t>(items, h->sm_count);
+  const size_t smem = stream_smem_bytes(h);
+  if (dtype == VET_F32)
+    vet::k_stream_simple<float><<<blocks, 1024, smem, st>>>(a);
+  else
+    vet::k_stream_simple<double><<<blocks, 1024, smem, st>>>(a);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+int launch_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, int64_t per_k_stride, double* hist0,
+                    cudaStream_t st) {
+  vet::EpilogueArgs a{};
+  a.cnt = h->d_cnt;
+  a.F = F;
+  a.C = (int)h->C;
+  a.K = h->K;
+  a.use_weight = h->use_weight;
+  for (int k = 0; k < h->K; ++k) {
+    a.ts[k].T = h->ts[k].T;
+    a.ts[k].lut = h->ts[k].d_lut;
+    a.ts[k].col_ptr = h->ts[k].d_col_ptr;
+    a.ts[k].cell_idx = h->ts[k].d_cell_idx;
+    a.ts[k].w_val = h->ts[k].d_w_val;
+  }
+  a.entropy = entropy;
+  a.per_k = per_k;
+  a.per_k_stride = per_k_stride;
+  a.hist0 = hist0;
+  a.flags = h->d_flags;
+  const int blocks = (int)std::min<int64_t>(F, (int64_t)h->sm_count * 2);
+  vet::k_epilogue<<<blocks, 512, epilogue_smem_bytes(h), st>>>(a, h->maxT);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+}  // namespace
+
+// ================================ C ABI ==========================================
+
+extern "C" const char* vet_last_error(void) { return g_err.c_str(); }
+extern "C" const char* vet_version(void) { return "vet_b200 0.1 (sm_100a)"; }
+
+extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
+  if (!out || !cfg) return fail(VET_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  // CFG:62-67
+  if (cfg->video_width <= 0 || cfg->video_height <= 0) return fail(VET_ERR_INVALID_ARG, "Video dimensions must be positive");
+  if (cfg->num_tile_counts <= 0 || !cfg->tile_counts) return fail(VET_ERR_INVALID_ARG, "Must specify at least one tile count");
+  for (int k = 0; k < cfg->num_tile_counts; ++k)
+    if (cfg->tile_counts[k] <= 0) return fail(VET_ERR_INVALID_ARG, "Tile counts must be positive");
+  // DU:239
+  if (cfg->video_width % 2 || cfg->video_height % 2) return fail(VET_ERR_INVALID_ARG, "Video dimensions must be even numbers");
+  // EU:35-38
+  if (!(cfg->fov_angle > 0 && cfg->fov_angle <= 360)) return fail(VET_ERR_INVALID_ARG, "FOV angle must be between 0 and 360 degrees");
+  if (!(cfg->power_factor > 0)) return fail(VET_ERR_INVALID_ARG, "Power factor must be positive");
+  if (cfg->num_tile_counts > vet::kMaxTileCounts)
+    return fail(VET_ERR_UNSUPPORTED, "at most %d tile counts per handle", vet::kMaxTileCounts);
+
+  int ndev = 0;
+  VET_CUDA(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(VET_ERR_INVALID_ARG, "no such CUDA device %d", cfg->device);
+  DeviceGuard guard(cfg->device);
+  if (!guard.ok) return fail(VET_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device);
+
+  vet_handle* h = new (std::nothrow) vet_handle();
+  if (!h) return fail(VET_ERR_NOMEM, "out of host memory");
+  struct Cleanup {
+    vet_handle* h;
+    bool armed = true;
+    ~Cleanup() {
+      if (armed) vet_destroy(h);
+    }
+  } cleanup{h};
+
+  h->device = cfg->device;
+  h->W = cfg->video_width;
+  h->H = cfg->video_height;
+  h->C = (int64_t)(h->W + 1) * (h->H + 1);
+  h->K = cfg->num_tile_counts;
+  h->fov = cfg->fov_angle;
+  h->pf = cfg->power_factor;
+  h->use_weight = cfg->use_weight_distribution ? 1 : 0;
+  h->max_d = np_radians(h->fov / 2.0);  // EU:124
+  cudaDeviceProp prop;
+  VET_CUDA(cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+
+  h->ts.resize(h->K);
+  for (int k = 0; k < h->K; ++k) {
+    TileSet& t = h->ts[k];
+    t.n = cfg->tile_counts[k];
+    t.T = 2 * (t.n / 2) + 1;  // DU:43-45
+    if (t.T > kMaxT) return fail(VET_ERR_UNSUPPORTED, "tile_count %d gives %d tiles; at most %d supported", t.n, t.T, kMaxT);
+    h->maxT = std::max(h->maxT, t.T);
+    if (cfg->centres && cfg->centres[k])
+      t.h_centres.assign(cfg->centres[k], cfg->centres[k] + (size_t)t.T * 3);
+    else
+      t.h_centres = make_lattice(t.n);
+  }
+  // table regime: the per-frame cell histogram (u32) and the LUT must fit in shared memory
+  if (stream_smem_bytes(h) + kStaticSmemSlack > h->smem_optin || epilogue_smem_bytes(h) + kStaticSmemSlack > h->smem_optin)
+    return fail(VET_ERR_UNSUPPORTED,
+                "video %dx%d has %lld cells; the shared-memory cell histogram supports at most ~%lld cells on this device",
+                h->W, h->H, (long long)h->C, (long long)((h->smem_optin - kStaticSmemSlack) / 6));
+
+  std::vector<double> lon, lat;
+  if (cfg->lon_by_px && cfg->lat_by_py) {
+    lon.assign(cfg->lon_by_px, cfg->lon_by_px + h->W + 1);
+    lat.assign(cfg->lat_by_py, cfg->lat_by_py + h->H + 1);
+  } else {
+    make_axis_tables(h->W, h->H, lon, lat);
+  }
+  for (double v : lon)
+    if (!(v >= -180 && v <= 180)) return fail(VET_ERR_INVALID_ARG, "Longitude must be between -180 and 180 degrees");  // DT:80-81
+  for (double v : lat)
+    if (!(v >= -90 && v <= 90)) return fail(VET_ERR_INVALID_ARG, "Latitude must be between -90 and 90 degrees");  // DT:82-83
+  std::vector<double> cosT(h->W + 1), sinT(h->W + 1), sinP(h->H + 1), cosP(h->H + 1);
+  for (int px = 0; px <= h->W; ++px) {
+    const double th = np_radians(lon[px]);  // DT:204
+    cosT[px] = std::cos(th);
+    sinT[px] = std::sin(th);
+  }
+  for (int py = 0; py <= h->H; ++py) {
+    const double ph = np_radians(90 - lat[py]);  // DT:205
+    sinP[py] = std::sin(ph);
+    cosP[py] = std::cos(ph);
+  }
+  if (int rc = upload(&h->d_cosT, cosT.data(), cosT.size())) return rc;
+  if (int rc = upload(&h->d_sinT, sinT.data(), sinT.size())) return rc;
+  if (int rc = upload(&h->d_sinP, sinP.data(), sinP.size())) return rc;
+  if (int rc = upload(&h->d_cosP, cosP.data(), cosP.size())) return rc;
+  VET_CUDA(cudaMalloc((void**)&h->d_cellvec, (size_t)h->C * 3 * sizeof(double)));
+  VET_CUDA(cudaMalloc((void**)&h->d_flags, sizeof(uint32_t)));
+  VET_CUDA(cudaMemset(h->d_flags, 0, sizeof(uint32_t)));
+  vet::k_cell_vectors<<<std::min<int64_t>((h->C + 255) / 256, 1024), 256>>>(h->d_cosT, h->d_sinT, h->d_sinP, h->d_cosP,
+                                                                             h->W, h->H, h->d_cellvec);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  for (int k = 0; k < h->K; ++k)
+    if (int rc = build_tile_set(h, h->ts[k])) return rc;
+
+  VET_CUDA(cudaFuncSetAttribute(vet::k_stream_simple<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)stream_smem_bytes(h)));
+  VET_CUDA(cudaFuncSetAttribute(vet::k_stream_simple<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)stream_smem_bytes(h)));
+  VET_CUDA(cudaFuncSetAttribute(vet::k_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)epilogue_smem_bytes(h)));
+  VET_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+  VET_CUDA(cudaStreamCreateWithFlags(&h->s_exec, cudaStreamNonBlocking));
+  VET_CUDA(cudaDeviceSynchronize());
+  cleanup.armed = false;
+  *out = h;
+  return VET_OK;
+}
+
+extern "C" int vet_destroy(vet_handle* h) {
+  if (!h) return VET_OK;
+  DeviceGuard guard(h->device);
+  for (auto& t : h->ts) free_tile_set(t);
+  cudaFree(h->d_cosT);
+  cudaFree(h->d_sinT);
+  cudaFree(h->d_sinP);
+  cudaFree(h->d_cosP);
+  cudaFree(h->d_cellvec);
+  cudaFree(h->d_flags);
+  cudaFree(h->d_cnt);
+  cudaFree(h->d_cells);
+  cudaFree(h->d_tables);
+  cudaFree(h->d_in[0]);
+  cudaFree(h->d_in[1]);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_exec) cudaStreamDestroy(h->s_exec);
+  delete h;
+  return VET_OK;
+}
+
+extern "C" int vet_num_tiles(const vet_handle* h, int k) {
+  if (!h || k < 0 || k >= h->K) return fail(VET_ERR_INVALID_ARG, "bad tile-count index");
+  return h->ts[k].T;
+}
+extern "C" int64_t vet_num_cells(const vet_handle* h) { return h ? h->C : fail(VET_ERR_INVALID_ARG, "null handle"); }
+extern "C" int64_t vet_launch_count(const vet_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int vet_lattice(const vet_handle* h, int k, double* centres_host) {
+  if (!h || !centres_host || k < 0 || k >= h->K) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  std::memcpy(centres_host, h->ts[k].h_centres.data(), h->ts[k].h_centres.size() * sizeof(double));
+  return VET_OK;
+}
+
+extern "C" int vet_cell_lut(const vet_handle* h, int k, uint16_t* lut_host) {
+  if (!h || !lut_host || k < 0 || k >= h->K) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  std::memcpy(lut_host, h->ts[k].h_lut.data(), h->ts[k].h_lut.size() * sizeof(uint16_t));
+  return VET_OK;
+}
+
+extern "C" int vet_decode(vet_handle* h, const void* packed_dev, int dtype, int64_t n, double* vec_dev, int32_t* cell_dev,
+                          void* stream) {
+  if (!h || (!packed_dev && n > 0) || n < 0 || (dtype != VET_F32 && dtype != VET_F64))
+    return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return VET_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
+  if (dtype == VET_F32)
+    vet::k_decode<float><<<blocks, 256, 0, st>>>((const float*)packed_dev, n, h->W, h->H, h->d_cosT, h->d_sinT, h->d_sinP,
+                                                 h->d_cosP, vec_dev, cell_dev, h->d_flags);
+  else
+    vet::k_decode<double><<<blocks, 256, 0, st>>>((const double*)packed_dev, n, h->W, h->H, h->d_cosT, h->d_sinT,
+                                                  h->d_sinP, h->d_cosP, vec_dev, cell_dev, h->d_flags);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+extern "C" int vet_nearest_tile(vet_handle* h, int k, const double* vec_dev, int64_t n, int32_t* idx_dev, void* stream) {
+  if (!h || k < 0 || k >= h->K || n < 0 || (n > 0 && (!vec_dev || !idx_dev))) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return VET_OK;
+  DeviceGuard guard(h->device);
+  const TileSet& t = h->ts[k];
+  const size_t smem = (size_t)t.T * 3 * sizeof(double);
+  VET_CUDA(cudaFuncSetAttribute(vet::k_nearest<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = 256;
+  const int64_t rounds = (n + threads / 4 - 1) / (threads / 4);
+  const int blocks = (int)std::min<int64_t>(rounds, (int64_t)h->sm_count * 8);
+  vet::k_nearest<int32_t><<<blocks, threads, smem, (cudaStream_t)stream>>>(vec_dev, n, t.d_unit, t.T, idx_dev);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+extern "C" int vet_tile_weights(vet_handle* h, int k, const double* vec_dev, int64_t n, double* w_dev, void* stream) {
+  if (!h || k < 0 || k >= h->K || n < 0 || (n > 0 && (!vec_dev || !w_dev))) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return VET_OK;
+  DeviceGuard guard(h->device);
+  const TileSet& t = h->ts[k];
+  const size_t smem = (size_t)t.T * 3 * sizeof(double);
+  VET_CUDA(cudaFuncSetAttribute(vet::k_tile_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)h->sm_count * 8);
+  vet::k_tile_weights<<<blocks, 256, smem, (cudaStream_t)stream>>>(vec_dev, n, t.d_unit, t.T, h->max_d, h->pf, h->use_weight,
+                                                                   w_dev);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
+                           double* per_k_dev, double* hist0_dev, uint16_t* assign0_dev, void* stream) {
+  if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (F == 0) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:168-169
+  if (!packed_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t fb = frames_per_batch(h, F, U, false);
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->C * 4)) return rc;
+  const size_t esz = dtype == VET_F32 ? 4 : 8;
+  const int T0 = h->ts[0].T;
+  for (int64_t f0 = 0; f0 < F; f0 += fb) {
+    const int64_t nf = std::min(fb, F - f0);
+    const char* in = (const char*)packed_dev + (size_t)f0 * U * 3 * esz;
+    if (int rc = launch_stream(h, in, dtype, nf, U, assign0_dev ? assign0_dev + f0 * U : nullptr, false, st)) return rc;
+    if (int rc = launch_epilogue(h, nf, entropy_dev + f0, per_k_dev ? per_k_dev + f0 : nullptr, F,
+                                 hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
+      return rc;
+  }
+  return VET_OK;
+}
+
+extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
+                              double* per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode, void* stream) {
+  if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
+  if (F <= 1) return VET_OK;  // TA:143-146: the first frame yields no row
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:239-240
+  if (!packed_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  if (U >= 0xFFFFFFFFll) return fail(VET_ERR_UNSUPPORTED, "too many users");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
+  const size_t csz = h->C <= 65535 ? 2 : 4;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->C * 4)) return rc;
+  if (int rc = grow(&h->d_cells, &h->cells_bytes, (size_t)fb * U * csz)) return rc;
+  // pair table: capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
+  const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)h->maxT * h->maxT);
+  uint32_t cap = 1024;
+  while ((uint64_t)cap < 2 * max_pairs) cap <<= 1;
+  const size_t tile_bytes = (size_t)h->maxT * (8 + 4 * 4);
+  const size_t smem_tab = tile_bytes + (size_t)cap * 16 + 64;
+  const bool in_smem = smem_tab + kStaticSmemSlack <= h->smem_optin;
+  int blocks = (int)std::min<int64_t>(F - 1, (int64_t)h->sm_count * (in_smem ? 1 : 2));
+  if (!in_smem) {
+    const size_t words = (size_t)blocks * 4 * cap;
+    if (h->tables_words < words) {
+      if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
+      h->d_tables = nullptr;
+      h->tables_words = 0;
+      VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
+      h->tables_words = words;
+    }
+    // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value); kernels leave the tables clean
+    for (int b = 0; b < blocks; ++b) {
+      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+    }
+  }
+  const size_t esz = dtype == VET_F32 ? 4 : 8;
+  const int T0 = h->ts[0].T;
+  // batches overlap by one frame (the halo frame of SURVEY 8e)
+  for (int64_t f0 = 0; f0 < F - 1; f0 += fb - 1) {
+    const int64_t nf = std::min(fb, F - f0);
+    const char* in = (const char*)packed_dev + (size_t)f0 * U * 3 * esz;
+    if (int rc = launch_stream(h, in, dtype, nf, U, nullptr, true, st)) return rc;
+    vet::TransitionArgs a{};
+    a.cell16 = csz == 2 ? (const uint16_t*)h->d_cells : nullptr;
+    a.cell32 = csz == 4 ? (const int32_t*)h->d_cells : nullptr;
+    a.F = nf;
+    a.U = U;
+    a.K = h->K;
+    for (int k = 0; k < h->K; ++k) {
+      a.T[k] = h->ts[k].T;
+      a.lut[k] = h->ts[k].d_lut;
+    }
+    a.entropy = entropy_dev + f0;
+    a.per_k = per_k_dev ? per_k_dev + f0 : nullptr;
+    a.per_k_stride = F - 1;
+    a.prev_count0 = prev_count0_dev ? prev_count0_dev + f0 * T0 : nullptr;
+    a.pairs0 = pairs0_dev ? pairs0_dev + f0 * U * 2 : nullptr;
+    a.mode = mode;
+    a.flags = h->d_flags;
+    a.cap = cap;
+    a.g_tables = h->d_tables;
+    const int nb = (int)std::min<int64_t>(nf - 1, blocks);
+    if (in_smem) {
+      VET_CUDA(cudaFuncSetAttribute(vet::k_transition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
+      vet::k_transition<true><<<nb, 512, smem_tab, st>>>(a, h->maxT);
+    } else {
+      VET_CUDA(cudaFuncSetAttribute(vet::k_transition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(tile_bytes + 64)));
+      vet::k_transition<false><<<nb, 512, tile_bytes + 64, st>>>(a, h->maxT);
+    }
+    h->launches++;
+    VET_CUDA(cudaGetLastError());
+    if (nf == F - f0) break;
+  }
+  return VET_OK;
+}
+
+extern "C" int vet_poll_flags(vet_handle* h, void* stream, uint32_t* flags) {
+  if (!h || !flags) return fail(VET_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  VET_CUDA(cudaMemcpyAsync(flags, h->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  VET_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(uint32_t), st));
+  VET_CUDA(cudaStreamSynchronize(st));
+  return VET_OK;
+}
+
+// ---- host-buffer variants ---------------------------------------------------------
+
+namespace {
+
+// frames per host batch: about 256 MiB of packed input per copy
+int64_t host_batch_frames(int64_t F, int64_t U, size_t esz) {
+  const size_t per_frame = (size_t)U * 3 * esz;
+  return std::min<int64_t>(F, std::max<int64_t>(2, (int64_t)(((size_t)256 << 20) / std::max<size_t>(per_frame, 1))));
+}
+
+}  // namespace
+
+extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U,
+                                double* entropy_host, double* per_k_host, double* hist0_host, uint16_t* assign0_host) {
+  if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (F == 0) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");
+  if (!packed_host || !entropy_host) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  DeviceGuard guard(h->device);
+  const size_t esz = dtype == VET_F32 ? 4 : 8;
+  const int64_t fb = host_batch_frames(F, U, esz);
+  const size_t in_bytes = (size_t)fb * U * 3 * esz;
+  if (h->in_bytes < in_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (h->d_in[i]) VET_CUDA(cudaFree(h->d_in[i]));
+      h->d_in[i] = nullptr;
+    }
+    h->in_bytes = 0;
+    for (int i = 0; i < 2; ++i) VET_CUDA(cudaMalloc(&h->d_in[i], in_bytes));
+    h->in_bytes = in_bytes;
+  }
+  const int T0 = h->ts[0].T;
+  double *d_ent = nullptr, *d_perk = nullptr, *d_hist = nullptr;
+  uint16_t* d_assign[2] = {nullptr, nullptr};
+  VET_CUDA(cudaMalloc((void**)&d_ent, (size_t)F * 8));
+  if (per_k_host) VET_CUDA(cudaMalloc((void**)&d_perk, (size_t)F * h->K * 8));
+  if (hist0_host) VET_CUDA(cudaMalloc((void**)&d_hist, (size_t)F * T0 * 8));
+  if (assign0_host)
+    for (int i = 0; i < 2; ++i) VET_CUDA(cudaMalloc((void**)&d_assign[i], (size_t)fb * U * 2));
+  cudaEvent_t in_done[2], buf_free[2];
+  for (int i = 0; i < 2; ++i) {
+    VET_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+    VET_CUDA(cudaEventCreateWithFlags(&buf_free[i], cudaEventDisableTiming));
+  }
+  int rc = VET_OK;
+  int b = 0;
+  for (int64_t f0 = 0; f0 < F && rc == VET_OK; f0 += fb, b ^= 1) {
+    const int64_t nf = std::min(fb, F - f0);
+    // copy stream: wait until the kernels that read this buffer two batches ago are done
+    cudaStreamWaitEvent(h->s_copy, buf_free[b], 0);
+    cudaMemcpyAsync(h->d_in[b], (const char*)packed_host + (size_t)f0 * U * 3 * esz, (size_t)nf * U * 3 * esz,
+                    cudaMemcpyHostToDevice, h->s_copy);
+    cudaEventRecord(in_done[b], h->s_copy);
+    cudaStreamWaitEvent(h->s_exec, in_done[b], 0);
+    // per_k is laid out [K,F] on the device; rows are filled batch by batch
+    {
+      const int64_t fbs = frames_per_batch(h, nf, U, false);
+      rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fbs * h->C * 4);
+      for (int64_t g0 = 0; g0 < nf && rc == VET_OK; g0 += fbs) {
+        const int64_t ng = std::min(fbs, nf - g0);
+        const char* in = (const char*)h->d_in[b] + (size_t)g0 * U * 3 * esz;
+        rc = launch_stream(h, in, dtype, ng, U, d_assign[b] ? d_assign[b] + g0 * U : nullptr, false, h->s_exec);
+        if (rc == VET_OK)
+          rc = launch_epilogue(h, ng, d_ent + f0 + g0, d_perk ? d_perk + f0 + g0 : nullptr, F,
+                               d_hist ? d_hist + (f0 + g0) * T0 : nullptr, h->s_exec);
+      }
+    }
+    if (rc == VET_OK && assign0_host)
+      cudaMemcpyAsync(assign0_host + f0 * U, d_assign[b], (size_t)nf * U * 2, cudaMemcpyDeviceToHost, h->s_exec);
+    cudaEventRecord(buf_free[b], h->s_exec);
+  }
+  if (rc == VET_OK) {
+    cudaMemcpyAsync(entropy_host, d_ent, (size_t)F * 8, cudaMemcpyDeviceToHost, h->s_exec);
+    if (per_k_host) cudaMemcpyAsync(per_k_host, d_perk, (size_t)F * h->K * 8, cudaMemcpyDeviceToHost, h->s_exec);
+    if (hist0_host) cudaMemcpyAsync(hist0_host, d_hist, (size_t)F * T0 * 8, cudaMemcpyDeviceToHost, h->s_exec);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(h->s_copy), e2 = cudaStreamSynchronize(h->s_exec);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(in_done[i]);
+    cudaEventDestroy(buf_free[i]);
+    cudaFree(d_assign[i]);
+  }
+  cudaFree(d_ent);
+  cudaFree(d_perk);
+  cudaFree(d_hist);
+  if (rc != VET_OK) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess)
+    return fail(VET_ERR_CUDA, "host-buffer pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  return VET_OK;
+}
+
+extern "C" int vet_transition_host(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U,
+                                   double* entropy_host, double* per_k_host, int32_t* prev_count0_host,
+                                   uint16_t* pairs0_host, int mode) {
+  if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (F <= 1) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");
+  if (!packed_host || !entropy_host) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  DeviceGuard guard(h->device);
+  const size_t esz = dtype == VET_F32 ? 4 : 8;
+  const int T0 = h->ts[0].T;
+  void* d_in = nullptr;
+  double *d_ent = nullptr, *d_perk = nullptr;
+  int32_t* d_pc = nullptr;
+  uint16_t* d_pairs = nullptr;
+  const size_t in_bytes = (size_t)F * U * 3 * esz;
+  VET_CUDA(cudaMalloc(&d_in, in_bytes));
+  VET_CUDA(cudaMalloc((void**)&d_ent, (size_t)(F - 1) * 8));
+  if (per_k_host) VET_CUDA(cudaMalloc((void**)&d_perk, (size_t)(F - 1) * h->K * 8));
+  if (prev_count0_host) VET_CUDA(cudaMalloc((void**)&d_pc, (size_t)(F - 1) * T0 * 4));
+  if (pairs0_host) VET_CUDA(cudaMalloc((void**)&d_pairs, (size_t)(F - 1) * U * 4));
+  cudaMemcpyAsync(d_in, packed_host, in_bytes, cudaMemcpyHostToDevice, h->s_exec);
+  int rc = vet_transition(h, d_in, dtype, F, U, d_ent, d_perk, d_pc, d_pairs, mode, h->s_exec);
+  if (rc == VET_OK) {
+    cudaMemcpyAsync(entropy_host, d_ent, (size_t)(F - 1) * 8, cudaMemcpyDeviceToHost, h->s_exec);
+    if (per_k_host) cudaMemcpyAsync(per_k_host, d_perk, (size_t)(F - 1) * h->K * 8, cudaMemcpyDeviceToHost, h->s_exec);
+    if (prev_count0_host)
+      cudaMemcpyAsync(prev_count0_host, d_pc, (size_t)(F - 1) * T0 * 4, cudaMemcpyDeviceToHost, h->s_exec);
+    if (pairs0_host) cudaMemcpyAsync(pairs0_host, d_pairs, (size_t)(F - 1) * U * 4, cudaMemcpyDeviceToHost, h->s_exec);
+  }
+  cudaError_t e = cudaStreamSynchronize(h->s_exec);
+  cudaFree(d_in);
+  cudaFree(d_ent);
+  cudaFree(d_perk);
+  cudaFree(d_pc);
+  cudaFree(d_pairs);
+  if (rc != VET_OK) return rc;
+  if (e != cudaSuccess) return fail(VET_ERR_CUDA, "host-buffer pipeline failed: %s", cudaGetErrorString(e));
+  return VET_OK;
+}

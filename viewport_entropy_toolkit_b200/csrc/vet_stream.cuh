@@ -1,0 +1,165 @@
+// Streaming kernels: packed samples -> per-frame cell histogram (+ tile assignment,
+// + cell ids), and the per-frame epilogue cell histogram -> tile histograms ->
+// normalised entropy (north_star stages 1-3 in the table regime: every sample is
+// one of (W+1)(H+1) cells, so all per-tile work is done per CELL, not per sample).
+#pragma once
+#include "vet_common.cuh"
+
+namespace vet {
+
+struct StreamArgs {
+  const void* packed;   // [F,U,3]
+  int64_t F, U;
+  int W, H, C;
+  const uint16_t* lut0; // [C] nearest tile of tile_counts[0]
+  uint16_t* assign0;    // [F,U] or null
+  uint16_t* cell16;     // [F,U] or null (cell ids for the transition stage, C <= 65535)
+  int32_t* cell32;      // [F,U] or null (same, any C)
+  uint32_t* cnt;        // [F,C] per-frame cell histogram
+  int chunks_per_frame; // >1: cnt is pre-zeroed and flushed with atomics
+  int64_t chunk_users;
+  uint32_t* flags;
+};
+
+// Baseline streaming kernel: one (frame, user-chunk) per block iteration, one
+// sample per thread iteration, shared-memory privatised cell histogram.
+template <typename TIN>
+__global__ void __launch_bounds__(1024, 1) k_stream_simple(StreamArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
+  uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_hist + a.C);
+  const TIN* __restrict__ packed = static_cast<const TIN*>(a.packed);
+  const float Wf = (float)a.W, Hf = (float)a.H;
+  const bool want_assign = a.assign0 != nullptr;
+  if (want_assign)
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_lut[c] = a.lut0[c];
+  const int64_t items = a.F * a.chunks_per_frame;
+  uint32_t bad = 0;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t f = item / a.chunks_per_frame;
+    const int64_t u0 = (item % a.chunks_per_frame) * a.chunk_users;
+    const int64_t u1 = min(a.U, u0 + a.chunk_users);
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_hist[c] = 0u;
+    __syncthreads();
+    const int64_t base = f * a.U;
+    for (int64_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
+      const TIN mu = packed[3 * (base + u) + 1];
+      const TIN mv = packed[3 * (base + u) + 2];
+      int cell;
+      const int st = decode_cell(mu, mv, Wf, Hf, a.W, a.H, cell);
+      if (st == kOk) atomicAdd(&s_hist[cell], 1u);
+      if (st == kOutOfRange) bad = 1;
+      if (want_assign) a.assign0[base + u] = (st == kOk) ? s_lut[cell] : (uint16_t)VET_MISSING;
+      if (a.cell16) a.cell16[base + u] = (st == kOk) ? (uint16_t)cell : (uint16_t)0xFFFF;
+      if (a.cell32) a.cell32[base + u] = cell;
+    }
+    __syncthreads();
+    uint32_t* __restrict__ row = a.cnt + f * (int64_t)a.C;
+    if (a.chunks_per_frame == 1) {
+      for (int c = threadIdx.x; c < a.C; c += blockDim.x) row[c] = s_hist[c];
+    } else {
+      for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        const uint32_t v = s_hist[c];
+        if (v) atomicAdd(&row[c], v);
+      }
+    }
+    __syncthreads();
+  }
+  if (bad) atomicOr(a.flags, (uint32_t)VET_FLAG_OUT_OF_RANGE);
+}
+
+struct TileSetDev {
+  int T;
+  const uint16_t* lut;       // [C]
+  const uint32_t* col_ptr;   // [T+1]  (weighted only)
+  const uint32_t* cell_idx;  // [nnz]
+  const double* w_val;       // [nnz]
+};
+
+constexpr int kMaxTileCounts = 16;
+
+struct EpilogueArgs {
+  const uint32_t* cnt;  // [F,C]
+  int64_t F;
+  int C;
+  int K;
+  int use_weight;
+  TileSetDev ts[kMaxTileCounts];
+  double* entropy;  // [F]
+  double* per_k;    // [K, per_k_stride] or null
+  int64_t per_k_stride;
+  double* hist0;    // [F,T0] or null
+  uint32_t* flags;
+};
+
+// Per-frame epilogue.  One block per frame (grid-stride).  The frame's cell
+// histogram is staged in shared memory; for every tile count the tile histogram is
+//   unweighted: hist[t] = sum of cnt[cell] over cells whose nearest tile is t
+//               (integer, exact, order-free)                              EU:139-142
+//   weighted:   hist[t] = sum_cell cnt[cell] * w(cell,t) as a gather over tile t's
+//               column of the weight table, one warp per tile, fixed summation
+//               order (deterministic)                                     EU:130-138,190-192
+// then EU:195-209 gives the normalised entropy; SA:156 averages over tile counts.
+__global__ void __launch_bounds__(512, 1) k_epilogue(EpilogueArgs a, int maxT) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw);
+  double* s_hist = reinterpret_cast<double*>(smem_raw + (((size_t)a.C * 4 + 15) & ~(size_t)15));
+  uint32_t* s_ihist = reinterpret_cast<uint32_t*>(s_hist + maxT);
+  __shared__ double s_red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int64_t f = blockIdx.x; f < a.F; f += gridDim.x) {
+    const uint32_t* __restrict__ row = a.cnt + f * (int64_t)a.C;
+    unsigned long long nloc = 0;
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      const uint32_t v = row[c];
+      s_cnt[c] = v;
+      nloc += v;
+    }
+    const double n_valid = block_sum((double)nloc, s_red);  // exact: integers < 2^53
+    if (n_valid == 0.0 && threadIdx.x == 0) atomicOr(a.flags, (uint32_t)VET_FLAG_EMPTY_FRAME);
+    double esum = 0.0;
+    for (int k = 0; k < a.K; ++k) {
+      const TileSetDev ts = a.ts[k];
+      const int T = ts.T;
+      double total;
+      if (!a.use_weight) {
+        for (int t = threadIdx.x; t < T; t += blockDim.x) s_ihist[t] = 0u;
+        __syncthreads();
+        for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+          const uint32_t v = s_cnt[c];
+          if (v) atomicAdd(&s_ihist[ts.lut[c]], v);
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < T; t += blockDim.x) s_hist[t] = (double)s_ihist[t];
+        total = n_valid;
+        __syncthreads();
+      } else {
+        for (int t = wid; t < T; t += nw) {
+          const uint32_t j0 = ts.col_ptr[t], j1 = ts.col_ptr[t + 1];
+          double acc = 0.0;
+          for (uint32_t j = j0 + lane; j < j1; j += 32) {
+            const uint32_t v = s_cnt[ts.cell_idx[j]];
+            acc = fma((double)v, ts.w_val[j], acc);
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) s_hist[t] = acc;
+        }
+        __syncthreads();
+        double part = 0.0;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) part += s_hist[t];
+        total = block_sum(part, s_red);
+      }
+      double e = normalized_entropy(s_hist, T, total, a.use_weight != 0, s_red);
+      if (n_valid == 0.0) e = __longlong_as_double(0x7ff8000000000000LL);
+      if (threadIdx.x == 0 && a.per_k) a.per_k[k * a.per_k_stride + f] = e;
+      if (k == 0 && a.hist0)
+        for (int t = threadIdx.x; t < T; t += blockDim.x) a.hist0[f * (int64_t)T + t] = s_hist[t];
+      esum += e;  // SA:151: sequential accumulation over tile counts
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) a.entropy[f] = esum / (double)a.K;  // SA:156
+    __syncthreads();
+  }
+}
+
+}  // namespace vet

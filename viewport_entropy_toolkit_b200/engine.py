@@ -1,0 +1,313 @@
+"""Device engine: owns one native handle per (device, configuration) and exposes
+the tensor-level API of the hot path.
+
+    packed[F, U, 3] = (time, 2dmu, 2dmv)  ->  entropy[F], hist0[F, T0], assign0[F, U]
+
+PyTorch is used for device memory and streams only; all compute happens in
+libvet_b200.so through the C ABI (include/vet_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import _tables
+from .config import EntropyConfig
+from .data_types import SpatialError, ValidationError
+
+
+class UnsupportedConfigurationError(SpatialError):
+    """The configuration is valid for the reference but outside what the device
+    tables of this build can hold."""
+
+
+@dataclass
+class SpatialResult:
+    """Outputs of SpatialEntropyAnalyzer.compute_entropy (SA:107-164) as tensors."""
+    entropy: torch.Tensor            # [F] float64, mean over tile counts
+    per_k: Optional[torch.Tensor]    # [K, F] float64
+    hist0: Optional[torch.Tensor]    # [F, T0] float64 tile weights of tile_counts[0]
+    assign0: Optional[torch.Tensor]  # [F, U] uint16 nearest tile of tile_counts[0] (0xFFFF = missing)
+
+
+@dataclass
+class TransitionResult:
+    """Outputs of TransitionEntropyAnalyzer.compute_entropy (TA:107-175) as tensors."""
+    entropy: torch.Tensor                # [F-1] float64
+    per_k: Optional[torch.Tensor]        # [K, F-1]
+    prev_count0: Optional[torch.Tensor]  # [F-1, T0] int32
+    pairs0: Optional[torch.Tensor]       # [F-1, U, 2] uint16
+
+
+def _check(rc: int) -> None:
+    if rc == N.VET_OK:
+        return
+    msg = N.last_error()
+    if rc == N.VET_ERR_INVALID_ARG:
+        raise ValidationError(msg)
+    if rc == N.VET_ERR_UNSUPPORTED:
+        raise UnsupportedConfigurationError(msg)
+    if rc == N.VET_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """One native handle.  Not thread-safe per instance; use one per thread/stream."""
+
+    def __init__(self, video_width: int, video_height: int, tile_counts: Sequence[int],
+                 entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None):
+        self._h = None
+        lib = N.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("viewport_entropy_toolkit_b200 needs a CUDA device; there is no CPU path")
+        ec = entropy_config or EntropyConfig()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("viewport_entropy_toolkit_b200 needs a CUDA device; there is no CPU path")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.video_width, self.video_height = int(video_width), int(video_height)
+        self.tile_counts = [int(c) for c in tile_counts]
+        self.entropy_config = ec
+        # DU:236-240 (the reference validates dims when the first sample is converted)
+        if self.video_width <= 0 or self.video_height <= 0:
+            raise ValidationError("Video dimensions must be positive")
+        if self.video_width % 2 or self.video_height % 2:
+            raise ValidationError("Video dimensions must be even numbers")
+        if not self.tile_counts or any(c <= 0 for c in self.tile_counts):
+            raise ValidationError("Tile counts must be positive")
+        K = len(self.tile_counts)
+        self._centres = [np.ascontiguousarray(_tables.fibonacci_lattice(c)) for c in self.tile_counts]
+        lon, lat = _tables.axis_tables(self.video_width, self.video_height)
+        tc = (C.c_int32 * K)(*self.tile_counts)
+        cptrs = (C.POINTER(C.c_double) * K)(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in self._centres])
+        cfg = N.VetConfig(
+            device=self.device.index, video_width=self.video_width, video_height=self.video_height,
+            num_tile_counts=K, tile_counts=tc, fov_angle=float(ec.fov_angle), power_factor=float(ec.power_factor),
+            use_weight_distribution=int(bool(ec.use_weight_distribution)), centres=cptrs,
+            lon_by_px=lon.ctypes.data_as(C.POINTER(C.c_double)), lat_by_py=lat.ctypes.data_as(C.POINTER(C.c_double)))
+        h = C.c_void_p()
+        _check(lib.vet_create(C.byref(h), C.byref(cfg)))
+        self._h = h
+        self._lib = lib
+        self.num_tiles = [lib.vet_num_tiles(h, k) for k in range(K)]
+        self.num_cells = int(lib.vet_num_cells(h))
+
+    # -- lifetime ---------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.vet_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _packed(self, packed: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        if not isinstance(packed, torch.Tensor):
+            raise TypeError("packed must be a torch.Tensor on the engine's device")
+        if packed.device != self.device:
+            raise ValueError(f"packed is on {packed.device}, engine on {self.device}")
+        if packed.dtype not in (torch.float32, torch.float64):
+            raise TypeError("packed must be float32 or float64")
+        if packed.shape[-1] != 3:
+            raise ValueError("packed must have shape [..., 3] = (time, 2dmu, 2dmv)")
+        return packed.contiguous(), (N.VET_F32 if packed.dtype == torch.float32 else N.VET_F64)
+
+    def launch_count(self) -> int:
+        return int(self._lib.vet_launch_count(self._h))
+
+    def poll_flags(self) -> int:
+        """Synchronises the current stream and returns (and clears) the sticky
+        device flag word."""
+        flags = C.c_uint32(0)
+        _check(self._lib.vet_poll_flags(self._h, self._stream(), C.byref(flags)))
+        return int(flags.value)
+
+    def raise_for_flags(self) -> None:
+        """Raises what the reference would have raised for the data it was given."""
+        flags = self.poll_flags()
+        if flags & N.VET_FLAG_OUT_OF_RANGE:
+            raise ValidationError("Normalized coordinates must be between 0 and 1")  # DU:256-257
+        if flags & N.VET_FLAG_EMPTY_FRAME:
+            raise ValidationError("Empty vector dictionary")  # EU:168-169
+        if flags & N.VET_FLAG_NO_COMMON_USER:
+            raise ZeroDivisionError("division by zero")  # EU:326
+
+    # -- tables -------------------------------------------------------------------
+    def lattice(self, k: int = 0) -> np.ndarray:
+        """generate_fibonacci_lattice(tile_counts[k]) as [T,3] float64 (DU:25-56)."""
+        out = np.empty((self.num_tiles[k], 3), dtype=np.float64)
+        _check(self._lib.vet_lattice(self._h, k, out.ctypes.data))
+        return out
+
+    def cell_lut(self, k: int = 0) -> np.ndarray:
+        """Nearest tile of every reachable cell, [(H+1), (W+1)] uint16."""
+        out = np.empty(self.num_cells, dtype=np.uint16)
+        _check(self._lib.vet_cell_lut(self._h, k, out.ctypes.data))
+        return out.reshape(self.video_height + 1, self.video_width + 1)
+
+    # -- stage 1 / 2 ------------------------------------------------------------------
+    def decode(self, packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """packed[..., 3] -> (vectors[..., 3] float64, cell[...] int32).  Missing or
+        out-of-range samples give NaN vectors and cell -1."""
+        p, dt = self._packed(packed)
+        n = p.numel() // 3
+        vec = torch.empty(p.shape, dtype=torch.float64, device=self.device)
+        cell = torch.empty(p.shape[:-1], dtype=torch.int32, device=self.device)
+        _check(self._lib.vet_decode(self._h, p.data_ptr(), dt, n, vec.data_ptr(), cell.data_ptr(), self._stream()))
+        return vec, cell
+
+    def nearest_tile(self, vectors: torch.Tensor, k: int = 0) -> torch.Tensor:
+        """find_nearest_tile (EU:89-106) for vectors[..., 3] float64 -> int32[...]."""
+        v = vectors.to(device=self.device, dtype=torch.float64).contiguous()
+        n = v.numel() // 3
+        idx = torch.empty(v.shape[:-1], dtype=torch.int32, device=self.device)
+        _check(self._lib.vet_nearest_tile(self._h, k, v.data_ptr(), n, idx.data_ptr(), self._stream()))
+        return idx
+
+    def tile_weights(self, vectors: torch.Tensor, k: int = 0) -> torch.Tensor:
+        """calculate_tile_weights (EU:108-144) as dense rows [..., T_k] float64."""
+        v = vectors.to(device=self.device, dtype=torch.float64).contiguous()
+        n = v.numel() // 3
+        w = torch.empty(v.shape[:-1] + (self.num_tiles[k],), dtype=torch.float64, device=self.device)
+        _check(self._lib.vet_tile_weights(self._h, k, v.data_ptr(), n, w.data_ptr(), self._stream()))
+        return w
+
+    # -- stages 1-3 fused -----------------------------------------------------------
+    def spatial(self, packed: torch.Tensor, want_per_k: bool = True, want_hist0: bool = True,
+                want_assign0: bool = True, out: Optional[SpatialResult] = None) -> SpatialResult:
+        p, dt = self._packed(packed)
+        if p.dim() != 3:
+            raise ValueError("packed must be [F, U, 3]")
+        F, U = int(p.shape[0]), int(p.shape[1])
+        K, T0 = len(self.tile_counts), self.num_tiles[0]
+        if out is None:
+            dev = self.device
+            out = SpatialResult(
+                entropy=torch.empty(F, dtype=torch.float64, device=dev),
+                per_k=torch.empty((K, F), dtype=torch.float64, device=dev) if want_per_k else None,
+                hist0=torch.empty((F, T0), dtype=torch.float64, device=dev) if want_hist0 else None,
+                assign0=torch.empty((F, U), dtype=torch.uint16, device=dev) if want_assign0 else None)
+        _check(self._lib.vet_spatial(self._h, p.data_ptr(), dt, F, U, out.entropy.data_ptr(), _ptr(out.per_k),
+                                     _ptr(out.hist0), _ptr(out.assign0), self._stream()))
+        return out
+
+    # -- stage 4 ---------------------------------------------------------------------
+    def transition(self, packed: torch.Tensor, mode: str = "literal", want_per_k: bool = True,
+                   want_prev_count0: bool = True, want_pairs0: bool = True,
+                   out: Optional[TransitionResult] = None) -> TransitionResult:
+        p, dt = self._packed(packed)
+        if p.dim() != 3:
+            raise ValueError("packed must be [F, U, 3]")
+        if mode not in ("literal", "textbook"):
+            raise ValueError("mode must be 'literal' or 'textbook'")
+        F, U = int(p.shape[0]), int(p.shape[1])
+        R = max(F - 1, 0)
+        K, T0 = len(self.tile_counts), self.num_tiles[0]
+        if out is None:
+            dev = self.device
+            out = TransitionResult(
+                entropy=torch.empty(R, dtype=torch.float64, device=dev),
+                per_k=torch.empty((K, R), dtype=torch.float64, device=dev) if want_per_k else None,
+                prev_count0=torch.empty((R, T0), dtype=torch.int32, device=dev) if want_prev_count0 else None,
+                pairs0=torch.empty((R, U, 2), dtype=torch.uint16, device=dev) if want_pairs0 else None)
+        m = N.VET_TRANSITION_LITERAL if mode == "literal" else N.VET_TRANSITION_TEXTBOOK
+        _check(self._lib.vet_transition(self._h, p.data_ptr(), dt, F, U, out.entropy.data_ptr(), _ptr(out.per_k),
+                                        _ptr(out.prev_count0), _ptr(out.pairs0), m, self._stream()))
+        return out
+
+    # -- host-buffer (numpy) variants -----------------------------------------------------
+    def spatial_host(self, packed: np.ndarray, want_per_k: bool = True, want_hist0: bool = True,
+                     want_assign0: bool = True) -> Dict[str, Optional[np.ndarray]]:
+        """numpy (or pinned torch CPU tensor) in, numpy out; the H2D/D2H copies are
+        pipelined inside the library (vet_spatial_host)."""
+        arr, dt, F, U = _host_packed(packed)
+        K, T0 = len(self.tile_counts), self.num_tiles[0]
+        ent = np.empty(F, dtype=np.float64)
+        per_k = np.empty((K, F), dtype=np.float64) if want_per_k else None
+        hist0 = np.empty((F, T0), dtype=np.float64) if want_hist0 else None
+        assign0 = np.empty((F, U), dtype=np.uint16) if want_assign0 else None
+        _check(self._lib.vet_spatial_host(self._h, _host_ptr(arr), dt, F, U, ent.ctypes.data, _np_ptr(per_k),
+                                          _np_ptr(hist0), _np_ptr(assign0)))
+        return dict(entropy=ent, per_k=per_k, hist0=hist0, assign0=assign0)
+
+    def transition_host(self, packed: np.ndarray, mode: str = "literal", want_per_k: bool = True,
+                        want_prev_count0: bool = True, want_pairs0: bool = True) -> Dict[str, Optional[np.ndarray]]:
+        arr, dt, F, U = _host_packed(packed)
+        R = max(F - 1, 0)
+        K, T0 = len(self.tile_counts), self.num_tiles[0]
+        ent = np.empty(R, dtype=np.float64)
+        per_k = np.empty((K, R), dtype=np.float64) if want_per_k else None
+        pc = np.empty((R, T0), dtype=np.int32) if want_prev_count0 else None
+        pairs = np.empty((R, U, 2), dtype=np.uint16) if want_pairs0 else None
+        m = N.VET_TRANSITION_LITERAL if mode == "literal" else N.VET_TRANSITION_TEXTBOOK
+        _check(self._lib.vet_transition_host(self._h, _host_ptr(arr), dt, F, U, ent.ctypes.data, _np_ptr(per_k),
+                                             _np_ptr(pc), _np_ptr(pairs), m))
+        return dict(entropy=ent, per_k=per_k, prev_count0=pc, pairs0=pairs)
+
+
+def _np_ptr(a: Optional[np.ndarray]) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+def _host_packed(packed):
+    if isinstance(packed, torch.Tensor):
+        if packed.device.type != "cpu":
+            raise ValueError("spatial_host/transition_host take host memory; use spatial()/transition() for device tensors")
+        arr = packed.contiguous()
+        dtype = {torch.float32: N.VET_F32, torch.float64: N.VET_F64}.get(arr.dtype)
+    else:
+        arr = np.ascontiguousarray(packed)
+        dtype = {np.dtype(np.float32): N.VET_F32, np.dtype(np.float64): N.VET_F64}.get(arr.dtype)
+    if dtype is None:
+        raise TypeError("packed must be float32 or float64")
+    if arr.ndim != 3 or arr.shape[-1] != 3:
+        raise ValueError("packed must be [F, U, 3]")
+    return arr, dtype, int(arr.shape[0]), int(arr.shape[1])
+
+
+def _host_ptr(arr) -> int:
+    return arr.data_ptr() if isinstance(arr, torch.Tensor) else arr.ctypes.data
+
+
+_ENGINES: Dict[tuple, Engine] = {}
+
+
+def get_engine(video_width: int, video_height: int, tile_counts: Sequence[int],
+               entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None) -> Engine:
+    """Engine cache keyed by (device, configuration): building the tables costs a
+    few milliseconds, analyzers and the functional API share them."""
+    ec = entropy_config or EntropyConfig()
+    if not torch.cuda.is_available():
+        raise RuntimeError("viewport_entropy_toolkit_b200 needs a CUDA device; there is no CPU path")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, int(video_width), int(video_height), tuple(int(c) for c in tile_counts), float(ec.fov_angle),
+           bool(ec.use_weight_distribution), float(ec.power_factor))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = Engine(video_width, video_height, tile_counts, ec, torch.device("cuda", idx))
+        _ENGINES[key] = eng
+    return eng
+
+
+def clear_engines() -> None:
+    for e in _ENGINES.values():
+        e.close()
+    _ENGINES.clear()
