@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the viewport-entropy hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c5shard|...]
+    python bench.py --impl reference ...     # CPU arm: the oracle port on host cores
+
+A "step" is one pass of the hot path (decode -> cell histogram -> FOV-weighted tile
+histogram -> per-frame entropy, + tile assignment output) over one synthetic batch.
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "user-frame samples/sec (bin+weighted entropy, 200 tiles)"
+UNIT = "samples/s"
+ALG_BYTES_PER_SAMPLE = 14  # 12 B packed (time,2dmu,2dmv) read + 2 B uint16 tile assignment written
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on (fits one GPU)
+    "c3": dict(F=3600, U=100_000, tile_counts=[200], fov=90.0, pf=2.0, use_w=True,
+               desc="configs[2]: synthetic 100k users x 3600 frames, 200 tiles, FOV-weighted (fov=90, pf=2)"),
+    "c2": dict(F=1800, U=10_000, tile_counts=[20, 50, 100, 200], fov=120.0, pf=2.0, use_w=False,
+               desc="configs[1]: synthetic 10k users x 1800 frames, tile_counts=[20,50,100,200], unweighted"),
+    # one rank's share of configs[4] (1M users x 3600 frames over 8 GPUs)
+    "c5shard": dict(F=450, U=1_000_000, tile_counts=[200], fov=90.0, pf=2.0, use_w=True,
+                    desc="configs[4] shard: 1M users x 450 frames per GPU, 200 tiles, FOV-weighted"),
+    "tiny": dict(F=64, U=20_000, tile_counts=[200], fov=90.0, pf=2.0, use_w=True, desc="debug size"),
+}
+
+
+def synth_on_device(torch, F, U, seed, device, chunk=256):
+    """Seeded 'realistic' trajectories: gaussian start, per-frame random-walk
+    steps N(0,0.010)/N(0,0.006), reflected into [0,1]; generated on the device in frame
+    chunks.  Returns packed[F,U,3] float32 = (time, 2dmu, 2dmv)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    packed = torch.empty((F, U, 3), dtype=torch.float32, device=device)
+    mu = (torch.randn(U, generator=g, device=device) * 0.15 + 0.5).clamp_(0, 1)
+    mv = (torch.randn(U, generator=g, device=device) * 0.10 + 0.5).clamp_(0, 1)
+
+    def reflect(x):
+        x = x.abs()
+        x = torch.where(x > 1, 2 - x, x)
+        return x.clamp_(0, 1)
+
+    for f0 in range(0, F, chunk):
+        n = min(chunk, F - f0)
+        su = torch.randn((n, U), generator=g, device=device) * 0.010
+        sv = torch.randn((n, U), generator=g, device=device) * 0.006
+        if f0 == 0:
+            su[0] = 0
+            sv[0] = 0
+        pu = reflect(mu[None] + torch.cumsum(su, 0))
+        pv = reflect(mv[None] + torch.cumsum(sv, 0))
+        packed[f0:f0 + n, :, 0] = (torch.arange(f0, f0 + n, device=device, dtype=torch.float32) * 0.1)[:, None]
+        packed[f0:f0 + n, :, 1] = pu
+        packed[f0:f0 + n, :, 2] = pv
+        mu, mv = pu[-1].clone(), pv[-1].clone()
+    edge = [(0.5, 0.5), (0.0, 0.5), (1.0, 0.5), (1.0, 1.0), (0.29, 0.57), (0.999, 0.001), (0.123456, 0.654321), (0.75, 0.25)]
+    for u, (a, b) in enumerate(edge[:U]):
+        packed[0, u, 1] = a
+        packed[0, u, 2] = b
+    return packed
+
+
+def synth_numpy(F, U, seed):
+    """Same distribution, numpy, for the bounded CPU samples."""
+    rng = np.random.default_rng(seed)
+    mu = np.clip(rng.normal(0.5, 0.15, U), 0, 1)[None] + np.cumsum(rng.normal(0, 0.010, (F, U)), 0)
+    mv = np.clip(rng.normal(0.5, 0.10, U), 0, 1)[None] + np.cumsum(rng.normal(0, 0.006, (F, U)), 0)
+    for a in (mu, mv):
+        np.abs(a, out=a)
+        a[a > 1] = 2 - a[a > 1]
+        np.clip(a, 0, 1, out=a)
+    t = np.broadcast_to((np.arange(F) * 0.1)[:, None], (F, U))
+    return np.stack([t, mu, mv], -1).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------
+# CPU arm: the oracle's literal (reference-shaped) layer on host cores
+# ------------------------------------------------------------------------------------
+def _cpu_frame(args):
+    frame, W, H, tile_counts, fov, use_w, pf = args
+    from oracle import vet_oracle as orc
+    vecs, ok = orc.decode_vectors(frame[:, 1], frame[:, 2], W, H)
+    d = {f"u{u}": tuple(vecs[u]) for u in range(len(vecs)) if ok[u]}
+    tot = 0
+    for n in tile_counts:
+        e, _, _ = orc.compute_spatial_entropy_literal(d, orc.lattice(n), fov, use_w, pf)
+        tot += e
+    return tot / len(tile_counts)
+
+
+def cpu_rate(wl, frames, users, cores, seed=20262000, pool=None):
+    """samples/s of the literal oracle port on `frames` x `users` of the workload."""
+    import multiprocessing as mp
+    sample = synth_numpy(frames, users, seed)
+    jobs = [(sample[f], 100, 200, wl["tile_counts"], wl["fov"], wl["use_w"], wl["pf"]) for f in range(frames)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        for j in jobs:
+            _cpu_frame(j)
+    else:
+        own = pool is None
+        pool = pool or mp.get_context("fork").Pool(cores)
+        pool.map(_cpu_frame, jobs, chunksize=1)
+        if own:
+            pool.close()
+    dt = time.perf_counter() - t0
+    return frames * users / dt, dt
+
+
+def run_reference_arm(args, wl, rank):
+    """`--impl reference`: the reference is pure Python and cannot travel to the GPU box;
+    its algorithm is timed through the oracle's literal layer (same scalar call structure:
+    one numpy-scalar arccos per (user, tile), twice per user, EU:147-211) on every host core."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    users, frames = 32, 2 * cores
+    pool = mp.get_context("fork").Pool(cores)
+    for _ in range(args.warmup):
+        cpu_rate(wl, frames, users, cores, pool=pool)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_rate(wl, frames, users, cores, seed=20262000 + s, pool=pool)
+    dt = time.perf_counter() - t0
+    pool.close()
+    value = args.steps * frames * users / dt
+    sample = f"{frames} frames x {users} users per step of the {args.workload} workload, literal oracle port, {cores} processes"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "tile_counts": wl["tile_counts"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--transition", action="store_true", help="also run the transition stage inside the step")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    from viewport_entropy_toolkit_b200 import EntropyConfig, get_engine
+    from viewport_entropy_toolkit_b200.engine import SpatialResult
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    F, U = wl["F"], wl["U"]
+    # weak scaling: every rank owns a full shard of the workload shape (its own frame range)
+    packed = synth_on_device(torch, F, U, 20260000 + 3000 + rank, device)
+    ec = EntropyConfig(fov_angle=wl["fov"], use_weight_distribution=wl["use_w"], power_factor=wl["pf"])
+    eng = get_engine(100, 200, wl["tile_counts"], ec, device)
+    K, T0 = len(wl["tile_counts"]), eng.num_tiles[0]
+    out = SpatialResult(entropy=torch.empty(F, dtype=torch.float64, device=device),
+                        per_k=None,
+                        hist0=torch.empty((F, T0), dtype=torch.float64, device=device),
+                        assign0=torch.empty((F, U), dtype=torch.uint16, device=device))
+    rows = torch.empty((F, 1 + T0), dtype=torch.float64, device=device)
+    gathered = torch.empty((world * F, 1 + T0), dtype=torch.float64, device=device) if world > 1 else None
+
+    def step():
+        eng.spatial(packed, out=out)
+        if args.transition:
+            eng.transition(packed, want_per_k=False, want_pairs0=False)
+        if world > 1:  # the path's only exchange: one all-gather of the per-frame result rows
+            rows[:, 0] = out.entropy
+            rows[:, 1:] = out.hist0
+            dist.all_gather_into_tensor(gathered, rows)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    flags = eng.poll_flags()
+    assert flags == 0, f"device flags {flags}"
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    eng.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    ms_per_step = ms_max / args.steps
+    samples_per_step = F * U * world
+    value = samples_per_step / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (device time of its own launches inside the timed region)
+    dom = max(("stream", "epilogue"), key=lambda k: prof[k][0])
+    k_ms, k_n = prof["stream"]
+    stream_ms = k_ms / max(k_n, 1)
+    launch_bytes = ALG_BYTES_PER_SAMPLE * F * U  # one launch of the streaming kernel covers the whole batch
+    achieved = launch_bytes / (stream_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": stream_ms, "launches": k_n,
+                "step_share": {k: prof[k][0] / ms for k in prof if prof[k][1]},
+                "whole_step_frac": (ALG_BYTES_PER_SAMPLE * F * U / (ms / args.steps * 1e-3) / 1e9) / peak_gbs,
+                "dominant_by_time": dom}
+
+    # end to end: host buffers in, host results out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((F, U, 3), dtype=torch.float32, pin_memory=True)
+        host.copy_(packed)
+        torch.cuda.synchronize()
+        eng.spatial_host(host, want_per_k=False)  # warm-up (allocates the staging buffers)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res = eng.spatial_host(host, want_per_k=False)
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt = float(t_e.item())
+        e2e = {"value": samples_per_step * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(host.numel() * 4),
+               "d2h_bytes_per_step": int(res["entropy"].nbytes + res["hist0"].nbytes + res["assign0"].nbytes),
+               "steps": args.e2e_steps, "api": "Engine.spatial_host (vet_spatial_host), pinned host input"}
+        del host
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate1, dt1 = cpu_rate(wl, 4, 64, 1)
+        cpu = {"value": rate1, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"4 frames x 64 users of the workload through the oracle's literal layer ({dt1:.1f} s)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "frames_per_gpu": F, "users": U, "tile_counts": wl["tile_counts"],
+                       "tiles": eng.num_tiles, "fov": wl["fov"], "power_factor": wl["pf"], "weighted": wl["use_w"],
+                       "video": "100x200", "input": "float32[F,U,3] resident in HBM", "outputs": "entropy[F], hist0[F,T0], assign0[F,U] u16",
+                       "l2": "input 4.32 GB per step >> 126 MB L2 (no flush needed)" if F * U * 12 > 2e9 else "input larger than L2" if F * U * 12 > 1.3e8 else "input smaller than L2",
+                       "transition": bool(args.transition), "sharding": "frames (one shard of the workload shape per rank), one all-gather of per-frame rows"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

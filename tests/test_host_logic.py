@@ -1,0 +1,191 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the
+host-side mirror of the reference API (configs, data types, ingest, tables) behaves
+like the reference.  No compute call is made (no GPU here)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import ROOT, group_keys, load_golden
+from oracle import vet_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as ge
+    ge.build()
+    import viewport_entropy_toolkit_b200 as p
+    return p
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from viewport_entropy_toolkit_b200 import _native
+    header = (ROOT / "include" / "vet_b200.h").read_text()
+    declared = set(re.findall(r"\b(vet_[a-z0-9_]+)\s*\(", header))
+    declared -= {"vet_handle", "vet_config", "vet_status"}
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    lib = _native.load_library()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.vet_version()
+    # argument validation happens before any CUDA call
+    h = ctypes.c_void_p()
+    assert lib.vet_create(ctypes.byref(h), None) == _native.VET_ERR_INVALID_ARG
+    cfg = _native.VetConfig(device=0, video_width=101, video_height=200, num_tile_counts=1,
+                            tile_counts=(ctypes.c_int32 * 1)(20), fov_angle=120.0, power_factor=2.0,
+                            use_weight_distribution=1)
+    assert lib.vet_create(ctypes.byref(h), ctypes.byref(cfg)) == _native.VET_ERR_INVALID_ARG
+    assert b"even" in lib.vet_last_error()
+    cfg.video_width = 100; cfg.fov_angle = 0.0
+    assert lib.vet_create(ctypes.byref(h), ctypes.byref(cfg)) == _native.VET_ERR_INVALID_ARG
+    assert b"FOV" in lib.vet_last_error()
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        pkg.Engine(100, 200, [20])
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        pkg.SpatialEntropyAnalyzer(pkg.AnalyzerConfig(output_dir=Path("/tmp/vet_t"))).engine
+
+
+def test_product_does_not_import_oracle():
+    for f in (ROOT / "viewport_entropy_toolkit_b200").rglob("*.py"):
+        src = f.read_text()
+        assert "oracle" not in src.replace("# oracle", ""), f
+    for f in (ROOT / "viewport_entropy_toolkit_b200" / "csrc").glob("*"):
+        assert "oracle" not in f.read_text(), f
+
+
+def test_reference_smoke_tests(pkg, tmp_path):
+    """The reference's own tests/test_core.py:10-44, against this package."""
+    p = pkg.Point(pixel_x=100, pixel_y=200)
+    assert (p.pixel_x, p.pixel_y) == (100, 200)
+    r = pkg.RadialPoint(lon=45.0, lat=30.0)
+    assert (r.lon, r.lat) == (45.0, 30.0)
+    v = pkg.Vector(x=1.0, y=2.0, z=3.0)
+    assert (v.x, v.y, v.z) == (1.0, 2.0, 3.0)
+    for cls in (pkg.SpatialEntropyAnalyzer, pkg.TransitionEntropyAnalyzer):
+        a = cls(config=pkg.AnalyzerConfig(video_width=100, video_height=200, output_dir=tmp_path))
+        assert a.config.video_width == 100 and a.config.video_height == 200
+
+
+def test_config_and_type_validation(pkg, tmp_path):
+    with pytest.raises(pkg.ValidationError):
+        pkg.EntropyConfig(fov_angle=361)
+    with pytest.raises(pkg.ValidationError):
+        pkg.EntropyConfig(power_factor=0)
+    with pytest.raises(ValueError):
+        pkg.AnalyzerConfig(video_width=0, output_dir=tmp_path)
+    with pytest.raises(ValueError):
+        pkg.AnalyzerConfig(tile_counts=[], output_dir=tmp_path)
+    with pytest.raises(ValueError):
+        pkg.AnalyzerConfig(tile_counts=[20, -1], output_dir=tmp_path)
+    with pytest.raises(TypeError):
+        pkg.AnalyzerConfig(use_weight_distribution=True)  # documented by the reference but not a field
+    out = tmp_path / "made" / "here"
+    cfg = pkg.AnalyzerConfig(output_dir=out)
+    assert out.is_dir() and cfg.tile_counts == [20, 50, 100, 250, 1000]
+    assert cfg.get_output_path("a", ".csv") == out / "a.csv"
+    with pytest.raises(pkg.ValidationError):
+        pkg.Point(-1, 0)
+    with pytest.raises(pkg.ValidationError):
+        pkg.RadialPoint(181, 0)
+    with pytest.raises(pkg.ValidationError):
+        pkg.Vector(0, 0, 0)
+    assert pkg.Vector.from_spherical(-79.2, -11.7) == pkg.Vector(0.183488, -0.961878, -0.202787)
+    assert pkg.RadialPoint(190 - 360, 0).normalize_coordinates().lon == -170
+    assert issubclass(pkg.ValidationError, pkg.SpatialError)
+
+
+def test_host_tables_equal_oracle_and_reference(pkg):
+    from viewport_entropy_toolkit_b200 import _tables
+    g = load_golden("lattices")
+    for key in g.files:
+        assert np.array_equal(_tables.fibonacci_lattice(int(key[1:])), g[key])
+    d = load_golden("decode")
+    for (W, H) in [(100, 200), (200, 400), (1920, 1080), (3840, 1920)]:
+        lon, lat = _tables.axis_tables(W, H)
+        assert np.array_equal(lon, d[f"lon_{W}x{H}"]) and np.array_equal(lat, d[f"lat_{W}x{H}"])
+    lon, lat = _tables.axis_tables(100, 200)
+    assert np.array_equal(_tables.spherical_to_vector(lon[None, :], lat[:, None]), d["cellvec_100x200"])
+
+
+def _write_dir(tmp_path, files):
+    for name, (t, mu, mv) in files.items():
+        pd.DataFrame({"time": t, "2dmu": mu, "2dmv": mv}).to_csv(tmp_path / f"{name}.csv", index=False)
+
+
+def test_ingest_ragged_directory(pkg, tmp_path):
+    """SURVEY Appendix B ragged directory: 0.1 s bins, first-appearance frame order,
+    last sample of a bin wins, absent samples are NaN."""
+    from viewport_entropy_toolkit_b200 import ingest
+    _write_dir(tmp_path, {
+        "a": ([5.0, 5.1, 5.2, 5.3], [.5, .5, .6, .7], [.5] * 4),
+        "b": ([9.0, 9.1, 9.14, 9.3], [.1, .2, .3, .4], [.2] * 4),
+        "c": ([1.2, 1.0, 1.1], [.9] * 3, [.9] * 3),
+    })
+    packed, times, ids = ingest.load_directory(tmp_path, order=["a", "b", "c"])
+    g = group_keys(load_golden("analyzers"))["ragged"]
+    assert ids == ["a", "b", "c"]
+    assert np.array_equal(times, g["sp_time"])
+    assert packed.shape == (4, 3, 3)
+    assert np.array_equal(packed[:, 1, 1], [.1, .3, np.nan, .4], equal_nan=True)   # 9.14 overwrote bin 0.1; bin 0.2 absent
+    assert np.array_equal(packed[:, 2, 1], [.9, .9, .9, np.nan], equal_nan=True)   # unsorted times binned, 0.3 absent
+    # the oracle on this packed tensor reproduces the reference analyzers' rows
+    sp = orc.spatial_analyzer(packed, 100, 200, [20])
+    np.testing.assert_allclose(sp["entropy"], g["sp_entropy"], rtol=1e-12)
+    assert np.array_equal(sp["assign0"], g["sp_assign0"])
+
+
+def test_ingest_matches_reference_on_synthetic_directory(pkg, tmp_path):
+    from viewport_entropy_toolkit_b200 import ingest
+    a = load_golden("analyzers")
+    g = group_keys(a)
+    names = [str(n) for n in g["dir10_default"]["order"]]
+    for n in names:
+        arr = a[f"dir10/{n}"]
+        pd.DataFrame({"extra": 0, "time": arr[:, 0], "2dmu": arr[:, 1], "2dmv": arr[:, 2]}).to_csv(tmp_path / f"{n}.csv", index=False)
+    packed, times, ids = ingest.load_directory(tmp_path, order=names)
+    assert np.array_equal(times, g["dir10_default"]["sp_time"])
+    sp = orc.spatial_analyzer(packed, 100, 200, [20, 50])
+    np.testing.assert_allclose(sp["entropy"], g["dir10_default"]["sp_entropy"], rtol=1e-12)
+    assert np.array_equal(sp["assign0"], g["dir10_default"]["sp_assign0"])
+    np.testing.assert_allclose(sp["hist0"], g["dir10_default"]["sp_hist0"], rtol=1e-12)
+    tr = orc.transition_analyzer(packed, 100, 200, [20, 50])
+    np.testing.assert_allclose(tr["entropy"], g["dir10_default"]["tr_entropy"], rtol=1e-12, atol=1e-15, equal_nan=True)
+    assert np.array_equal(tr["prev_count0"], g["dir10_default"]["tr_prev_count0"])
+    # reversed user order + unweighted + three tile counts
+    names_r = [str(n) for n in g["dir10_unw"]["order"]]
+    packed_r, _, _ = ingest.load_directory(tmp_path, order=names_r)
+    sp = orc.spatial_analyzer(packed_r, 100, 200, [50, 20, 200], 90.0, False, 2.0)
+    np.testing.assert_allclose(sp["entropy"], g["dir10_unw"]["sp_entropy"], rtol=1e-12)
+    tr = orc.transition_analyzer(packed_r, 100, 200, [50, 20, 200])
+    np.testing.assert_allclose(tr["entropy"], g["dir10_unw"]["tr_entropy"], rtol=1e-12, atol=1e-15, equal_nan=True)
+
+
+def test_ingest_errors(pkg, tmp_path):
+    from viewport_entropy_toolkit_b200 import ingest
+    _write_dir(tmp_path, {"bad": ([0.0, 0.1], [0.5, 1.5], [0.5, 0.5])})
+    with pytest.raises(pkg.ValidationError, match="between 0 and 1"):
+        ingest.load_directory(tmp_path)
+    with pytest.raises(pkg.ValidationError, match="File not found"):
+        ingest.read_viewport_csv(tmp_path / "nope.csv")
+    a = pkg.SpatialEntropyAnalyzer(pkg.AnalyzerConfig(output_dir=tmp_path / "o"))
+    with pytest.raises(FileNotFoundError):
+        a.process_directory(tmp_path / "missing_dir")
+    with pytest.raises(pkg.ValidationError, match="Failed to process directory"):
+        a.process_directory(tmp_path)
+    with pytest.raises(pkg.ValidationError, match="No data available"):
+        a.compute_entropy()
+    with pytest.raises(pkg.ValidationError, match="No entropy results"):
+        a.create_visualization("x")
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(pkg.ValidationError, match="No trajectory data"):
+        a.process_directory(empty)

@@ -62,7 +62,10 @@ SYMBOLS = {
     "vet_transition_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, C.c_int]),
     "vet_poll_flags": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
     "vet_launch_count": (_I64, [_P]),
+    "vet_profile_enable": (C.c_int, [_P, C.c_int]),
+    "vet_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
+KERNEL_NAMES = ("stream", "epilogue", "transition")
 
 _lib: Optional[C.CDLL] = None
 

@@ -82,6 +82,13 @@ struct vet_handle {
   size_t in_bytes = 0;
   cudaStream_t s_copy = nullptr, s_exec = nullptr;
   int64_t launches = 0;
+  // optional per-kernel timing (vet_profile_*): CUDA events recorded around each launch
+  bool profiling = false;
+  struct Span {
+    int kernel;
+    cudaEvent_t a, b;
+  };
+  std::vector<Span> spans;
 };
 
 namespace {
@@ -174,6 +181,23 @@ struct DeviceGuard {
   }
   ~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct LaunchTimer {  // records an event pair around one kernel launch when profiling is on
+  vet_handle* h;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kernel;
+  LaunchTimer(vet_handle* h_, int kernel_, cudaStream_t st_) : h(h_), st(st_), kernel(kernel_) {
+    h->launches++;
+    if (h->profiling && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+  }
+  ~LaunchTimer() {
+    if (a && b) {
+      cudaEventRecord(b, st);
+      h->spans.push_back({kernel, a, b});
+    }
   }
 };
 
@@ -281,11 +305,13 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
   const int64_t items = F * a.chunks_per_frame;
   const int blocks = (int)std::min<int64_t>(items, h->sm_count);
   const size_t smem = stream_smem_bytes(h);
-  if (dtype == VET_F32)
-    vet::k_stream_simple<float><<<blocks, 1024, smem, st>>>(a);
-  else
-    vet::k_stream_simple<double><<<blocks, 1024, smem, st>>>(a);
-  h->launches++;
+  {
+    LaunchTimer lt(h, VET_KERNEL_STREAM, st);
+    if (dtype == VET_F32)
+      vet::k_stream_simple<float><<<blocks, 1024, smem, st>>>(a);
+    else
+      vet::k_stream_simple<double><<<blocks, 1024, smem, st>>>(a);
+  }
   VET_CUDA(cudaGetLastError());
   return VET_OK;
 }
@@ -311,8 +337,10 @@ int launch_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, in
   a.hist0 = hist0;
   a.flags = h->d_flags;
   const int blocks = (int)std::min<int64_t>(F, (int64_t)h->sm_count * 2);
-  vet::k_epilogue<<<blocks, 512, epilogue_smem_bytes(h), st>>>(a, h->maxT);
-  h->launches++;
+  {
+    LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
+    vet::k_epilogue<<<blocks, 512, epilogue_smem_bytes(h), st>>>(a, h->maxT);
+  }
   VET_CUDA(cudaGetLastError());
   return VET_OK;
 }
@@ -442,6 +470,10 @@ extern "C" int vet_destroy(vet_handle* h) {
   if (!h) return VET_OK;
   DeviceGuard guard(h->device);
   for (auto& t : h->ts) free_tile_set(t);
+  for (auto& s : h->spans) {
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
   cudaFree(h->d_cosT);
   cudaFree(h->d_sinT);
   cudaFree(h->d_sinP);
@@ -617,13 +649,14 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
     const int nb = (int)std::min<int64_t>(nf - 1, blocks);
     if (in_smem) {
       VET_CUDA(cudaFuncSetAttribute(vet::k_transition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
+      LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
       vet::k_transition<true><<<nb, 512, smem_tab, st>>>(a, h->maxT);
     } else {
       VET_CUDA(cudaFuncSetAttribute(vet::k_transition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(tile_bytes + 64)));
+      LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
       vet::k_transition<false><<<nb, 512, tile_bytes + 64, st>>>(a, h->maxT);
     }
-    h->launches++;
     VET_CUDA(cudaGetLastError());
     if (nf == F - f0) break;
   }
@@ -637,6 +670,38 @@ extern "C" int vet_poll_flags(vet_handle* h, void* stream, uint32_t* flags) {
   VET_CUDA(cudaMemcpyAsync(flags, h->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   VET_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(uint32_t), st));
   VET_CUDA(cudaStreamSynchronize(st));
+  return VET_OK;
+}
+
+extern "C" int vet_profile_enable(vet_handle* h, int on) {
+  if (!h) return fail(VET_ERR_INVALID_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  for (auto& s : h->spans) {
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  h->spans.clear();
+  h->profiling = on != 0;
+  return VET_OK;
+}
+
+extern "C" int vet_profile_read(vet_handle* h, double* ms_by_kernel, int64_t* launches_by_kernel) {
+  if (!h || !ms_by_kernel || !launches_by_kernel) return fail(VET_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(h->device);
+  for (int i = 0; i < VET_KERNEL_COUNT; ++i) {
+    ms_by_kernel[i] = 0.0;
+    launches_by_kernel[i] = 0;
+  }
+  for (auto& s : h->spans) {
+    VET_CUDA(cudaEventSynchronize(s.b));
+    float ms = 0.f;
+    VET_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+    ms_by_kernel[s.kernel] += ms;
+    launches_by_kernel[s.kernel] += 1;
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  h->spans.clear();
   return VET_OK;
 }
 

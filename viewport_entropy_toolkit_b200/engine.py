@@ -65,7 +65,10 @@ class Engine:
     """One native handle.  Not thread-safe per instance; use one per thread/stream."""
 
     def __init__(self, video_width: int, video_height: int, tile_counts: Sequence[int],
-                 entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None):
+                 entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None,
+                 native_tables: bool = False):
+        """native_tables=True lets the library derive the lattice and axis tables itself
+        (libm) instead of receiving the numpy-made ones; used by tests to show both agree."""
         self._h = None
         lib = N.load_library()
         if not torch.cuda.is_available():
@@ -93,8 +96,10 @@ class Engine:
         cfg = N.VetConfig(
             device=self.device.index, video_width=self.video_width, video_height=self.video_height,
             num_tile_counts=K, tile_counts=tc, fov_angle=float(ec.fov_angle), power_factor=float(ec.power_factor),
-            use_weight_distribution=int(bool(ec.use_weight_distribution)), centres=cptrs,
-            lon_by_px=lon.ctypes.data_as(C.POINTER(C.c_double)), lat_by_py=lat.ctypes.data_as(C.POINTER(C.c_double)))
+            use_weight_distribution=int(bool(ec.use_weight_distribution)),
+            centres=None if native_tables else cptrs,
+            lon_by_px=None if native_tables else lon.ctypes.data_as(C.POINTER(C.c_double)),
+            lat_by_py=None if native_tables else lat.ctypes.data_as(C.POINTER(C.c_double)))
         h = C.c_void_p()
         _check(lib.vet_create(C.byref(h), C.byref(cfg)))
         self._h = h
@@ -131,6 +136,17 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self._lib.vet_launch_count(self._h))
+
+    def profile(self, on: bool = True) -> None:
+        """Starts (or stops) recording a CUDA-event pair around every kernel launch."""
+        _check(self._lib.vet_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel: (summed device milliseconds, launches)} since profile(True)."""
+        ms = (C.c_double * len(N.KERNEL_NAMES))()
+        cnt = (C.c_int64 * len(N.KERNEL_NAMES))()
+        _check(self._lib.vet_profile_read(self._h, ms, cnt))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(N.KERNEL_NAMES)}
 
     def poll_flags(self) -> int:
         """Synchronises the current stream and returns (and clears) the sticky
