@@ -17,6 +17,7 @@
 #include "vet_b200.h"
 #include "vet_common.cuh"
 #include "vet_stream.cuh"
+#include "vet_stream_tma.cuh"
 #include "vet_tables.cuh"
 #include "vet_transition.cuh"
 
@@ -47,6 +48,7 @@ struct TileSet {
   std::vector<double> h_centres;  // [T,3]
   double* d_unit = nullptr;       // [T,3] centres / ||centre||
   uint16_t* d_lut = nullptr;      // [C]
+  uint8_t* d_lut8 = nullptr;      // [C] same table in bytes when T <= 255 (halves the shared-memory LUT)
   std::vector<uint16_t> h_lut;
   uint32_t* d_col_ptr = nullptr;  // [T+1]
   uint32_t* d_cell_idx = nullptr;
@@ -60,6 +62,7 @@ struct vet_handle {
   int device = 0;
   int W = 0, H = 0;
   int64_t C = 0;
+  int Cpad = 0;  // C rounded up to a multiple of 4: row pitch (in cells) of the per-frame cell histogram
   int K = 0;
   double fov = 120.0, pf = 2.0, max_d = 0.0;
   int use_weight = 1;
@@ -228,6 +231,11 @@ int build_tile_set(vet_handle* h, TileSet& t) {
   VET_CUDA(cudaGetLastError());
   t.h_lut.resize(h->C);
   VET_CUDA(cudaMemcpy(t.h_lut.data(), t.d_lut, (size_t)h->C * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  if (T <= 255) {
+    std::vector<uint8_t> l8(h->C);
+    for (int64_t c = 0; c < h->C; ++c) l8[c] = (uint8_t)t.h_lut[c];
+    if (int rc = upload(&t.d_lut8, l8.data(), l8.size())) return rc;
+  }
   if (h->use_weight) {
     uint32_t* d_count = nullptr;
     VET_CUDA(cudaMalloc((void**)&d_count, (size_t)T * sizeof(uint32_t)));
@@ -260,20 +268,34 @@ int build_tile_set(vet_handle* h, TileSet& t) {
 void free_tile_set(TileSet& t) {
   cudaFree(t.d_unit);
   cudaFree(t.d_lut);
+  cudaFree(t.d_lut8);
   cudaFree(t.d_col_ptr);
   cudaFree(t.d_cell_idx);
   cudaFree(t.d_w_val);
 }
 
-size_t stream_smem_bytes(const vet_handle* h) { return (size_t)h->C * 4 + (size_t)h->C * 2 + 16; }
+size_t stream_smem_bytes(const vet_handle* h) { return (size_t)h->Cpad * 4 + (size_t)h->C * 2 + 16; }
+size_t stream_tma_smem_bytes(const vet_handle* h, bool lut8) {
+  return (size_t)vet::kStages * vet::kStageBytes + (size_t)h->Cpad * 4 + (size_t)h->C * (lut8 ? 1 : 2) + 16;
+}
 size_t epilogue_smem_bytes(const vet_handle* h) {
-  return (((size_t)h->C * 4 + 15) & ~(size_t)15) + (size_t)h->maxT * 8 + (size_t)h->maxT * 4 + 16;
+  return (size_t)h->Cpad * 4 + (size_t)h->maxT * 8 + (size_t)h->maxT * 4 + 16;
+}
+bool use_tma_stream(const vet_handle* h, const void* packed) {
+  static const bool force_simple = [] {
+    const char* e = getenv("VET_STREAM_IMPL");
+    return e && std::string(e) == "simple";
+  }();
+  if (force_simple) return false;
+  if (((uintptr_t)packed & 15) != 0) return false;  // bulk copies need a 16 B aligned tensor base
+  const bool lut8 = h->ts[0].d_lut8 != nullptr;
+  return stream_tma_smem_bytes(h, lut8) + kStaticSmemSlack <= h->smem_optin;
 }
 
 // frames per batch so that the per-frame cell histogram scratch stays bounded
 int64_t frames_per_batch(const vet_handle* h, int64_t F, int64_t U, bool need_cells) {
   const size_t budget = (size_t)1 << 30;  // 1 GiB of scratch
-  size_t per_frame = (size_t)h->C * 4;
+  size_t per_frame = (size_t)h->Cpad * 4;
   if (need_cells) per_frame += (size_t)U * (h->C <= 65535 ? 2 : 4);
   int64_t fb = (int64_t)std::max<size_t>(2, budget / std::max<size_t>(per_frame, 1));
   return std::min<int64_t>(F, fb);
@@ -301,11 +323,32 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
   a.chunk_users = (U + cpf - 1) / cpf;
   a.chunks_per_frame = (int)((U + a.chunk_users - 1) / std::max<int64_t>(a.chunk_users, 1));
   if (a.chunks_per_frame < 1) a.chunks_per_frame = 1;
-  if (a.chunks_per_frame > 1) VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->C * 4, st));
+  a.cpad = h->Cpad;
+  if (a.chunks_per_frame > 1) VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->Cpad * 4, st));
   const int64_t items = F * a.chunks_per_frame;
   const int blocks = (int)std::min<int64_t>(items, h->sm_count);
-  const size_t smem = stream_smem_bytes(h);
-  {
+  if (use_tma_stream(h, packed)) {
+    const bool lut8 = h->ts[0].d_lut8 != nullptr;
+    vet::StreamTmaArgs A{};
+    A.s = a;
+    A.lut0_typed = lut8 ? (const void*)h->ts[0].d_lut8 : (const void*)h->ts[0].d_lut;
+    A.total_bytes = F * U * 3 * (int64_t)(dtype == VET_F32 ? 4 : 8);
+    A.cpad = h->Cpad;
+    const size_t smem = stream_tma_smem_bytes(h, lut8);
+    LaunchTimer lt(h, VET_KERNEL_STREAM, st);
+    if (dtype == VET_F32) {
+      if (lut8)
+        vet::k_stream_tma<float, uint8_t><<<blocks, vet::kStreamThreads, smem, st>>>(A);
+      else
+        vet::k_stream_tma<float, uint16_t><<<blocks, vet::kStreamThreads, smem, st>>>(A);
+    } else {
+      if (lut8)
+        vet::k_stream_tma<double, uint8_t><<<blocks, vet::kStreamThreads, smem, st>>>(A);
+      else
+        vet::k_stream_tma<double, uint16_t><<<blocks, vet::kStreamThreads, smem, st>>>(A);
+    }
+  } else {
+    const size_t smem = stream_smem_bytes(h);
     LaunchTimer lt(h, VET_KERNEL_STREAM, st);
     if (dtype == VET_F32)
       vet::k_stream_simple<float><<<blocks, 1024, smem, st>>>(a);
@@ -322,6 +365,7 @@ int launch_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, in
   a.cnt = h->d_cnt;
   a.F = F;
   a.C = (int)h->C;
+  a.cpad = h->Cpad;
   a.K = h->K;
   a.use_weight = h->use_weight;
   for (int k = 0; k < h->K; ++k) {
@@ -388,6 +432,7 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   h->W = cfg->video_width;
   h->H = cfg->video_height;
   h->C = (int64_t)(h->W + 1) * (h->H + 1);
+  h->Cpad = (int)((h->C + 3) & ~(int64_t)3);
   h->K = cfg->num_tile_counts;
   h->fov = cfg->fov_angle;
   h->pf = cfg->power_factor;
@@ -458,6 +503,16 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
                                 (int)stream_smem_bytes(h)));
   VET_CUDA(cudaFuncSetAttribute(vet::k_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)epilogue_smem_bytes(h)));
+  {
+    const bool lut8 = h->ts[0].d_lut8 != nullptr;
+    const size_t sm = stream_tma_smem_bytes(h, lut8);
+    if (sm + kStaticSmemSlack <= h->smem_optin) {
+      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<float, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<float, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<double, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<double, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+  }
   VET_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
   VET_CUDA(cudaStreamCreateWithFlags(&h->s_exec, cudaStreamNonBlocking));
   VET_CUDA(cudaDeviceSynchronize());
@@ -569,7 +624,7 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t fb = frames_per_batch(h, F, U, false);
-  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->C * 4)) return rc;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->Cpad * 4)) return rc;
   const size_t esz = dtype == VET_F32 ? 4 : 8;
   const int T0 = h->ts[0].T;
   for (int64_t f0 = 0; f0 < F; f0 += fb) {
@@ -595,7 +650,7 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
   const size_t csz = h->C <= 65535 ? 2 : 4;
-  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->C * 4)) return rc;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->Cpad * 4)) return rc;
   if (int rc = grow(&h->d_cells, &h->cells_bytes, (size_t)fb * U * csz)) return rc;
   // pair table: capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
   const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)h->maxT * h->maxT);
@@ -762,7 +817,7 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
     // per_k is laid out [K,F] on the device; rows are filled batch by batch
     {
       const int64_t fbs = frames_per_batch(h, nf, U, false);
-      rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fbs * h->C * 4);
+      rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fbs * h->Cpad * 4);
       for (int64_t g0 = 0; g0 < nf && rc == VET_OK; g0 += fbs) {
         const int64_t ng = std::min(fbs, nf - g0);
         const char* in = (const char*)h->d_in[b] + (size_t)g0 * U * 3 * esz;

@@ -15,7 +15,8 @@ struct StreamArgs {
   uint16_t* assign0;    // [F,U] or null
   uint16_t* cell16;     // [F,U] or null (cell ids for the transition stage, C <= 65535)
   int32_t* cell32;      // [F,U] or null (same, any C)
-  uint32_t* cnt;        // [F,C] per-frame cell histogram
+  uint32_t* cnt;        // [F,cpad] per-frame cell histogram
+  int cpad;             // row pitch of cnt in cells (C rounded up to a multiple of 4)
   int chunks_per_frame; // >1: cnt is pre-zeroed and flushed with atomics
   int64_t chunk_users;
   uint32_t* flags;
@@ -27,7 +28,7 @@ template <typename TIN>
 __global__ void __launch_bounds__(1024, 1) k_stream_simple(StreamArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
-  uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_hist + a.C);
+  uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_hist + a.cpad);
   const TIN* __restrict__ packed = static_cast<const TIN*>(a.packed);
   const float Wf = (float)a.W, Hf = (float)a.H;
   const bool want_assign = a.assign0 != nullptr;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(1024, 1) k_stream_simple(StreamArgs a) {
       if (a.cell32) a.cell32[base + u] = cell;
     }
     __syncthreads();
-    uint32_t* __restrict__ row = a.cnt + f * (int64_t)a.C;
+    uint32_t* __restrict__ row = a.cnt + f * (int64_t)a.cpad;
     if (a.chunks_per_frame == 1) {
       for (int c = threadIdx.x; c < a.C; c += blockDim.x) row[c] = s_hist[c];
     } else {
@@ -79,9 +80,10 @@ struct TileSetDev {
 constexpr int kMaxTileCounts = 16;
 
 struct EpilogueArgs {
-  const uint32_t* cnt;  // [F,C]
+  const uint32_t* cnt;  // [F,cpad]
   int64_t F;
   int C;
+  int cpad;
   int K;
   int use_weight;
   TileSetDev ts[kMaxTileCounts];
@@ -103,12 +105,12 @@ struct EpilogueArgs {
 __global__ void __launch_bounds__(512, 1) k_epilogue(EpilogueArgs a, int maxT) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw);
-  double* s_hist = reinterpret_cast<double*>(smem_raw + (((size_t)a.C * 4 + 15) & ~(size_t)15));
+  double* s_hist = reinterpret_cast<double*>(smem_raw + (size_t)a.cpad * 4);
   uint32_t* s_ihist = reinterpret_cast<uint32_t*>(s_hist + maxT);
   __shared__ double s_red[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int64_t f = blockIdx.x; f < a.F; f += gridDim.x) {
-    const uint32_t* __restrict__ row = a.cnt + f * (int64_t)a.C;
+    const uint32_t* __restrict__ row = a.cnt + f * (int64_t)a.cpad;
     unsigned long long nloc = 0;
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       const uint32_t v = row[c];
