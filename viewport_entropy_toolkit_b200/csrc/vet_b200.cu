@@ -20,6 +20,7 @@
 #include "vet_stream_tma.cuh"
 #include "vet_tables.cuh"
 #include "vet_transition.cuh"
+#include "vet_whist.cuh"
 
 namespace {
 
@@ -54,6 +55,14 @@ struct TileSet {
   uint32_t* d_cell_idx = nullptr;
   double* d_w_val = nullptr;
   uint64_t nnz = 0;
+  // grouped dense weight blocks for the batched weighted histogram (vet_whist.cuh)
+  int G = 0;
+  int32_t* d_group_tiles = nullptr;    // [G,8]
+  uint32_t* d_group_chunk0 = nullptr;  // [G+1]
+  unsigned char* d_chunks = nullptr;
+  uint32_t nchunks = 0;
+  double* d_hist = nullptr;            // [frames,T] scratch rows (grown on demand)
+  size_t hist_bytes = 0;
 };
 
 }  // namespace
@@ -76,6 +85,9 @@ struct vet_handle {
   // scratch (grown on demand)
   uint32_t* d_cnt = nullptr;
   size_t cnt_bytes = 0;
+  uint32_t* d_nvalid = nullptr;  // [frames] present users per frame
+  size_t nvalid_bytes = 0;
+  uint32_t* d_work = nullptr;    // work counters of the dynamic schedulers
   void* d_cells = nullptr;
   size_t cells_bytes = 0;
   uint32_t* d_tables = nullptr;
@@ -207,6 +219,86 @@ struct LaunchTimer {  // records an event pair around one kernel launch when pro
 constexpr size_t kStaticSmemSlack = 1024;
 constexpr int kMaxT = 16384;
 
+// Clusters the tiles into groups of kTG spatial neighbours and lays every group's
+// weights out as dense [cells][kTG] blocks over the union of the members' supports
+// (see vet_whist.cuh).  Values are the device-computed ones of the column table.
+int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& col_ptr, const std::vector<double>& unit) {
+  const int T = t.T;
+  std::vector<uint32_t> cell_idx(std::max<uint64_t>(t.nnz, 1));
+  std::vector<double> w_val(std::max<uint64_t>(t.nnz, 1));
+  if (t.nnz) {
+    VET_CUDA(cudaMemcpy(cell_idx.data(), t.d_cell_idx, t.nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    VET_CUDA(cudaMemcpy(w_val.data(), t.d_w_val, t.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  // greedy proximity clustering: seed = lowest unassigned tile, members = its nearest unassigned tiles
+  std::vector<char> used(T, 0);
+  std::vector<int32_t> group_tiles;
+  std::vector<std::pair<double, int>> cand;
+  for (int seed = 0; seed < T; ++seed) {
+    if (used[seed]) continue;
+    cand.clear();
+    for (int j = 0; j < T; ++j)
+      if (!used[j]) {
+        const double d = unit[3 * seed] * unit[3 * j] + unit[3 * seed + 1] * unit[3 * j + 1] + unit[3 * seed + 2] * unit[3 * j + 2];
+        cand.emplace_back(-d, j);
+      }
+    const size_t take = std::min<size_t>(vet::kTG, cand.size());
+    std::partial_sort(cand.begin(), cand.begin() + take, cand.end());
+    for (int m = 0; m < vet::kTG; ++m) {
+      if ((size_t)m < take) {
+        group_tiles.push_back(cand[m].second);
+        used[cand[m].second] = 1;
+      } else {
+        group_tiles.push_back(-1);
+      }
+    }
+  }
+  const int G = (int)(group_tiles.size() / vet::kTG);
+  std::vector<uint32_t> chunk0(G + 1, 0);
+  std::vector<unsigned char> chunks;
+  std::vector<int32_t> slot(h->C, -1);
+  std::vector<uint32_t> cells;
+  for (int g = 0; g < G; ++g) {
+    cells.clear();
+    for (int m = 0; m < vet::kTG; ++m) {
+      const int tile = group_tiles[g * vet::kTG + m];
+      if (tile < 0) continue;
+      for (uint32_t j = col_ptr[tile]; j < col_ptr[tile + 1]; ++j)
+        if (slot[cell_idx[j]] < 0) {
+          slot[cell_idx[j]] = 0;
+          cells.push_back(cell_idx[j]);
+        }
+    }
+    std::sort(cells.begin(), cells.end());
+    for (size_t i = 0; i < cells.size(); ++i) slot[cells[i]] = (int32_t)i;
+    const uint32_t nch = (uint32_t)((cells.size() + vet::kChunkCells - 1) / vet::kChunkCells);
+    chunk0[g] = (uint32_t)(chunks.size() / vet::kChunkBytes);
+    const size_t base = chunks.size();
+    chunks.resize(base + (size_t)nch * vet::kChunkBytes, 0);  // zero weights, idx 0 for padding
+    for (size_t i = 0; i < cells.size(); ++i) {
+      unsigned char* ch = chunks.data() + base + (i / vet::kChunkCells) * vet::kChunkBytes;
+      reinterpret_cast<uint32_t*>(ch + vet::kChunkCells * vet::kTG * 8)[i % vet::kChunkCells] = cells[i];
+    }
+    for (int m = 0; m < vet::kTG; ++m) {
+      const int tile = group_tiles[g * vet::kTG + m];
+      if (tile < 0) continue;
+      for (uint32_t j = col_ptr[tile]; j < col_ptr[tile + 1]; ++j) {
+        const size_t i = (size_t)slot[cell_idx[j]];
+        unsigned char* ch = chunks.data() + base + (i / vet::kChunkCells) * vet::kChunkBytes;
+        reinterpret_cast<double*>(ch)[m * vet::kChunkCells + i % vet::kChunkCells] = w_val[j];
+      }
+    }
+    for (uint32_t c : cells) slot[c] = -1;
+  }
+  chunk0[G] = (uint32_t)(chunks.size() / vet::kChunkBytes);
+  t.G = G;
+  t.nchunks = chunk0[G];
+  if (int rc = upload(&t.d_group_tiles, group_tiles.data(), group_tiles.size())) return rc;
+  if (int rc = upload(&t.d_group_chunk0, chunk0.data(), chunk0.size())) return rc;
+  if (int rc = upload(&t.d_chunks, chunks.data(), chunks.size())) return rc;
+  return VET_OK;
+}
+
 int build_tile_set(vet_handle* h, TileSet& t) {
   const int T = t.T;
   std::vector<double> unit((size_t)T * 3);
@@ -261,6 +353,7 @@ int build_tile_set(vet_handle* h, TileSet& t) {
                                             t.d_cell_idx, t.d_w_val);
     h->launches++;
     VET_CUDA(cudaGetLastError());
+    if (int rc = build_weight_groups(h, t, ptr, unit)) return rc;
   }
   return VET_OK;
 }
@@ -272,6 +365,10 @@ void free_tile_set(TileSet& t) {
   cudaFree(t.d_col_ptr);
   cudaFree(t.d_cell_idx);
   cudaFree(t.d_w_val);
+  cudaFree(t.d_group_tiles);
+  cudaFree(t.d_group_chunk0);
+  cudaFree(t.d_chunks);
+  cudaFree(t.d_hist);
 }
 
 size_t stream_smem_bytes(const vet_handle* h) { return (size_t)h->Cpad * 4 + (size_t)h->C * 2 + 16; }
@@ -315,6 +412,7 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
   a.cell16 = (cells && h->C <= 65535) ? (uint16_t*)h->d_cells : nullptr;
   a.cell32 = (cells && h->C > 65535) ? (int32_t*)h->d_cells : nullptr;
   a.cnt = h->d_cnt;
+  a.nvalid = h->d_nvalid;
   a.flags = h->d_flags;
   // enough work items to balance the SMs, chunks no smaller than 32k users
   const int64_t want_items = (int64_t)h->sm_count * 24;
@@ -324,7 +422,10 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
   a.chunks_per_frame = (int)((U + a.chunk_users - 1) / std::max<int64_t>(a.chunk_users, 1));
   if (a.chunks_per_frame < 1) a.chunks_per_frame = 1;
   a.cpad = h->Cpad;
-  if (a.chunks_per_frame > 1) VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->Cpad * 4, st));
+  if (a.chunks_per_frame > 1) {
+    VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->Cpad * 4, st));
+    VET_CUDA(cudaMemsetAsync(h->d_nvalid, 0, (size_t)F * 4, st));
+  }
   const int64_t items = F * a.chunks_per_frame;
   const int blocks = (int)std::min<int64_t>(items, h->sm_count);
   if (use_tma_stream(h, packed)) {
@@ -359,8 +460,59 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
   return VET_OK;
 }
 
+int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, int64_t per_k_stride,
+                             double* hist0, cudaStream_t st) {
+  vet::EntropyRowsArgs e{};
+  e.F = F;
+  e.K = h->K;
+  e.nvalid = h->d_nvalid;
+  e.use_weight = 1;
+  e.entropy = entropy;
+  e.per_k = per_k;
+  e.per_k_stride = per_k_stride;
+  e.flags = h->d_flags;
+  const int64_t fblocks = (F + vet::kWhWarps * vet::kFW - 1) / (vet::kWhWarps * vet::kFW);
+  VET_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t) * vet::kMaxTileCounts, st));
+  for (int k = 0; k < h->K; ++k) {
+    TileSet& t = h->ts[k];
+    double* hist = (k == 0 && hist0) ? hist0 : nullptr;
+    if (!hist) {
+      if (int rc = grow((void**)&t.d_hist, &t.hist_bytes, (size_t)F * t.T * 8)) return rc;
+      hist = t.d_hist;
+    }
+    vet::WhistArgs a{};
+    a.cnt = h->d_cnt;
+    a.F = F;
+    a.cpad = h->Cpad;
+    a.T = t.T;
+    a.G = t.G;
+    a.group_tiles = t.d_group_tiles;
+    a.group_chunk0 = t.d_group_chunk0;
+    a.chunks = t.d_chunks;
+    a.hist = hist;
+    a.work_counter = h->d_work + k;
+    a.items = fblocks * t.G;
+    const int blocks = (int)std::min<int64_t>(a.items, h->sm_count);
+    {
+      LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
+      vet::k_whist<<<blocks, vet::kWhThreads, vet::kWhStages * vet::kChunkBytes, st>>>(a);
+    }
+    VET_CUDA(cudaGetLastError());
+    e.T[k] = t.T;
+    e.hist[k] = hist;
+  }
+  {
+    LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
+    const int blocks = (int)std::min<int64_t>((F + 7) / 8, (int64_t)h->sm_count * 8);
+    vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e);
+  }
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
 int launch_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, int64_t per_k_stride, double* hist0,
                     cudaStream_t st) {
+  if (h->use_weight) return launch_weighted_epilogue(h, F, entropy, per_k, per_k_stride, hist0, st);
   vet::EpilogueArgs a{};
   a.cnt = h->d_cnt;
   a.F = F;
@@ -490,6 +642,9 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   VET_CUDA(cudaMalloc((void**)&h->d_cellvec, (size_t)h->C * 3 * sizeof(double)));
   VET_CUDA(cudaMalloc((void**)&h->d_flags, sizeof(uint32_t)));
   VET_CUDA(cudaMemset(h->d_flags, 0, sizeof(uint32_t)));
+  VET_CUDA(cudaMalloc((void**)&h->d_work, sizeof(uint32_t) * vet::kMaxTileCounts));
+  VET_CUDA(cudaFuncSetAttribute(vet::k_whist, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                vet::kWhStages * vet::kChunkBytes));
   vet::k_cell_vectors<<<std::min<int64_t>((h->C + 255) / 256, 1024), 256>>>(h->d_cosT, h->d_sinT, h->d_sinP, h->d_cosP,
                                                                              h->W, h->H, h->d_cellvec);
   h->launches++;
@@ -536,6 +691,8 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_cellvec);
   cudaFree(h->d_flags);
   cudaFree(h->d_cnt);
+  cudaFree(h->d_nvalid);
+  cudaFree(h->d_work);
   cudaFree(h->d_cells);
   cudaFree(h->d_tables);
   cudaFree(h->d_in[0]);
@@ -625,6 +782,7 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t fb = frames_per_batch(h, F, U, false);
   if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->Cpad * 4)) return rc;
+  if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
   const size_t esz = dtype == VET_F32 ? 4 : 8;
   const int T0 = h->ts[0].T;
   for (int64_t f0 = 0; f0 < F; f0 += fb) {
@@ -651,6 +809,7 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
   const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
   const size_t csz = h->C <= 65535 ? 2 : 4;
   if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->Cpad * 4)) return rc;
+  if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
   if (int rc = grow(&h->d_cells, &h->cells_bytes, (size_t)fb * U * csz)) return rc;
   // pair table: capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
   const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)h->maxT * h->maxT);
@@ -818,6 +977,7 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
     {
       const int64_t fbs = frames_per_batch(h, nf, U, false);
       rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fbs * h->Cpad * 4);
+      if (rc == VET_OK) rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fbs * 4);
       for (int64_t g0 = 0; g0 < nf && rc == VET_OK; g0 += fbs) {
         const int64_t ng = std::min(fbs, nf - g0);
         const char* in = (const char*)h->d_in[b] + (size_t)g0 * U * 3 * esz;

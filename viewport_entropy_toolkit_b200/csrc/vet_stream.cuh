@@ -15,6 +15,7 @@ struct StreamArgs {
   uint16_t* assign0;    // [F,U] or null
   uint16_t* cell16;     // [F,U] or null (cell ids for the transition stage, C <= 65535)
   int32_t* cell32;      // [F,U] or null (same, any C)
+  uint32_t* nvalid;     // [F] present users per frame (pre-zeroed when chunks_per_frame > 1)
   uint32_t* cnt;        // [F,cpad] per-frame cell histogram
   int cpad;             // row pitch of cnt in cells (C rounded up to a multiple of 4)
   int chunks_per_frame; // >1: cnt is pre-zeroed and flushed with atomics
@@ -36,25 +37,35 @@ __global__ void __launch_bounds__(1024, 1) k_stream_simple(StreamArgs a) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_lut[c] = a.lut0[c];
   const int64_t items = a.F * a.chunks_per_frame;
   uint32_t bad = 0;
+  __shared__ uint32_t s_nvalid;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     const int64_t f = item / a.chunks_per_frame;
     const int64_t u0 = (item % a.chunks_per_frame) * a.chunk_users;
     const int64_t u1 = min(a.U, u0 + a.chunk_users);
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_hist[c] = 0u;
+    if (threadIdx.x == 0) s_nvalid = 0u;
     __syncthreads();
     const int64_t base = f * a.U;
+    uint32_t nv = 0;
     for (int64_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
       const TIN mu = packed[3 * (base + u) + 1];
       const TIN mv = packed[3 * (base + u) + 2];
       int cell;
       const int st = decode_cell(mu, mv, Wf, Hf, a.W, a.H, cell);
+      nv += (st == kOk);
       if (st == kOk) atomicAdd(&s_hist[cell], 1u);
       if (st == kOutOfRange) bad = 1;
       if (want_assign) a.assign0[base + u] = (st == kOk) ? s_lut[cell] : (uint16_t)VET_MISSING;
       if (a.cell16) a.cell16[base + u] = (st == kOk) ? (uint16_t)cell : (uint16_t)0xFFFF;
       if (a.cell32) a.cell32[base + u] = cell;
     }
+    nv = __reduce_add_sync(kFull, nv);
+    if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&s_nvalid, nv);
     __syncthreads();
+    if (threadIdx.x == 0) {
+      if (a.chunks_per_frame == 1) a.nvalid[f] = s_nvalid;
+      else if (s_nvalid) atomicAdd(&a.nvalid[f], s_nvalid);
+    }
     uint32_t* __restrict__ row = a.cnt + f * (int64_t)a.cpad;
     if (a.chunks_per_frame == 1) {
       for (int c = threadIdx.x; c < a.C; c += blockDim.x) row[c] = s_hist[c];

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kStages * kStageBytes);
   TLUT* s_lut = reinterpret_cast<TLUT*>(s_hist + A.cpad);
   __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
+  __shared__ uint32_t s_nvalid;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool want_assign = a.assign0 != nullptr;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int c = threadIdx.x; c < A.cpad; c += blockDim.x) s_hist[c] = 0u;
+  if (threadIdx.x == 0) s_nvalid = 0u;
   if (want_assign) {
     const TLUT* __restrict__ g_lut = static_cast<const TLUT*>(A.lut0_typed);
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_lut[c] = g_lut[c];
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
     const int64_t u1 = min(a.U, u0 + a.chunk_users);
     const int64_t s0 = f * a.U + u0, s1 = f * a.U + u1;
     const int ntiles = (int)((s1 - s0 + kTileSamples - 1) / kTileSamples);
+    uint32_t nv = 0;
     for (int t = 0; t < ntiles; ++t, ++n) {
       const int stage = n % kStages;
       const uint32_t phase = (n / kStages) & 1u;
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
         if (s < r.nsamp) {
           int cell;
           const int st = decode_cell(mu[j], mv[j], Wf, Hf, a.W, a.H, cell);
+          nv += (st == kOk);
           if (st == kOk) atomicAdd(&s_hist[cell], 1u);
           if (st == kOutOfRange) bad = 1;
           const int64_t g = sample0 + s;
@@ -200,7 +204,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
       if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));
     }
     // item finished: flush the privatised histogram and clear it
+    nv = __reduce_add_sync(kFull, nv);
+    if (lane == 0 && nv) atomicAdd(&s_nvalid, nv);
     consumer_sync();
+    if (ctid == 0) {
+      if (a.chunks_per_frame == 1) a.nvalid[f] = s_nvalid;
+      else if (s_nvalid) atomicAdd(&a.nvalid[f], s_nvalid);
+      s_nvalid = 0u;
+    }
     uint4* __restrict__ row = reinterpret_cast<uint4*>(a.cnt + f * (int64_t)A.cpad);
     uint4* s_hist4 = reinterpret_cast<uint4*>(s_hist);
     const int n4 = A.cpad >> 2;

@@ -1,0 +1,248 @@
+// FOV-weighted tile histograms for many frames at once (north_star stage 3, weighted).
+//
+//   HIST[f, t] = sum_cell CNT[f, cell] * w(cell, t)            (EU:130-138, 190-192)
+//
+// CNT is the per-frame cell histogram written by the streaming kernel; w is the
+// (cell, tile) FOV weight, non-zero for ~15-25 % of the pairs.  A per-frame gather
+// re-reads the whole weight table for every frame and is L2-bandwidth bound (first
+// profile: 2.0 ms, 13 TB/s of L2 traffic).  Here the contraction is blocked like a
+// GEMM on the FP64 pipe instead:
+//
+//   * tiles are clustered into groups of 8 spatial neighbours; a group owns the UNION
+//     of its members' supports as a sorted cell list and a dense [cells][8] weight
+//     block (zeros where a member does not see the cell), chunked 256 cells at a time;
+//   * a CTA = 1 producer warp + 7 consumer warps works on (frame block of 56, group):
+//     the producer streams the group's chunks into shared memory with cp.async.bulk
+//     (two stages, mbarrier hand-off); every consumer warp owns 8 frames;
+//   * lane = cell: per step a lane reads its cell's 8 weights from shared memory
+//     (conflict-free) and its cell's count in each of the warp's 8 frames from global
+//     (L2-resident, near-coalesced), and issues 8x8 DFMAs into register accumulators,
+//     i.e. one 4-byte load per 8 DFMAs and one 8-byte shared load per 8 DFMAs;
+//   * at the end the 64 accumulators are reduced across the warp with a transposing
+//     butterfly (62 shuffles instead of 320) in a fixed order -> deterministic sums.
+//
+// No tensor cores: the contraction runs on counts and weights that must stay fp64 for
+// the 1e-9 entropy tolerance, and the fp64 tensor path offers no throughput over DFMA.
+#pragma once
+#include "vet_common.cuh"
+#include "vet_stream_tma.cuh"
+
+namespace vet {
+
+constexpr int kTG = 8;            // tiles per group
+constexpr int kFW = 8;            // frames per consumer warp
+constexpr int kWhWarps = 7;       // consumer warps per CTA (7 + producer = 256 threads -> 255 registers each)
+constexpr int kChunkCells = 256;  // cells per staged chunk
+constexpr int kChunkBytes = kChunkCells * kTG * 8 + kChunkCells * 4;  // weights [8][256] f64 + idx[256] u32
+constexpr int kWhStages = 2;
+constexpr int kWhThreads = (kWhWarps + 1) * 32;
+
+struct WhistArgs {
+  const uint32_t* cnt;     // [F,cpad]
+  int64_t F;
+  int cpad;
+  int T;
+  int G;                         // tile groups
+  const int32_t* group_tiles;    // [G,8] tile index or -1
+  const uint32_t* group_chunk0;  // [G+1] first chunk of each group
+  const unsigned char* chunks;   // [nchunks][kChunkBytes]
+  double* hist;                  // [F,T]
+  uint32_t* work_counter;        // dynamic work distribution (zeroed before launch)
+  int64_t items;                 // frame blocks * G
+};
+
+__device__ __forceinline__ void consumer_sync_wh() {
+  asm volatile("bar.sync 2, %0;" ::"n"(kWhWarps * 32) : "memory");
+}
+
+// exact u32 -> f64 without the slow I2F.F64 path: 2^52 + v has v in its low mantissa bits
+__device__ __forceinline__ double u32_to_f64(uint32_t v) {
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+
+// One step of the transposing warp reduction: lanes with (lane & O) keep the upper LIVE
+// values and send the lower ones to their partner, the others the reverse.
+template <int O, int LIVE>
+__device__ __forceinline__ void butterfly_step(double* flat, int lane) {
+  const bool upper = (lane & O) != 0;
+#pragma unroll
+  for (int i = 0; i < LIVE; ++i) {
+    const double keep = upper ? flat[i + LIVE] : flat[i];
+    const double send = upper ? flat[i] : flat[i + LIVE];
+    flat[i] = keep + __shfl_xor_sync(kFull, send, O);
+  }
+}
+
+__global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_full[kWhStages], s_empty[kWhStages];
+  __shared__ uint32_t s_item[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWhStages; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_empty[i]), kWhWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Work items are claimed by the producer lane and published through shared memory so
+  // that producer and consumers walk the same sequence.  Item order is frame-block major:
+  // CTAs running at the same time share the frame block's CNT rows in L2.
+  uint32_t n = 0;  // chunk sequence number (stage = n % kWhStages), same on both sides
+  int round = 0;
+  while (true) {
+    // ---- claim the next item (all threads agree through s_item[round & 1]) ----
+    if (threadIdx.x == 0) s_item[round & 1] = atomicAdd(a.work_counter, 1u);
+    __syncthreads();
+    const uint32_t item = s_item[round & 1];
+    ++round;
+    if ((int64_t)item >= a.items) break;
+    const int g = (int)(item % (uint32_t)a.G);
+    const int64_t fb = item / (uint32_t)a.G;
+    const uint32_t c0 = a.group_chunk0[g], c1 = a.group_chunk0[g + 1];
+
+    if (warp == 0) {
+      if (lane == 0) {
+        for (uint32_t c = c0; c < c1; ++c, ++n) {
+          const int stage = n % kWhStages;
+          mbar_wait(smem_u32(&s_empty[stage]), ((n / kWhStages) & 1u) ^ 1u);
+          const uint32_t bar = smem_u32(&s_full[stage]);
+          mbar_expect_tx(bar, kChunkBytes);
+          bulk_g2s(smem_u32(smem_raw + stage * kChunkBytes), a.chunks + (size_t)c * kChunkBytes, kChunkBytes, bar);
+        }
+      }
+      n = __shfl_sync(kFull, n, 0);
+    } else {
+      const int cw = warp - 1;
+      const int64_t f0 = fb * (kWhWarps * kFW) + cw * kFW;
+      // rows of this warp's frames; frames past the end alias the last frame (results discarded)
+      const uint32_t* rows[kFW];
+#pragma unroll
+      for (int r = 0; r < kFW; ++r) rows[r] = a.cnt + min(f0 + r, a.F - 1) * (int64_t)a.cpad;
+      double acc[kTG][kFW];
+#pragma unroll
+      for (int t = 0; t < kTG; ++t)
+#pragma unroll
+        for (int r = 0; r < kFW; ++r) acc[t][r] = 0.0;
+
+      for (uint32_t c = c0; c < c1; ++c, ++n) {
+        const int stage = n % kWhStages;
+        mbar_wait(smem_u32(&s_full[stage]), (n / kWhStages) & 1u);
+        const double* sW = reinterpret_cast<const double*>(smem_raw + stage * kChunkBytes);
+        const uint32_t* sI = reinterpret_cast<const uint32_t*>(smem_raw + stage * kChunkBytes + kChunkCells * kTG * 8);
+        // software pipeline: counts of step s+1 are in flight while step s computes
+        uint32_t nxt[kFW];
+        {
+          const uint32_t idx = sI[lane];
+#pragma unroll
+          for (int r = 0; r < kFW; ++r) nxt[r] = __ldg(rows[r] + idx);
+        }
+#pragma unroll 1
+        for (int s = 0; s < kChunkCells / 32; ++s) {
+          uint32_t cur[kFW];
+#pragma unroll
+          for (int r = 0; r < kFW; ++r) cur[r] = nxt[r];
+          if (s + 1 < kChunkCells / 32) {
+            const uint32_t idx = sI[(s + 1) * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < kFW; ++r) nxt[r] = __ldg(rows[r] + idx);
+          }
+          double w[kTG];
+#pragma unroll
+          for (int t = 0; t < kTG; ++t) w[t] = sW[t * kChunkCells + s * 32 + lane];
+          double v[kFW];
+#pragma unroll
+          for (int r = 0; r < kFW; ++r) v[r] = u32_to_f64(cur[r]);
+#pragma unroll
+          for (int t = 0; t < kTG; ++t)
+#pragma unroll
+            for (int r = 0; r < kFW; ++r) acc[t][r] = fma(v[r], w[t], acc[t][r]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));
+      }
+
+      // transposing butterfly: after the step with offset o a lane keeps the half of its
+      // live accumulators selected by (lane & o); 64 values -> 2 per lane
+      double* flat = &acc[0][0];
+      butterfly_step<16, 32>(flat, lane);
+      butterfly_step<8, 16>(flat, lane);
+      butterfly_step<4, 8>(flat, lane);
+      butterfly_step<2, 4>(flat, lane);
+      butterfly_step<1, 2>(flat, lane);
+      // lane holds flat[0], flat[1]; its original accumulator index:
+      //   bits contributed by offsets 16,8,4,2,1 select halves of 64,32,16,8,4 -> index = 2*rev + j
+      int base = 0;
+      {
+        int span = kTG * kFW;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          span >>= 1;
+          if (lane & o) base += span;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int id = base + j;  // = t * kFW + r
+        const int t = id / kFW, r = id % kFW;
+        const int tile = a.group_tiles[g * kTG + t];
+        const int64_t f = f0 + r;
+        if (tile >= 0 && f < a.F) a.hist[f * (int64_t)a.T + tile] = flat[j];
+      }
+    }
+  }
+}
+
+// Per-frame normalised entropy from finished histogram rows (EU:195-209) and the
+// average over tile counts (SA:151-156).  One warp per frame.
+struct EntropyRowsArgs {
+  int64_t F;
+  int K;
+  int T[kMaxTileCounts];
+  const double* hist[kMaxTileCounts];  // [F,T_k]
+  const uint32_t* nvalid;              // [F] present users per frame
+  int use_weight;
+  double* entropy;   // [F]
+  double* per_k;     // [K, stride] or null
+  int64_t per_k_stride;
+  uint32_t* flags;
+};
+
+__global__ void k_entropy_rows(EntropyRowsArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t f = warp; f < a.F; f += nwarps) {
+    const uint32_t nv = a.nvalid[f];
+    if (nv == 0 && lane == 0) atomicOr(a.flags, (uint32_t)VET_FLAG_EMPTY_FRAME);
+    double esum = 0.0;
+    for (int k = 0; k < a.K; ++k) {
+      const int T = a.T[k];
+      const double* __restrict__ row = a.hist[k] + f * (int64_t)T;
+      double part = 0.0;
+      for (int t = lane; t < T; t += 32) part += row[t];
+      const double total = a.use_weight ? warp_sum(part) : (double)nv;
+      double acc = 0.0;
+      for (int t = lane; t < T; t += 32) {
+        const double w = row[t];
+        if (w > 0.0) {
+          const double p = w / total;
+          acc -= p * log2(p);
+        }
+      }
+      const double Hs = warp_sum(acc);
+      const double nn = (a.use_weight || total > (double)T) ? (double)T : total;
+      const double mp = 1.0 / nn;
+      const double mx = -nn * mp * log2(mp);
+      double e = Hs / mx;
+      if (nv == 0) e = __longlong_as_double(0x7ff8000000000000LL);
+      if (lane == 0 && a.per_k) a.per_k[k * a.per_k_stride + f] = e;
+      esum += e;
+    }
+    if (lane == 0) a.entropy[f] = esum / (double)a.K;
+  }
+}
+
+}  // namespace vet
