@@ -59,7 +59,8 @@ struct TileSet {
   int G = 0;
   int32_t* d_group_tiles = nullptr;    // [G,8]
   uint32_t* d_group_chunk0 = nullptr;  // [G+1]
-  unsigned char* d_chunks = nullptr;
+  double* d_chunks = nullptr;          // [nchunks][kTG][kQ][kChunkUnits]
+  uint32_t* d_units = nullptr;         // [nchunks*kChunkUnits + pad]
   uint32_t nchunks = 0;
   double* d_hist = nullptr;            // [frames,T] scratch rows (grown on demand)
   size_t hist_bytes = 0;
@@ -255,47 +256,53 @@ int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& 
   }
   const int G = (int)(group_tiles.size() / vet::kTG);
   std::vector<uint32_t> chunk0(G + 1, 0);
-  std::vector<unsigned char> chunks;
-  std::vector<int32_t> slot(h->C, -1);
-  std::vector<uint32_t> cells;
+  std::vector<double> chunks;       // [nchunks][kTG][kQ][kChunkUnits]
+  std::vector<uint32_t> units_all;  // [nchunks][kChunkUnits] first cell of each load unit
+  const int64_t n_units_total = (h->Cpad + vet::kQ - 1) / vet::kQ;
+  std::vector<int32_t> slot(n_units_total, -1);
+  std::vector<uint32_t> units;
+  const size_t chunk_doubles = (size_t)vet::kChunkCells * vet::kTG;
   for (int g = 0; g < G; ++g) {
-    cells.clear();
-    for (int m = 0; m < vet::kTG; ++m) {
-      const int tile = group_tiles[g * vet::kTG + m];
-      if (tile < 0) continue;
-      for (uint32_t j = col_ptr[tile]; j < col_ptr[tile + 1]; ++j)
-        if (slot[cell_idx[j]] < 0) {
-          slot[cell_idx[j]] = 0;
-          cells.push_back(cell_idx[j]);
-        }
-    }
-    std::sort(cells.begin(), cells.end());
-    for (size_t i = 0; i < cells.size(); ++i) slot[cells[i]] = (int32_t)i;
-    const uint32_t nch = (uint32_t)((cells.size() + vet::kChunkCells - 1) / vet::kChunkCells);
-    chunk0[g] = (uint32_t)(chunks.size() / vet::kChunkBytes);
-    const size_t base = chunks.size();
-    chunks.resize(base + (size_t)nch * vet::kChunkBytes, 0);  // zero weights, idx 0 for padding
-    for (size_t i = 0; i < cells.size(); ++i) {
-      unsigned char* ch = chunks.data() + base + (i / vet::kChunkCells) * vet::kChunkBytes;
-      reinterpret_cast<uint32_t*>(ch + vet::kChunkCells * vet::kTG * 8)[i % vet::kChunkCells] = cells[i];
-    }
+    units.clear();
     for (int m = 0; m < vet::kTG; ++m) {
       const int tile = group_tiles[g * vet::kTG + m];
       if (tile < 0) continue;
       for (uint32_t j = col_ptr[tile]; j < col_ptr[tile + 1]; ++j) {
-        const size_t i = (size_t)slot[cell_idx[j]];
-        unsigned char* ch = chunks.data() + base + (i / vet::kChunkCells) * vet::kChunkBytes;
-        reinterpret_cast<double*>(ch)[m * vet::kChunkCells + i % vet::kChunkCells] = w_val[j];
+        const uint32_t u = cell_idx[j] / vet::kQ;
+        if (slot[u] < 0) {
+          slot[u] = 0;
+          units.push_back(u);
+        }
       }
     }
-    for (uint32_t c : cells) slot[c] = -1;
+    std::sort(units.begin(), units.end());
+    for (size_t i = 0; i < units.size(); ++i) slot[units[i]] = (int32_t)i;
+    const uint32_t nch = (uint32_t)((units.size() + vet::kChunkUnits - 1) / vet::kChunkUnits);
+    chunk0[g] = (uint32_t)(chunks.size() / chunk_doubles);
+    const size_t base = chunks.size();
+    chunks.resize(base + (size_t)nch * chunk_doubles, 0.0);           // zero weights for padding
+    units_all.resize((size_t)(chunk0[g] + nch) * vet::kChunkUnits, 0);  // padding units point at cells 0..kQ-1
+    for (size_t i = 0; i < units.size(); ++i) units_all[(size_t)chunk0[g] * vet::kChunkUnits + i] = units[i] * vet::kQ;
+    for (int m = 0; m < vet::kTG; ++m) {
+      const int tile = group_tiles[g * vet::kTG + m];
+      if (tile < 0) continue;
+      for (uint32_t j = col_ptr[tile]; j < col_ptr[tile + 1]; ++j) {
+        const size_t i = (size_t)slot[cell_idx[j] / vet::kQ];
+        const int q = (int)(cell_idx[j] % vet::kQ);
+        double* ch = chunks.data() + base + (i / vet::kChunkUnits) * chunk_doubles;
+        ch[(m * vet::kQ + q) * vet::kChunkUnits + i % vet::kChunkUnits] = w_val[j];
+      }
+    }
+    for (uint32_t u : units) slot[u] = -1;
   }
-  chunk0[G] = (uint32_t)(chunks.size() / vet::kChunkBytes);
+  chunk0[G] = (uint32_t)(chunks.size() / chunk_doubles);
+  units_all.resize((size_t)chunk0[G] * vet::kChunkUnits + vet::kUnitPad, 0);
   t.G = G;
   t.nchunks = chunk0[G];
   if (int rc = upload(&t.d_group_tiles, group_tiles.data(), group_tiles.size())) return rc;
   if (int rc = upload(&t.d_group_chunk0, chunk0.data(), chunk0.size())) return rc;
   if (int rc = upload(&t.d_chunks, chunks.data(), chunks.size())) return rc;
+  if (int rc = upload(&t.d_units, units_all.data(), units_all.size())) return rc;
   return VET_OK;
 }
 
@@ -368,6 +375,7 @@ void free_tile_set(TileSet& t) {
   cudaFree(t.d_group_tiles);
   cudaFree(t.d_group_chunk0);
   cudaFree(t.d_chunks);
+  cudaFree(t.d_units);
   cudaFree(t.d_hist);
 }
 
@@ -488,7 +496,8 @@ int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* 
     a.G = t.G;
     a.group_tiles = t.d_group_tiles;
     a.group_chunk0 = t.d_group_chunk0;
-    a.chunks = t.d_chunks;
+    a.chunks = reinterpret_cast<const unsigned char*>(t.d_chunks);
+    a.units = t.d_units;
     a.hist = hist;
     a.work_counter = h->d_work + k;
     a.items = fblocks * t.G;

@@ -10,14 +10,15 @@
 //
 //   * tiles are clustered into groups of 8 spatial neighbours; a group owns the UNION
 //     of its members' supports as a sorted cell list and a dense [cells][8] weight
-//     block (zeros where a member does not see the cell), chunked 256 cells at a time;
+//     block (zeros where a member does not see the cell); cells are taken as aligned
+//     pairs so that counts load as 8-byte words; weights are chunked 128 cells at a time;
 //   * a CTA = 1 producer warp + 7 consumer warps works on (frame block of 56, group):
 //     the producer streams the group's chunks into shared memory with cp.async.bulk
-//     (two stages, mbarrier hand-off); every consumer warp owns 8 frames;
-//   * lane = cell: per step a lane reads its cell's 8 weights from shared memory
-//     (conflict-free) and its cell's count in each of the warp's 8 frames from global
-//     (L2-resident, near-coalesced), and issues 8x8 DFMAs into register accumulators,
-//     i.e. one 4-byte load per 8 DFMAs and one 8-byte shared load per 8 DFMAs;
+//     (three stages, mbarrier hand-off); every consumer warp owns 8 frames;
+//   * lane = cell pair: per step a lane reads its cells' 8 weights each from shared
+//     memory (conflict-free) and the pair's counts in each of the warp's 8 frames from
+//     global (L2-resident, near-coalesced, prefetched two steps ahead in registers) and
+//     issues 2x8x8 DFMAs into register accumulators: one 4-byte load per 8 DFMAs;
 //   * at the end the 64 accumulators are reduced across the warp with a transposing
 //     butterfly (62 shuffles instead of 320) in a fixed order -> deterministic sums.
 //
@@ -29,13 +30,16 @@
 
 namespace vet {
 
-constexpr int kTG = 8;            // tiles per group
-constexpr int kFW = 8;            // frames per consumer warp
-constexpr int kWhWarps = 7;       // consumer warps per CTA (7 + producer = 256 threads -> 255 registers each)
-constexpr int kChunkCells = 256;  // cells per staged chunk
-constexpr int kChunkBytes = kChunkCells * kTG * 8 + kChunkCells * 4;  // weights [8][256] f64 + idx[256] u32
-constexpr int kWhStages = 2;
+constexpr int kTG = 8;             // tiles per group
+constexpr int kFW = 8;             // frames per consumer warp
+constexpr int kWhWarps = 7;        // consumer warps per CTA (7 + producer = 256 threads -> 255 registers each)
+constexpr int kQ = 2;              // cells per load unit: counts are fetched as aligned pairs (LDG.64)
+constexpr int kChunkUnits = 64;    // load units per staged weight chunk (two warp steps)
+constexpr int kChunkCells = kChunkUnits * kQ;
+constexpr int kChunkBytes = kChunkCells * kTG * 8;  // weights [8 tiles][kQ][64 units] f64
+constexpr int kWhStages = 3;
 constexpr int kWhThreads = (kWhWarps + 1) * 32;
+constexpr int kUnitPad = 4 * 32;   // the unit list is readable this far past its end (prefetch runs ahead)
 
 struct WhistArgs {
   const uint32_t* cnt;     // [F,cpad]
@@ -46,14 +50,11 @@ struct WhistArgs {
   const int32_t* group_tiles;    // [G,8] tile index or -1
   const uint32_t* group_chunk0;  // [G+1] first chunk of each group
   const unsigned char* chunks;   // [nchunks][kChunkBytes]
+  const uint32_t* units;         // [nchunks*kChunkUnits + kUnitPad] first cell of every load unit (multiple of kQ)
   double* hist;                  // [F,T]
   uint32_t* work_counter;        // dynamic work distribution (zeroed before launch)
   int64_t items;                 // frame blocks * G
 };
-
-__device__ __forceinline__ void consumer_sync_wh() {
-  asm volatile("bar.sync 2, %0;" ::"n"(kWhWarps * 32) : "memory");
-}
 
 // exact u32 -> f64 without the slow I2F.F64 path: 2^52 + v has v in its low mantissa bits
 __device__ __forceinline__ double u32_to_f64(uint32_t v) {
@@ -73,6 +74,8 @@ __device__ __forceinline__ void butterfly_step(double* flat, int lane) {
   }
 }
 
+__device__ __forceinline__ uint2 ldg_pair(const uint32_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+
 __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kWhStages], s_empty[kWhStages];
@@ -87,13 +90,12 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
   }
   __syncthreads();
 
-  // Work items are claimed by the producer lane and published through shared memory so
-  // that producer and consumers walk the same sequence.  Item order is frame-block major:
+  // Work items are claimed by thread 0 and published through shared memory so that the
+  // producer and the consumers walk the same sequence.  Item order is frame-block major:
   // CTAs running at the same time share the frame block's CNT rows in L2.
   uint32_t n = 0;  // chunk sequence number (stage = n % kWhStages), same on both sides
   int round = 0;
   while (true) {
-    // ---- claim the next item (all threads agree through s_item[round & 1]) ----
     if (threadIdx.x == 0) s_item[round & 1] = atomicAdd(a.work_counter, 1u);
     __syncthreads();
     const uint32_t item = s_item[round & 1];
@@ -117,48 +119,56 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
     } else {
       const int cw = warp - 1;
       const int64_t f0 = fb * (kWhWarps * kFW) + cw * kFW;
-      // rows of this warp's frames; frames past the end alias the last frame (results discarded)
-      const uint32_t* rows[kFW];
+      // element offsets of this warp's frame rows; frames past the end alias the last frame (results discarded)
+      uint32_t roff[kFW];
 #pragma unroll
-      for (int r = 0; r < kFW; ++r) rows[r] = a.cnt + min(f0 + r, a.F - 1) * (int64_t)a.cpad;
+      for (int r = 0; r < kFW; ++r) roff[r] = (uint32_t)(min(f0 + r, a.F - 1) * (int64_t)a.cpad);
       double acc[kTG][kFW];
 #pragma unroll
       for (int t = 0; t < kTG; ++t)
 #pragma unroll
         for (int r = 0; r < kFW; ++r) acc[t][r] = 0.0;
 
+      // Register pipeline over warp steps (32 load units each): the counts of steps s+1 and
+      // s+2 and the unit index of step s+3 are in flight while step s runs its 128 DFMAs, so
+      // L2 latency is covered by ~2 steps of FP64 work without any shared-memory staging.
+      const uint32_t* __restrict__ up = a.units + (size_t)c0 * kChunkUnits + lane;
+      uint2 cur[kFW], n1[kFW], n2[kFW];
+      uint32_t u0 = __ldg(up), u1 = __ldg(up + 32), u2 = __ldg(up + 64);
+#pragma unroll
+      for (int r = 0; r < kFW; ++r) cur[r] = ldg_pair(a.cnt + roff[r] + u0);
+#pragma unroll
+      for (int r = 0; r < kFW; ++r) n1[r] = ldg_pair(a.cnt + roff[r] + u1);
+      up += 96;
+
       for (uint32_t c = c0; c < c1; ++c, ++n) {
         const int stage = n % kWhStages;
         mbar_wait(smem_u32(&s_full[stage]), (n / kWhStages) & 1u);
         const double* sW = reinterpret_cast<const double*>(smem_raw + stage * kChunkBytes);
-        const uint32_t* sI = reinterpret_cast<const uint32_t*>(smem_raw + stage * kChunkBytes + kChunkCells * kTG * 8);
-        // software pipeline: counts of step s+1 are in flight while step s computes
-        uint32_t nxt[kFW];
-        {
-          const uint32_t idx = sI[lane];
-#pragma unroll
-          for (int r = 0; r < kFW; ++r) nxt[r] = __ldg(rows[r] + idx);
-        }
 #pragma unroll 1
-        for (int s = 0; s < kChunkCells / 32; ++s) {
-          uint32_t cur[kFW];
+        for (int s = 0; s < kChunkUnits / 32; ++s) {
+          const uint32_t u3 = __ldg(up);
+          up += 32;
 #pragma unroll
-          for (int r = 0; r < kFW; ++r) cur[r] = nxt[r];
-          if (s + 1 < kChunkCells / 32) {
-            const uint32_t idx = sI[(s + 1) * 32 + lane];
+          for (int r = 0; r < kFW; ++r) n2[r] = ldg_pair(a.cnt + roff[r] + u2);
+          u2 = u3;
 #pragma unroll
-            for (int r = 0; r < kFW; ++r) nxt[r] = __ldg(rows[r] + idx);
+          for (int j = 0; j < kQ; ++j) {
+            double w[kTG];
+#pragma unroll
+            for (int t = 0; t < kTG; ++t) w[t] = sW[(t * kQ + j) * kChunkUnits + s * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < kFW; ++r) {
+              const double v = u32_to_f64(j == 0 ? cur[r].x : cur[r].y);
+#pragma unroll
+              for (int t = 0; t < kTG; ++t) acc[t][r] = fma(v, w[t], acc[t][r]);
+            }
           }
-          double w[kTG];
 #pragma unroll
-          for (int t = 0; t < kTG; ++t) w[t] = sW[t * kChunkCells + s * 32 + lane];
-          double v[kFW];
-#pragma unroll
-          for (int r = 0; r < kFW; ++r) v[r] = u32_to_f64(cur[r]);
-#pragma unroll
-          for (int t = 0; t < kTG; ++t)
-#pragma unroll
-            for (int r = 0; r < kFW; ++r) acc[t][r] = fma(v[r], w[t], acc[t][r]);
+          for (int r = 0; r < kFW; ++r) {
+            cur[r] = n1[r];
+            n1[r] = n2[r];
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));
@@ -172,8 +182,6 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
       butterfly_step<4, 8>(flat, lane);
       butterfly_step<2, 4>(flat, lane);
       butterfly_step<1, 2>(flat, lane);
-      // lane holds flat[0], flat[1]; its original accumulator index:
-      //   bits contributed by offsets 16,8,4,2,1 select halves of 64,32,16,8,4 -> index = 2*rev + j
       int base = 0;
       {
         int span = kTG * kFW;
