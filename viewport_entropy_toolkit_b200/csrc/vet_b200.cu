@@ -480,7 +480,6 @@ int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* 
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
   const int64_t fblocks = (F + vet::kWhWarps * vet::kFW - 1) / (vet::kWhWarps * vet::kFW);
-  VET_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t) * vet::kMaxTileCounts, st));
   for (int k = 0; k < h->K; ++k) {
     TileSet& t = h->ts[k];
     double* hist = (k == 0 && hist0) ? hist0 : nullptr;
@@ -499,7 +498,6 @@ int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* 
     a.chunks = reinterpret_cast<const unsigned char*>(t.d_chunks);
     a.units = t.d_units;
     a.hist = hist;
-    a.work_counter = h->d_work + k;
     a.items = fblocks * t.G;
     const int blocks = (int)std::min<int64_t>(a.items, h->sm_count);
     {

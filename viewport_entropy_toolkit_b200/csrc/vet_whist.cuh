@@ -12,8 +12,8 @@
 //     of its members' supports as a sorted cell list and a dense [cells][8] weight
 //     block (zeros where a member does not see the cell); cells are taken as aligned
 //     pairs so that counts load as 8-byte words; weights are chunked 128 cells at a time;
-//   * a CTA = 1 producer warp + 7 consumer warps works on (frame block of 56, group):
-//     the producer streams the group's chunks into shared memory with cp.async.bulk
+//   * a CTA of 8 warps works on (frame block of 64, group):
+//     lane 0 of warp 0 streams the group's chunks into shared memory with cp.async.bulk
 //     (three stages, mbarrier hand-off); every consumer warp owns 8 frames;
 //   * lane = cell pair: per step a lane reads its cells' 8 weights each from shared
 //     memory (conflict-free) and the pair's counts in each of the warp's 8 frames from
@@ -32,14 +32,17 @@ namespace vet {
 
 constexpr int kTG = 8;             // tiles per group
 constexpr int kFW = 8;             // frames per consumer warp
-constexpr int kWhWarps = 7;        // consumer warps per CTA (7 + producer = 256 threads -> 255 registers each)
+constexpr int kWhWarps = 8;        // warps per CTA, two per SM sub-partition; lane 0 of warp 0 doubles as the
+                                   // weight-chunk producer (256 threads -> 255 registers each)
 constexpr int kQ = 2;              // cells per load unit: counts are fetched as aligned pairs (LDG.64)
-constexpr int kChunkUnits = 64;    // load units per staged weight chunk (two warp steps)
+constexpr int kDepth = 4;          // depth of the register ring: counts are fetched kDepth-1 warp steps ahead
+constexpr int kChunkUnits = 32 * kDepth;  // load units per staged weight chunk = kDepth warp steps (the ring is
+                                          // unrolled over them, so its rotation costs no register moves)
 constexpr int kChunkCells = kChunkUnits * kQ;
 constexpr int kChunkBytes = kChunkCells * kTG * 8;  // weights [8 tiles][kQ][64 units] f64
 constexpr int kWhStages = 3;
-constexpr int kWhThreads = (kWhWarps + 1) * 32;
-constexpr int kUnitPad = 4 * 32;   // the unit list is readable this far past its end (prefetch runs ahead)
+constexpr int kWhThreads = kWhWarps * 32;
+constexpr int kUnitPad = 2 * kDepth * 32;   // the unit list is readable this far past its end (prefetch runs ahead)
 
 struct WhistArgs {
   const uint32_t* cnt;     // [F,cpad]
@@ -52,13 +55,18 @@ struct WhistArgs {
   const unsigned char* chunks;   // [nchunks][kChunkBytes]
   const uint32_t* units;         // [nchunks*kChunkUnits + kUnitPad] first cell of every load unit (multiple of kQ)
   double* hist;                  // [F,T]
-  uint32_t* work_counter;        // dynamic work distribution (zeroed before launch)
   int64_t items;                 // frame blocks * G
 };
 
-// exact u32 -> f64 without the slow I2F.F64 path: 2^52 + v has v in its low mantissa bits
+// exact u32 -> f64.  VET_CVT_MAGIC: 2^52 + v has v in its low mantissa bits, one DADD on
+// the FP64 pipe plus two register moves; otherwise I2F.F64.U32 on the conversion unit,
+// which runs beside the FP64 pipe.
 __device__ __forceinline__ double u32_to_f64(uint32_t v) {
+#ifdef VET_CVT_MAGIC
   return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#else
+  return (double)v;
+#endif
 }
 
 // One step of the transposing warp reduction: lanes with (lane & O) keep the upper LIVE
@@ -79,7 +87,6 @@ __device__ __forceinline__ uint2 ldg_pair(const uint32_t* p) { return __ldg(rein
 __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kWhStages], s_empty[kWhStages];
-  __shared__ uint32_t s_item[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWhStages; ++i) {
@@ -90,115 +97,120 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
   }
   __syncthreads();
 
-  // Work items are claimed by thread 0 and published through shared memory so that the
-  // producer and the consumers walk the same sequence.  Item order is frame-block major:
-  // CTAs running at the same time share the frame block's CNT rows in L2.
-  uint32_t n = 0;  // chunk sequence number (stage = n % kWhStages), same on both sides
-  int round = 0;
-  while (true) {
-    if (threadIdx.x == 0) s_item[round & 1] = atomicAdd(a.work_counter, 1u);
-    __syncthreads();
-    const uint32_t item = s_item[round & 1];
-    ++round;
-    if ((int64_t)item >= a.items) break;
-    const int g = (int)(item % (uint32_t)a.G);
-    const int64_t fb = item / (uint32_t)a.G;
+  // Static round-robin over (frame block, group) items, frame-block major so that CTAs
+  // running at the same time share the block's CNT rows in L2.  No CTA-wide barrier
+  // after this point: warps only meet through the weight-chunk mbarriers.
+  uint32_t n = 0;  // chunk sequence number (stage = n % kWhStages), identical in every warp
+  for (int64_t item = blockIdx.x; item < a.items; item += gridDim.x) {
+    const int g = (int)(item % a.G);
+    const int64_t fb = item / a.G;
     const uint32_t c0 = a.group_chunk0[g], c1 = a.group_chunk0[g + 1];
-
-    if (warp == 0) {
-      if (lane == 0) {
-        for (uint32_t c = c0; c < c1; ++c, ++n) {
-          const int stage = n % kWhStages;
-          mbar_wait(smem_u32(&s_empty[stage]), ((n / kWhStages) & 1u) ^ 1u);
-          const uint32_t bar = smem_u32(&s_full[stage]);
-          mbar_expect_tx(bar, kChunkBytes);
-          bulk_g2s(smem_u32(smem_raw + stage * kChunkBytes), a.chunks + (size_t)c * kChunkBytes, kChunkBytes, bar);
-        }
+    // weight chunk `c` of this item goes to stage (n0 + c - c0) % kWhStages; issued by lane 0 of warp 0
+    const uint32_t n0 = n;
+    auto produce = [&](uint32_t c) {
+      if (warp == 0 && lane == 0 && c < c1) {
+        const uint32_t m = n0 + (c - c0);
+        const int stage = m % kWhStages;
+        mbar_wait(smem_u32(&s_empty[stage]), ((m / kWhStages) & 1u) ^ 1u);
+        const uint32_t bar = smem_u32(&s_full[stage]);
+        mbar_expect_tx(bar, kChunkBytes);
+        bulk_g2s(smem_u32(smem_raw + stage * kChunkBytes), a.chunks + (size_t)c * kChunkBytes, kChunkBytes, bar);
       }
-      n = __shfl_sync(kFull, n, 0);
-    } else {
-      const int cw = warp - 1;
-      const int64_t f0 = fb * (kWhWarps * kFW) + cw * kFW;
-      // element offsets of this warp's frame rows; frames past the end alias the last frame (results discarded)
-      uint32_t roff[kFW];
+    };
 #pragma unroll
-      for (int r = 0; r < kFW; ++r) roff[r] = (uint32_t)(min(f0 + r, a.F - 1) * (int64_t)a.cpad);
-      double acc[kTG][kFW];
-#pragma unroll
-      for (int t = 0; t < kTG; ++t)
-#pragma unroll
-        for (int r = 0; r < kFW; ++r) acc[t][r] = 0.0;
+    for (int i = 0; i < kWhStages - 1; ++i) produce(c0 + i);
 
-      // Register pipeline over warp steps (32 load units each): the counts of steps s+1 and
-      // s+2 and the unit index of step s+3 are in flight while step s runs its 128 DFMAs, so
-      // L2 latency is covered by ~2 steps of FP64 work without any shared-memory staging.
-      const uint32_t* __restrict__ up = a.units + (size_t)c0 * kChunkUnits + lane;
-      uint2 cur[kFW], n1[kFW], n2[kFW];
-      uint32_t u0 = __ldg(up), u1 = __ldg(up + 32), u2 = __ldg(up + 64);
+    const int64_t f0 = fb * (kWhWarps * kFW) + warp * kFW;
+    // element offsets of this warp's frame rows; frames past the end alias the last frame (results discarded)
+    uint32_t roff[kFW];
 #pragma unroll
-      for (int r = 0; r < kFW; ++r) cur[r] = ldg_pair(a.cnt + roff[r] + u0);
+    for (int r = 0; r < kFW; ++r) roff[r] = (uint32_t)(min(f0 + r, a.F - 1) * (int64_t)a.cpad);
+    double acc[kTG][kFW];
 #pragma unroll
-      for (int r = 0; r < kFW; ++r) n1[r] = ldg_pair(a.cnt + roff[r] + u1);
-      up += 96;
+    for (int t = 0; t < kTG; ++t)
+#pragma unroll
+      for (int r = 0; r < kFW; ++r) acc[t][r] = 0.0;
 
-      for (uint32_t c = c0; c < c1; ++c, ++n) {
-        const int stage = n % kWhStages;
-        mbar_wait(smem_u32(&s_full[stage]), (n / kWhStages) & 1u);
-        const double* sW = reinterpret_cast<const double*>(smem_raw + stage * kChunkBytes);
-#pragma unroll 1
-        for (int s = 0; s < kChunkUnits / 32; ++s) {
-          const uint32_t u3 = __ldg(up);
-          up += 32;
+    // Register pipeline over warp steps (32 load units each).  While step S runs its 128
+    // DFMAs, the counts of steps S+1 .. S+kDepth-1 are in flight in the ring and the unit
+    // indices of steps up to S+2(kDepth-1) in uring, so L2/DRAM latency is covered by
+    // kDepth-1 steps of FP64 work without staging the counts in shared memory.
+    const uint32_t* __restrict__ up = a.units + (size_t)c0 * kChunkUnits + lane;
+    uint2 ring[kDepth][kFW];
+    uint32_t uring[kDepth];
 #pragma unroll
-          for (int r = 0; r < kFW; ++r) n2[r] = ldg_pair(a.cnt + roff[r] + u2);
-          u2 = u3;
+    for (int i = 0; i < kDepth - 1; ++i) {
+      const uint32_t u = __ldg(up + 32 * i);
 #pragma unroll
-          for (int j = 0; j < kQ; ++j) {
-            double w[kTG];
+      for (int r = 0; r < kFW; ++r) ring[i][r] = ldg_pair(a.cnt + roff[r] + u);
+    }
 #pragma unroll
-            for (int t = 0; t < kTG; ++t) w[t] = sW[(t * kQ + j) * kChunkUnits + s * 32 + lane];
+    for (int x = kDepth - 1; x < 2 * kDepth - 2; ++x) uring[x % kDepth] = __ldg(up + 32 * x);
+    up += 32 * (2 * kDepth - 2);
+
+    for (uint32_t c = c0; c < c1; ++c, ++n) {
+      produce(c + kWhStages - 1);
+      const int stage = n % kWhStages;
+      mbar_wait(smem_u32(&s_full[stage]), (n / kWhStages) & 1u);
+      const double* sW = reinterpret_cast<const double*>(smem_raw + stage * kChunkBytes);
 #pragma unroll
-            for (int r = 0; r < kFW; ++r) {
-              const double v = u32_to_f64(j == 0 ? cur[r].x : cur[r].y);
+      for (int s = 0; s < kDepth; ++s) {
+        // issue the count loads of step S+kDepth-1 and the unit load of step S+2(kDepth-1)
+        const uint32_t u = uring[(s + kDepth - 1) % kDepth];
 #pragma unroll
-              for (int t = 0; t < kTG; ++t) acc[t][r] = fma(v, w[t], acc[t][r]);
-            }
-          }
+#ifndef VET_DBG_NO_CNT_LOADS
+        for (int r = 0; r < kFW; ++r) ring[(s + kDepth - 1) % kDepth][r] = ldg_pair(a.cnt + roff[r] + u);
+#else
+        for (int r = 0; r < kFW; ++r) ring[(s + kDepth - 1) % kDepth][r].x += u;
+#endif
+        uring[(s + kDepth - 2) % kDepth] = __ldg(up);
+        up += 32;
+        // step S out of ring[s]
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) {
+          double w[kTG];
+#pragma unroll
+#ifndef VET_DBG_NO_W_LOADS
+          for (int t = 0; t < kTG; ++t) w[t] = sW[(t * kQ + j) * kChunkUnits + s * 32 + lane];
+#else
+          for (int t = 0; t < kTG; ++t) w[t] = 1.0 + t + j + (double)n;
+#endif
 #pragma unroll
           for (int r = 0; r < kFW; ++r) {
-            cur[r] = n1[r];
-            n1[r] = n2[r];
+            const double v = u32_to_f64(j == 0 ? ring[s][r].x : ring[s][r].y);
+#pragma unroll
+            for (int t = 0; t < kTG; ++t) acc[t][r] = fma(v, w[t], acc[t][r]);
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));
+    }
 
-      // transposing butterfly: after the step with offset o a lane keeps the half of its
-      // live accumulators selected by (lane & o); 64 values -> 2 per lane
-      double* flat = &acc[0][0];
-      butterfly_step<16, 32>(flat, lane);
-      butterfly_step<8, 16>(flat, lane);
-      butterfly_step<4, 8>(flat, lane);
-      butterfly_step<2, 4>(flat, lane);
-      butterfly_step<1, 2>(flat, lane);
-      int base = 0;
-      {
-        int span = kTG * kFW;
+    // transposing butterfly: after the step with offset o a lane keeps the half of its
+    // live accumulators selected by (lane & o); 64 values -> 2 per lane
+    double* flat = &acc[0][0];
+    butterfly_step<16, 32>(flat, lane);
+    butterfly_step<8, 16>(flat, lane);
+    butterfly_step<4, 8>(flat, lane);
+    butterfly_step<2, 4>(flat, lane);
+    butterfly_step<1, 2>(flat, lane);
+    int base = 0;
+    {
+      int span = kTG * kFW;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          span >>= 1;
-          if (lane & o) base += span;
-        }
+      for (int o = 16; o >= 1; o >>= 1) {
+        span >>= 1;
+        if (lane & o) base += span;
       }
+    }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int id = base + j;  // = t * kFW + r
-        const int t = id / kFW, r = id % kFW;
-        const int tile = a.group_tiles[g * kTG + t];
-        const int64_t f = f0 + r;
-        if (tile >= 0 && f < a.F) a.hist[f * (int64_t)a.T + tile] = flat[j];
-      }
+    for (int j = 0; j < 2; ++j) {
+      const int id = base + j;  // = t * kFW + r
+      const int t = id / kFW, r = id % kFW;
+      const int tile = a.group_tiles[g * kTG + t];
+      const int64_t f = f0 + r;
+      if (tile >= 0 && f < a.F) a.hist[f * (int64_t)a.T + tile] = flat[j];
     }
   }
 }
