@@ -93,35 +93,36 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.t_from = 0.0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for (t, r) in self.rows if t >= self.t_from and len(r) >= 9]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region + 0.6 s of the same steps right after it (the timed region alone is shorter than nvidia-smi's sampling period)"}
 
 
 # ------------------------------------------------------------------------------------
@@ -242,7 +243,7 @@ def main():
                         hist0=torch.empty((F, T0), dtype=torch.float64, device=device),
                         assign0=torch.empty((F, U), dtype=torch.uint16, device=device))
     rows = torch.empty((F, 1 + T0), dtype=torch.float64, device=device)
-    gathered = torch.empty((world * F, 1 + T0), dtype=torch.float64, device=device) if world > 1 else None
+    from viewport_entropy_toolkit_b200.distributed import all_gather_rows
 
     def step():
         eng.spatial(packed, out=out)
@@ -251,7 +252,7 @@ def main():
         if world > 1:  # the path's only exchange: one all-gather of the per-frame result rows
             rows[:, 0] = out.entropy
             rows[:, 1:] = out.hist0
-            dist.all_gather_into_tensor(gathered, rows)
+            all_gather_rows(rows, [F] * world)
 
     for _ in range(args.warmup):
         step()
@@ -262,12 +263,14 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.2)
     launches0 = eng.launch_count()
     eng.profile(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.t_from = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
@@ -279,7 +282,13 @@ def main():
     prof = eng.profile_read()
     eng.profile(False)
     launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:  # keep the same load running long enough for nvidia-smi to see it
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            eng.spatial(packed, out=out)
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
     t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -307,12 +316,12 @@ def main():
         host = torch.empty((F, U, 3), dtype=torch.float32, pin_memory=True)
         host.copy_(packed)
         torch.cuda.synchronize()
-        eng.spatial_host(host, want_per_k=False)  # warm-up (allocates the staging buffers)
+        eng.spatial_host(host, want_per_k=False, reuse_buffers=True)  # warm-up (allocates the staging buffers)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            res = eng.spatial_host(host, want_per_k=False)
+            res = eng.spatial_host(host, want_per_k=False, reuse_buffers=True)
         dt = time.perf_counter() - t0
         t_e = torch.tensor([dt], dtype=torch.float64, device=device)
         if world > 1:

@@ -96,7 +96,9 @@ struct vet_handle {
   // host-buffer path
   void* d_in[2] = {nullptr, nullptr};
   size_t in_bytes = 0;
-  cudaStream_t s_copy = nullptr, s_exec = nullptr;
+  void* d_hout[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // entropy, per_k, hist0, assign x2
+  size_t hout_bytes[5] = {0, 0, 0, 0, 0};
+  cudaStream_t s_copy = nullptr, s_exec = nullptr, s_out = nullptr;
   int64_t launches = 0;
   // optional per-kernel timing (vet_profile_*): CUDA events recorded around each launch
   bool profiling = false;
@@ -445,17 +447,27 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
     A.cpad = h->Cpad;
     const size_t smem = stream_tma_smem_bytes(h, lut8);
     LaunchTimer lt(h, VET_KERNEL_STREAM, st);
-    if (dtype == VET_F32) {
-      if (lut8)
-        vet::k_stream_tma<float, uint8_t><<<blocks, vet::kStreamThreads, smem, st>>>(A);
-      else
-        vet::k_stream_tma<float, uint16_t><<<blocks, vet::kStreamThreads, smem, st>>>(A);
+    const dim3 grid(blocks), block(vet::kStreamThreads);
+#define VET_LAUNCH_STREAM(TIN, TLUT, ASSIGN, CELLS) vet::k_stream_tma<TIN, TLUT, ASSIGN, CELLS><<<grid, block, smem, st>>>(A)
+    const int cmode = a.cell16 ? 1 : (a.cell32 ? 2 : 0);
+    if (assign0) {  // spatial stage: assignments, no cell ids
+      if (dtype == VET_F32) {
+        if (lut8) VET_LAUNCH_STREAM(float, uint8_t, true, 0);
+        else VET_LAUNCH_STREAM(float, uint16_t, true, 0);
+      } else {
+        if (lut8) VET_LAUNCH_STREAM(double, uint8_t, true, 0);
+        else VET_LAUNCH_STREAM(double, uint16_t, true, 0);
+      }
+    } else if (dtype == VET_F32) {
+      if (cmode == 0) VET_LAUNCH_STREAM(float, uint8_t, false, 0);
+      else if (cmode == 1) VET_LAUNCH_STREAM(float, uint8_t, false, 1);
+      else VET_LAUNCH_STREAM(float, uint8_t, false, 2);
     } else {
-      if (lut8)
-        vet::k_stream_tma<double, uint8_t><<<blocks, vet::kStreamThreads, smem, st>>>(A);
-      else
-        vet::k_stream_tma<double, uint16_t><<<blocks, vet::kStreamThreads, smem, st>>>(A);
+      if (cmode == 0) VET_LAUNCH_STREAM(double, uint8_t, false, 0);
+      else if (cmode == 1) VET_LAUNCH_STREAM(double, uint8_t, false, 1);
+      else VET_LAUNCH_STREAM(double, uint8_t, false, 2);
     }
+#undef VET_LAUNCH_STREAM
   } else {
     const size_t smem = stream_smem_bytes(h);
     LaunchTimer lt(h, VET_KERNEL_STREAM, st);
@@ -669,14 +681,23 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
     const bool lut8 = h->ts[0].d_lut8 != nullptr;
     const size_t sm = stream_tma_smem_bytes(h, lut8);
     if (sm + kStaticSmemSlack <= h->smem_optin) {
-      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<float, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<float, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<double, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<double, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+#define VET_SMEM_ATTR(...) VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm))
+      VET_SMEM_ATTR(float, uint8_t, true, 0);
+      VET_SMEM_ATTR(float, uint16_t, true, 0);
+      VET_SMEM_ATTR(double, uint8_t, true, 0);
+      VET_SMEM_ATTR(double, uint16_t, true, 0);
+      VET_SMEM_ATTR(float, uint8_t, false, 0);
+      VET_SMEM_ATTR(float, uint8_t, false, 1);
+      VET_SMEM_ATTR(float, uint8_t, false, 2);
+      VET_SMEM_ATTR(double, uint8_t, false, 0);
+      VET_SMEM_ATTR(double, uint8_t, false, 1);
+      VET_SMEM_ATTR(double, uint8_t, false, 2);
+#undef VET_SMEM_ATTR
     }
   }
   VET_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
   VET_CUDA(cudaStreamCreateWithFlags(&h->s_exec, cudaStreamNonBlocking));
+  VET_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
   VET_CUDA(cudaDeviceSynchronize());
   cleanup.armed = false;
   *out = h;
@@ -704,8 +725,10 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_tables);
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);
+  for (void* p : h->d_hout) cudaFree(p);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_exec) cudaStreamDestroy(h->s_exec);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
   return VET_OK;
 }
@@ -958,63 +981,70 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
     h->in_bytes = in_bytes;
   }
   const int T0 = h->ts[0].T;
-  double *d_ent = nullptr, *d_perk = nullptr, *d_hist = nullptr;
-  uint16_t* d_assign[2] = {nullptr, nullptr};
-  VET_CUDA(cudaMalloc((void**)&d_ent, (size_t)F * 8));
-  if (per_k_host) VET_CUDA(cudaMalloc((void**)&d_perk, (size_t)F * h->K * 8));
-  if (hist0_host) VET_CUDA(cudaMalloc((void**)&d_hist, (size_t)F * T0 * 8));
+  // device-side result buffers are kept in the handle and only grown (cudaMalloc/cudaFree synchronise)
+  if (int rc = grow(&h->d_hout[0], &h->hout_bytes[0], (size_t)F * 8)) return rc;
+  if (per_k_host)
+    if (int rc = grow(&h->d_hout[1], &h->hout_bytes[1], (size_t)F * h->K * 8)) return rc;
+  if (hist0_host)
+    if (int rc = grow(&h->d_hout[2], &h->hout_bytes[2], (size_t)F * T0 * 8)) return rc;
   if (assign0_host)
-    for (int i = 0; i < 2; ++i) VET_CUDA(cudaMalloc((void**)&d_assign[i], (size_t)fb * U * 2));
-  cudaEvent_t in_done[2], buf_free[2];
+    for (int i = 0; i < 2; ++i)
+      if (int rc = grow(&h->d_hout[3 + i], &h->hout_bytes[3 + i], (size_t)fb * U * 2)) return rc;
+  double* d_ent = (double*)h->d_hout[0];
+  double* d_perk = per_k_host ? (double*)h->d_hout[1] : nullptr;
+  double* d_hist = hist0_host ? (double*)h->d_hout[2] : nullptr;
+  uint16_t* d_assign[2] = {assign0_host ? (uint16_t*)h->d_hout[3] : nullptr, assign0_host ? (uint16_t*)h->d_hout[4] : nullptr};
+  // Three streams: copy-in, execute, copy-out.  Batch b+1 is uploaded while batch b runs and
+  // batch b-1's assignments are downloaded (PCIe is full duplex).
+  cudaEvent_t in_done[2], exec_done[2], out_done[2];
   for (int i = 0; i < 2; ++i) {
     VET_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
-    VET_CUDA(cudaEventCreateWithFlags(&buf_free[i], cudaEventDisableTiming));
+    VET_CUDA(cudaEventCreateWithFlags(&exec_done[i], cudaEventDisableTiming));
+    VET_CUDA(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
   }
   int rc = VET_OK;
   int b = 0;
   for (int64_t f0 = 0; f0 < F && rc == VET_OK; f0 += fb, b ^= 1) {
     const int64_t nf = std::min(fb, F - f0);
-    // copy stream: wait until the kernels that read this buffer two batches ago are done
-    cudaStreamWaitEvent(h->s_copy, buf_free[b], 0);
+    cudaStreamWaitEvent(h->s_copy, exec_done[b], 0);  // input buffer b was last read two batches ago
     cudaMemcpyAsync(h->d_in[b], (const char*)packed_host + (size_t)f0 * U * 3 * esz, (size_t)nf * U * 3 * esz,
                     cudaMemcpyHostToDevice, h->s_copy);
     cudaEventRecord(in_done[b], h->s_copy);
     cudaStreamWaitEvent(h->s_exec, in_done[b], 0);
-    // per_k is laid out [K,F] on the device; rows are filled batch by batch
-    {
-      const int64_t fbs = frames_per_batch(h, nf, U, false);
-      rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fbs * h->Cpad * 4);
-      if (rc == VET_OK) rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fbs * 4);
-      for (int64_t g0 = 0; g0 < nf && rc == VET_OK; g0 += fbs) {
-        const int64_t ng = std::min(fbs, nf - g0);
-        const char* in = (const char*)h->d_in[b] + (size_t)g0 * U * 3 * esz;
-        rc = launch_stream(h, in, dtype, ng, U, d_assign[b] ? d_assign[b] + g0 * U : nullptr, false, h->s_exec);
-        if (rc == VET_OK)
-          rc = launch_epilogue(h, ng, d_ent + f0 + g0, d_perk ? d_perk + f0 + g0 : nullptr, F,
-                               d_hist ? d_hist + (f0 + g0) * T0 : nullptr, h->s_exec);
-      }
+    cudaStreamWaitEvent(h->s_exec, out_done[b], 0);  // assignment buffer b must have been downloaded
+    const int64_t fbs = frames_per_batch(h, nf, U, false);
+    rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fbs * h->Cpad * 4);
+    if (rc == VET_OK) rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fbs * 4);
+    for (int64_t g0 = 0; g0 < nf && rc == VET_OK; g0 += fbs) {
+      const int64_t ng = std::min(fbs, nf - g0);
+      const char* in = (const char*)h->d_in[b] + (size_t)g0 * U * 3 * esz;
+      rc = launch_stream(h, in, dtype, ng, U, d_assign[b] ? d_assign[b] + g0 * U : nullptr, false, h->s_exec);
+      if (rc == VET_OK)
+        rc = launch_epilogue(h, ng, d_ent + f0 + g0, d_perk ? d_perk + f0 + g0 : nullptr, F,
+                             d_hist ? d_hist + (f0 + g0) * T0 : nullptr, h->s_exec);
     }
-    if (rc == VET_OK && assign0_host)
-      cudaMemcpyAsync(assign0_host + f0 * U, d_assign[b], (size_t)nf * U * 2, cudaMemcpyDeviceToHost, h->s_exec);
-    cudaEventRecord(buf_free[b], h->s_exec);
+    cudaEventRecord(exec_done[b], h->s_exec);
+    if (rc == VET_OK && assign0_host) {
+      cudaStreamWaitEvent(h->s_out, exec_done[b], 0);
+      cudaMemcpyAsync(assign0_host + f0 * U, d_assign[b], (size_t)nf * U * 2, cudaMemcpyDeviceToHost, h->s_out);
+      cudaEventRecord(out_done[b], h->s_out);
+    }
   }
   if (rc == VET_OK) {
     cudaMemcpyAsync(entropy_host, d_ent, (size_t)F * 8, cudaMemcpyDeviceToHost, h->s_exec);
     if (per_k_host) cudaMemcpyAsync(per_k_host, d_perk, (size_t)F * h->K * 8, cudaMemcpyDeviceToHost, h->s_exec);
     if (hist0_host) cudaMemcpyAsync(hist0_host, d_hist, (size_t)F * T0 * 8, cudaMemcpyDeviceToHost, h->s_exec);
   }
-  cudaError_t e1 = cudaStreamSynchronize(h->s_copy), e2 = cudaStreamSynchronize(h->s_exec);
+  cudaError_t e1 = cudaStreamSynchronize(h->s_copy), e2 = cudaStreamSynchronize(h->s_exec),
+              e3 = cudaStreamSynchronize(h->s_out);
   for (int i = 0; i < 2; ++i) {
     cudaEventDestroy(in_done[i]);
-    cudaEventDestroy(buf_free[i]);
-    cudaFree(d_assign[i]);
+    cudaEventDestroy(exec_done[i]);
+    cudaEventDestroy(out_done[i]);
   }
-  cudaFree(d_ent);
-  cudaFree(d_perk);
-  cudaFree(d_hist);
   if (rc != VET_OK) return rc;
-  if (e1 != cudaSuccess || e2 != cudaSuccess)
-    return fail(VET_ERR_CUDA, "host-buffer pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  for (cudaError_t e : {e1, e2, e3})
+    if (e != cudaSuccess) return fail(VET_ERR_CUDA, "host-buffer pipeline failed: %s", cudaGetErrorString(e));
   return VET_OK;
 }
 

@@ -68,31 +68,26 @@ struct StreamTmaArgs {
   int cpad;                 // C rounded up to a multiple of 4 (row pitch of cnt, in cells)
 };
 
-// byte range of tile `t` of the item's sample range and the 16 B-aligned range actually fetched
-struct TileRange {
-  int64_t b0;        // first payload byte (relative to packed base)
-  int64_t a0, a1;    // aligned fetch range [a0, a1), clipped to the tensor
-  int nsamp;
-};
-template <typename TIN>
-__device__ __forceinline__ TileRange tile_range(int64_t s0, int64_t s1, int t, int64_t total_bytes) {
-  constexpr int kTileSamples = kTileBytes / (3 * (int)sizeof(TIN));
-  TileRange r;
-  const int64_t ts0 = s0 + (int64_t)t * kTileSamples;
-  const int64_t ts1 = min(s1, ts0 + kTileSamples);
-  r.nsamp = (int)(ts1 - ts0);
-  r.b0 = ts0 * 3 * (int64_t)sizeof(TIN);
-  const int64_t b1 = ts1 * 3 * (int64_t)sizeof(TIN);
-  r.a0 = r.b0 & ~(int64_t)15;
-  r.a1 = min((b1 + 15) & ~(int64_t)15, total_bytes & ~(int64_t)15);
-  if (r.a1 < r.a0) r.a1 = r.a0;
-  return r;
+// Slow-path classification of a sample that failed the fast [0,1] bit test.
+template <typename T>
+__device__ __forceinline__ int classify_slow(T mu, T mv) {
+  if (mu != mu || mv != mv) return kMissing;
+  if (mu < (T)0 || mu > (T)1 || mv < (T)0 || mv > (T)1) return kOutOfRange;
+  return kOk;  // -0.0
+}
+// v in [+0, 1] as one unsigned compare on the bit pattern (false for NaN, negatives and -0.0,
+// which take the slow path)
+__device__ __forceinline__ bool unit_range_fast(float v) { return __float_as_uint(v) <= 0x3F800000u; }
+__device__ __forceinline__ bool unit_range_fast(double v) {
+  return (unsigned long long)__double_as_longlong(v) <= 0x3FF0000000000000ull;
 }
 
-template <typename TIN, typename TLUT>
+// CELLS: 0 = no cell-id output, 1 = uint16 cell ids, 2 = int32 cell ids (transition stage input)
+template <typename TIN, typename TLUT, bool ASSIGN, int CELLS>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs A) {
   constexpr int kTileSamples = kTileBytes / (3 * (int)sizeof(TIN));
   constexpr int kPerThread = kTileSamples / (kConsumerWarps * 32);
+  constexpr int kSampleBytes = 3 * (int)sizeof(TIN);
   static_assert(kTileSamples % (kConsumerWarps * 32) == 0, "tile must split evenly over the consumer threads");
   const StreamArgs& a = A.s;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -103,7 +98,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
   __shared__ uint32_t s_nvalid;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool want_assign = a.assign0 != nullptr;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
@@ -113,7 +107,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
   }
   for (int c = threadIdx.x; c < A.cpad; c += blockDim.x) s_hist[c] = 0u;
   if (threadIdx.x == 0) s_nvalid = 0u;
-  if (want_assign) {
+  if (ASSIGN) {
     const TLUT* __restrict__ g_lut = static_cast<const TLUT*>(A.lut0_typed);
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_lut[c] = g_lut[c];
   }
@@ -121,6 +115,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
 
   const int64_t items = a.F * a.chunks_per_frame;
   const unsigned char* __restrict__ gbase = static_cast<const unsigned char*>(a.packed);
+  const int64_t total16 = A.total_bytes & ~(int64_t)15;  // bulk copies never read past this
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -130,17 +125,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
         const int64_t f = item / a.chunks_per_frame;
         const int64_t u0 = (item % a.chunks_per_frame) * a.chunk_users;
         const int64_t u1 = min(a.U, u0 + a.chunk_users);
-        const int64_t s0 = f * a.U + u0, s1 = f * a.U + u1;
-        const int ntiles = (int)((s1 - s0 + kTileSamples - 1) / kTileSamples);
-        for (int t = 0; t < ntiles; ++t, ++n) {
+        int64_t b = (f * a.U + u0) * kSampleBytes;
+        const int64_t bend = (f * a.U + u1) * kSampleBytes;
+        for (; b < bend; b += kTileBytes, ++n) {
           const int stage = n % kStages;
-          const uint32_t phase = (n / kStages) & 1u;
-          mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
-          const TileRange r = tile_range<TIN>(s0, s1, t, A.total_bytes);
-          const uint32_t bytes = (uint32_t)(r.a1 - r.a0);
+          mbar_wait(smem_u32(&s_empty[stage]), ((n / kStages) & 1u) ^ 1u);
+          const int64_t a0 = b & ~(int64_t)15;
+          int64_t a1 = min((min(b + kTileBytes, bend) + 15) & ~(int64_t)15, total16);
+          const uint32_t bytes = a1 > a0 ? (uint32_t)(a1 - a0) : 0u;
           const uint32_t bar = smem_u32(&s_full[stage]);
           mbar_expect_tx(bar, bytes);
-          if (bytes) bulk_g2s(smem_u32(s_stage + stage * kStageBytes), gbase + r.a0, bytes, bar);
+          if (bytes) bulk_g2s(smem_u32(s_stage + stage * kStageBytes), gbase + a0, bytes, bar);
         }
       }
     }
@@ -150,54 +145,72 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
   // ===================== consumers =====================
   const int ctid = threadIdx.x - 32;  // 0 .. kConsumerWarps*32-1
   const float Wf = (float)a.W, Hf = (float)a.H;
+  const int W1 = a.W + 1;
   uint32_t n = 0;
   uint32_t bad = 0;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     const int64_t f = item / a.chunks_per_frame;
     const int64_t u0 = (item % a.chunks_per_frame) * a.chunk_users;
     const int64_t u1 = min(a.U, u0 + a.chunk_users);
-    const int64_t s0 = f * a.U + u0, s1 = f * a.U + u1;
-    const int ntiles = (int)((s1 - s0 + kTileSamples - 1) / kTileSamples);
+    int64_t scur = f * a.U + u0;
+    const int64_t send = f * a.U + u1;
     uint32_t nv = 0;
-    for (int t = 0; t < ntiles; ++t, ++n) {
+    for (; scur < send; scur += kTileSamples, ++n) {
       const int stage = n % kStages;
-      const uint32_t phase = (n / kStages) & 1u;
-      const TileRange r = tile_range<TIN>(s0, s1, t, A.total_bytes);
-      mbar_wait(smem_u32(&s_full[stage]), phase);
-      const unsigned char* sbuf = s_stage + stage * kStageBytes + (int)(r.b0 - r.a0);
-      const int64_t sample0 = s0 + (int64_t)t * kTileSamples;
+      const int64_t b0 = scur * kSampleBytes;
+      const int nsamp = (int)min((int64_t)kTileSamples, send - scur);
+      const bool full_tile = (nsamp == kTileSamples) && (b0 + kTileBytes <= total16);
+      mbar_wait(smem_u32(&s_full[stage]), (n / kStages) & 1u);
+      const TIN* sbuf = reinterpret_cast<const TIN*>(s_stage + stage * kStageBytes + (int)(b0 & 15));
+      uint16_t* __restrict__ out_assign = ASSIGN ? a.assign0 + scur : nullptr;
+      uint16_t* __restrict__ out_c16 = CELLS == 1 ? a.cell16 + scur : nullptr;
+      int32_t* __restrict__ out_c32 = CELLS == 2 ? a.cell32 + scur : nullptr;
       TIN mu[kPerThread], mv[kPerThread];
+      if (full_tile) {
 #pragma unroll
-      for (int j = 0; j < kPerThread; ++j) {
-        const int s = ctid + j * (kConsumerWarps * 32);
-        mu[j] = (TIN)0;
-        mv[j] = (TIN)0;
-        if (s < r.nsamp) {
-          const int64_t bend = r.b0 + (int64_t)(s + 1) * 3 * (int64_t)sizeof(TIN);
-          if (bend <= r.a1) {
-            const TIN* p = reinterpret_cast<const TIN*>(sbuf) + 3 * s;
-            mu[j] = p[1];
-            mv[j] = p[2];
-          } else {  // the last bytes of a tensor whose size is not a multiple of 16
-            const TIN* p = reinterpret_cast<const TIN*>(gbase) + 3 * (sample0 + s);
-            mu[j] = p[1];
-            mv[j] = p[2];
+        for (int j = 0; j < kPerThread; ++j) {
+          const int s = ctid + j * (kConsumerWarps * 32);
+          mu[j] = sbuf[3 * s + 1];
+          mv[j] = sbuf[3 * s + 2];
+        }
+      } else {
+        const int64_t a1 = min((b0 + (int64_t)nsamp * kSampleBytes + 15) & ~(int64_t)15, total16);
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+          const int s = ctid + j * (kConsumerWarps * 32);
+          mu[j] = (TIN)0;
+          mv[j] = (TIN)0;
+          if (s < nsamp) {
+            if (b0 + (int64_t)(s + 1) * kSampleBytes <= a1) {
+              mu[j] = sbuf[3 * s + 1];
+              mv[j] = sbuf[3 * s + 2];
+            } else {  // the last bytes of a tensor whose size is not a multiple of 16
+              const TIN* p = reinterpret_cast<const TIN*>(gbase) + 3 * (scur + s);
+              mu[j] = p[1];
+              mv[j] = p[2];
+            }
           }
         }
       }
 #pragma unroll
       for (int j = 0; j < kPerThread; ++j) {
         const int s = ctid + j * (kConsumerWarps * 32);
-        if (s < r.nsamp) {
-          int cell;
-          const int st = decode_cell(mu[j], mv[j], Wf, Hf, a.W, a.H, cell);
-          nv += (st == kOk);
-          if (st == kOk) atomicAdd(&s_hist[cell], 1u);
-          if (st == kOutOfRange) bad = 1;
-          const int64_t g = sample0 + s;
-          if (want_assign) a.assign0[g] = (st == kOk) ? (uint16_t)s_lut[cell] : (uint16_t)VET_MISSING;
-          if (a.cell16) a.cell16[g] = (st == kOk) ? (uint16_t)cell : (uint16_t)0xFFFF;
-          if (a.cell32) a.cell32[g] = cell;
+        if (full_tile || s < nsamp) {
+          bool ok = unit_range_fast(mu[j]) && unit_range_fast(mv[j]);
+          if (!ok) {
+            const int st = classify_slow(mu[j], mv[j]);
+            ok = st == kOk;
+            if (st == kOutOfRange) bad = 1;
+          }
+          int cell = 0;
+          if (ok) {
+            cell = pixel_of(mv[j], Hf, a.H) * W1 + pixel_of(mu[j], Wf, a.W);
+            atomicAdd(&s_hist[cell], 1u);
+            ++nv;
+          }
+          if (ASSIGN) out_assign[s] = ok ? (uint16_t)s_lut[cell] : (uint16_t)VET_MISSING;
+          if (CELLS == 1) out_c16[s] = ok ? (uint16_t)cell : (uint16_t)0xFFFF;
+          if (CELLS == 2) out_c32[s] = ok ? cell : -1;
         }
       }
       __syncwarp();
