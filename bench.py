@@ -223,6 +223,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=device)
 
     peaks = {}
@@ -242,17 +244,15 @@ def main():
                         per_k=None,
                         hist0=torch.empty((F, T0), dtype=torch.float64, device=device),
                         assign0=torch.empty((F, U), dtype=torch.uint16, device=device))
-    rows = torch.empty((F, 1 + T0), dtype=torch.float64, device=device)
     from viewport_entropy_toolkit_b200.distributed import all_gather_rows
 
     def step():
         eng.spatial(packed, out=out)
         if args.transition:
             eng.transition(packed, want_per_k=False, want_pairs0=False)
-        if world > 1:  # the path's only exchange: one all-gather of the per-frame result rows
-            rows[:, 0] = out.entropy
-            rows[:, 1:] = out.hist0
-            all_gather_rows(rows, [F] * world)
+        if world > 1:  # the path's only exchange: the all-gather of the per-frame results (no staging copies)
+            all_gather_rows(out.entropy, [F] * world)
+            all_gather_rows(out.hist0, [F] * world)
 
     for _ in range(args.warmup):
         step()

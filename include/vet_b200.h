@@ -75,6 +75,10 @@ typedef struct {
   const double* const* centres; /* [K] pointers to [T_k,3] lattice centres (generate_fibonacci_lattice, DU:25-56) */
   const double* lon_by_px;      /* [W+1] degrees, after round(.,1) and the wrap quirk (DU:390-395) */
   const double* lat_by_py;      /* [H+1] degrees, after round(.,1) and the wrap quirk (DU:391-397) */
+  /* Optional: explicit number of tile centres per tile set, for ARBITRARY tile_centers lists
+   * (the reference's free functions accept any List[Vector], EU:70-151,213-219).  When
+   * non-NULL, T_k = num_tiles[k] (tile_counts[k] is ignored) and `centres` is required. */
+  const int32_t* num_tiles;
 } vet_config;
 
 const char* vet_last_error(void);
@@ -116,6 +120,26 @@ int vet_nearest_tile(vet_handle* h, int k, const double* vec_dev, int64_t n, int
  * w_dev[n,T_k] float64 (0 where the reference's dict has no entry). */
 int vet_tile_weights(vet_handle* h, int k, const double* vec_dev, int64_t n, double* w_dev,
                      void* stream);
+
+/* find_angular_distances (EU:70-87) for n arbitrary vectors: d_dev[n,T_k] = arccos(clip(dot)),
+ * radians (the reference returns [tile_index, distance] pairs; the index is the column). */
+int vet_angular_distances(vet_handle* h, int k, const double* vec_dev, int64_t n, double* d_dev,
+                          void* stream);
+
+/* compute_spatial_entropy (EU:147-211) for frames of ARBITRARY direction vectors:
+ * vec_dev[F,U,3] float64, NaN = absent user.  Same outputs as vet_spatial.  Every
+ * (user, tile) pair is evaluated directly (no cell tables); per-tile sums run in user
+ * order like EU:190-192.  Also the path vet_spatial takes for videos too large for the
+ * cell tables. */
+int vet_spatial_vectors(vet_handle* h, const double* vec_dev, int64_t F, int64_t U,
+                        double* entropy_dev, double* per_k_dev, double* hist0_dev,
+                        uint16_t* assign0_dev, void* stream);
+
+/* compute_transition_entropy (EU:213-332) for frames of arbitrary direction vectors;
+ * same outputs as vet_transition. */
+int vet_transition_vectors(vet_handle* h, const double* vec_dev, int64_t F, int64_t U,
+                           double* entropy_dev, double* per_k_dev, int32_t* prev_count0_dev,
+                           uint16_t* pairs0_dev, int mode, void* stream);
 
 /* Stages 1-3 fused.  SpatialEntropyAnalyzer.compute_entropy (SA:107-164) on
  * packed_dev[F,U,3]:

@@ -364,3 +364,157 @@ def test_properties_at_scale(vet):
     part = ew.spatial(p[:1, :4096].contiguous())
     np.testing.assert_allclose(part.hist0[0].cpu().numpy(), dense.cpu().numpy(), rtol=RTOL, atol=ATOL)
     ew.close()
+
+
+# ---------------------------------------------------------------------------------
+# functional API (reference names, dicts of Vector, arbitrary tile-centre lists)
+# ---------------------------------------------------------------------------------
+def test_functional_api_vs_reference_fixtures(vet):
+    """compute_spatial_entropy / compute_transition_entropy called like the reference's free
+    functions (EU:147-332) on the frames of the live-reference fixtures."""
+    fx = group_keys(load_golden("frames"))
+    for case in ["c_small_w120", "c_small_unw", "c_missing", "c_iid_w"]:
+        c = fx[case]
+        packed, tcs = c["packed"], [int(v) for v in c["tile_counts"]]
+        fov, use_w, pf = float(c["cfg"][0]), bool(c["cfg"][1]), float(c["cfg"][2])
+        cfg = vet.EntropyConfig(fov_angle=fov, use_weight_distribution=use_w, power_factor=pf)
+        vecs, ok = orc.decode_vectors(packed[..., 1], packed[..., 2], W0, H0)
+        for k, n in enumerate(tcs[:2]):
+            centres = vet.generate_fibonacci_lattice(n)
+            for f in range(min(3, packed.shape[0])):
+                d = {f"u{u:05d}": vet.Vector(*vecs[f, u]) for u in range(packed.shape[1]) if ok[f, u]}
+                e, wts, asg = vet.compute_spatial_entropy(d, centres, cfg)
+                np.testing.assert_allclose(e, c["sp_per_k"][k, f], rtol=RTOL, atol=ATOL, equal_nan=True)
+                if k == 0:
+                    assert [asg[key] for key in d] == [int(a) for a in c["sp_assign0"][f][ok[f]]]
+                    ref_hist = c["sp_hist0"][f]
+                    got = np.zeros_like(ref_hist)
+                    idx = {ct: i for i, ct in enumerate(centres)}
+                    for ct, w in wts.items():
+                        got[idx[ct]] = w
+                    np.testing.assert_allclose(got, ref_hist, rtol=RTOL, atol=ATOL)
+                if f + 1 < packed.shape[0]:
+                    d1 = {f"u{u:05d}": vet.Vector(*vecs[f + 1, u]) for u in range(packed.shape[1]) if ok[f + 1, u]}
+                    te, tw, ta = vet.compute_transition_entropy(d, d1, centres, cfg, 120)
+                    np.testing.assert_allclose(te, c["tr_per_k"][k, f], rtol=RTOL, atol=ATOL, equal_nan=True)
+                    if k == 0:
+                        both = ok[f] & ok[f + 1]
+                        assert [list(ta[f"u{u:05d}"]) for u in np.flatnonzero(both)] == c["tr_pairs0"][f][both].tolist()
+
+
+def test_functional_api_arbitrary_centres(vet):
+    """Tile centres that are NOT a Fibonacci lattice (even count, non-unit vectors) and
+    arbitrary user vectors, against the oracle's literal (reference-shaped) layer."""
+    rng = np.random.default_rng(99)
+    centres_np = rng.normal(size=(12, 3)) * rng.uniform(0.5, 2.0, size=(12, 1))
+    centres = [vet.Vector(*c) for c in centres_np]
+    users = rng.normal(size=(30, 3))
+    d0 = {f"p{i}": vet.Vector(*users[i]) for i in range(30)}
+    d1 = {f"p{i}": vet.Vector(*(users[i] + 0.4 * rng.normal(size=3))) for i in range(29, -1, -1) if i % 7}
+    for cfg in (vet.EntropyConfig(fov_angle=100.0, power_factor=1.5), vet.EntropyConfig(use_weight_distribution=False)):
+        e, wts, asg = vet.compute_spatial_entropy(d0, centres, cfg)
+        re, rw, ra = orc.compute_spatial_entropy_literal({k: v.as_tuple() for k, v in d0.items()}, centres_np,
+                                                         cfg.fov_angle, cfg.use_weight_distribution, cfg.power_factor)
+        np.testing.assert_allclose(e, re, rtol=RTOL)
+        assert asg == ra
+        assert {centres.index(c) for c in wts} == set(rw)
+        for ct, w in wts.items():
+            np.testing.assert_allclose(w, rw[centres.index(ct)], rtol=RTOL, atol=1e-14)
+    te, tw, ta = vet.compute_transition_entropy(d0, d1, centres, vet.EntropyConfig(), 120)
+    rte, rtw, rta = orc.compute_transition_entropy_literal({k: v.as_tuple() for k, v in d0.items()},
+                                                           {k: v.as_tuple() for k, v in d1.items()}, centres_np)
+    np.testing.assert_allclose(te, rte, rtol=RTOL, atol=ATOL)
+    assert ta == rta and {centres.index(c): n for c, n in tw.items()} == {int(k): int(v) for k, v in rtw.items()}
+    assert list(ta) == list(rta)   # current-frame dict order
+    v = vet.Vector(0.3, -0.2, 0.9)
+    dist = vet.find_angular_distances(v, centres)
+    ref = orc.find_angular_distances_literal(v.as_tuple(), centres_np)
+    np.testing.assert_allclose(dist, ref, rtol=1e-12, atol=1e-15)
+    assert vet.find_nearest_tile(v, centres) == orc.find_nearest_tile_literal(v.as_tuple(), centres_np)
+    np.testing.assert_allclose(vet.vector_angle_distance(v, centres[3]), ref[3, 1], rtol=1e-12)
+    cw = vet.calculate_tile_weights(v, centres, vet.EntropyConfig(fov_angle=140.0))
+    rw = orc.calculate_tile_weights_literal(v.as_tuple(), centres_np, 140.0, True, 2.0)
+    assert [centres.index(c) for c in cw] == list(rw)   # insertion order = ascending distance
+    with pytest.raises(vet.ValidationError, match="Empty vector dictionary"):
+        vet.compute_spatial_entropy({}, centres, vet.EntropyConfig())
+    with pytest.raises(vet.ValidationError, match="No tile centers"):
+        vet.compute_spatial_entropy(d0, [], vet.EntropyConfig())
+    with pytest.raises(ZeroDivisionError):
+        vet.compute_transition_entropy({"a": v}, {"b": v}, centres)
+
+
+@pytest.mark.parametrize("dims", [(200, 400), (1920, 1080)])
+def test_large_video_direct_mode(vet, dims):
+    """Videos whose cell grid does not fit the shared-memory tables run the direct per-sample
+    path (decode -> vectors -> brute force); results must match the oracle all the same."""
+    W, H = dims
+    p = synth(4, 300, 4242, iid=True, missing=0.1, dtype=np.float64)
+    for use_w, tcs in ((True, [20, 50]), (False, [200])):
+        e = engine(vet, tcs, fov=100.0, use_w=use_w, W=W, H=H)
+        sp = e.spatial(dev(p))
+        assert e.poll_flags() == 0
+        ref = orc.spatial_analyzer(p, W, H, tcs, 100.0, use_w, 2.0)
+        assert np.array_equal(sp.assign0.cpu().numpy(), ref["assign0"])
+        np.testing.assert_allclose(sp.hist0.cpu().numpy(), ref["hist0"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(sp.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL)
+        tr = e.transition(dev(p))
+        tref = orc.transition_analyzer(p, W, H, tcs)
+        assert np.array_equal(tr.pairs0.cpu().numpy(), tref["pairs0"])
+        assert np.array_equal(tr.prev_count0.cpu().numpy(), tref["prev_count0"])
+        np.testing.assert_allclose(tr.entropy.cpu().numpy(), tref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+        h = e.spatial_host(p)
+        assert np.array_equal(h["entropy"], sp.entropy.cpu().numpy())
+        e.close()
+
+
+def test_analyzers_end_to_end_vs_reference(vet, tmp_path):
+    """process_directory -> compute_entropy of both analyzers on CSV directories, against the
+    rows the reference's analyzers produced (fixtures), incl. the ragged directory."""
+    import pandas as pd
+    a = load_golden("analyzers")
+    g = group_keys(a)
+    rag = tmp_path / "ragged"; rag.mkdir()
+    pd.DataFrame({"time": [5.0, 5.1, 5.2, 5.3], "2dmu": [.5, .5, .6, .7], "2dmv": [.5] * 4}).to_csv(rag / "a.csv", index=False)
+    pd.DataFrame({"time": [9.0, 9.1, 9.14, 9.3], "2dmu": [.1, .2, .3, .4], "2dmv": [.2] * 4}).to_csv(rag / "b.csv", index=False)
+    pd.DataFrame({"time": [1.2, 1.0, 1.1], "2dmu": [.9] * 3, "2dmv": [.9] * 3}).to_csv(rag / "c.csv", index=False)
+    d10 = tmp_path / "dir10"; d10.mkdir()
+    names = [str(n) for n in g["dir10_default"]["order"]]
+    for n in names:
+        arr = a[f"dir10/{n}"]
+        pd.DataFrame({"time": arr[:, 0], "2dmu": arr[:, 1], "2dmv": arr[:, 2]}).to_csv(d10 / f"{n}.csv", index=False)
+    runs = [("ragged", rag, ["a", "b", "c"], [20], vet.EntropyConfig()),
+            ("dir10_default", d10, names, [20, 50], vet.EntropyConfig()),
+            ("dir10_unw", d10, names[::-1], [50, 20, 200], vet.EntropyConfig(fov_angle=90.0, use_weight_distribution=False))]
+    for tag, directory, order, tcs, ec in runs:
+        cfg = vet.AnalyzerConfig(tile_counts=tcs, output_dir=tmp_path / "out", entropy_config=ec)
+        sa = vet.SpatialEntropyAnalyzer(cfg)
+        sa.process_directory(directory, order=order)
+        df = sa.compute_entropy()
+        ref = g[tag]
+        assert np.array_equal(df["time"].to_numpy(), ref["sp_time"])
+        np.testing.assert_allclose(df["entropy"].to_numpy(), ref["sp_entropy"], rtol=RTOL, atol=ATOL)
+        centres = sa._fibonacci_vectors[tcs[0]]
+        for r in range(len(df)):
+            hist = np.zeros(len(centres))
+            for ct, w in df["tile_weights"][r].items():
+                hist[centres.index(ct)] = w
+            np.testing.assert_allclose(hist, ref["sp_hist0"][r], rtol=RTOL, atol=ATOL)
+            asg = np.full(len(order), 0xFFFF)
+            for k, t in df["tile_assignments"][r].items():
+                asg[order.index(k)] = t
+            assert np.array_equal(asg, ref["sp_assign0"][r])
+        ta = vet.TransitionEntropyAnalyzer(cfg)
+        ta.process_directory(directory, order=order)
+        if tag == "ragged":   # the last pair has one common user -> NaN, no exception
+            tdf = ta.compute_entropy()
+        else:
+            tdf = ta.compute_entropy()
+        assert np.array_equal(tdf["time"].to_numpy(), ref["tr_time"])
+        np.testing.assert_allclose(tdf["entropy"].to_numpy(), ref["tr_entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+        for r in range(len(tdf)):
+            pc = np.zeros(len(centres), dtype=np.int64)
+            for ct, w in tdf["tile_weights"][r].items():
+                pc[centres.index(ct)] = w
+            assert np.array_equal(pc, ref["tr_prev_count0"][r])
+    sa.create_visualization("e2e_test")
+    assert (tmp_path / "out" / "e2e_test.csv").exists()

@@ -10,6 +10,10 @@ from .config import (AnalyzerConfig, EntropyConfig, VisualizationConfig, DEFAULT
                      DEFAULT_TILE_COUNTS, DEFAULT_OUTPUT_FORMATS)
 from .engine import Engine, SpatialResult, TransitionResult, UnsupportedConfigurationError, get_engine
 from .analyzers import SpatialEntropyAnalyzer, TransitionEntropyAnalyzer
+from . import utilities
+from .utilities import (generate_fibonacci_lattice, normalize_to_pixel, pixel_to_spherical, validate_video_dimensions,
+                        vector_angle_distance, find_angular_distances, find_nearest_tile, calculate_tile_weights,
+                        compute_spatial_entropy, compute_transition_entropy)
 
 __version__ = "0.1.0"
 __all__ = [
@@ -18,4 +22,7 @@ __all__ = [
     "DEFAULT_VIDEO_DIMENSIONS", "DEFAULT_TILE_COUNTS", "DEFAULT_OUTPUT_FORMATS",
     "Engine", "SpatialResult", "TransitionResult", "UnsupportedConfigurationError", "get_engine",
     "SpatialEntropyAnalyzer", "TransitionEntropyAnalyzer",
+    "generate_fibonacci_lattice", "normalize_to_pixel", "pixel_to_spherical", "validate_video_dimensions",
+    "vector_angle_distance", "find_angular_distances", "find_nearest_tile", "calculate_tile_weights",
+    "compute_spatial_entropy", "compute_transition_entropy",
 ]

@@ -38,6 +38,7 @@ class VetConfig(C.Structure):
         ("centres", C.POINTER(C.POINTER(C.c_double))),
         ("lon_by_px", C.POINTER(C.c_double)),
         ("lat_by_py", C.POINTER(C.c_double)),
+        ("num_tiles", C.POINTER(C.c_int32)),
     ]
 
 
@@ -56,6 +57,9 @@ SYMBOLS = {
     "vet_decode": (C.c_int, [_P, _P, C.c_int, _I64, _P, _P, _P]),
     "vet_nearest_tile": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P]),
     "vet_tile_weights": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P]),
+    "vet_angular_distances": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P]),
+    "vet_spatial_vectors": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, _P]),
+    "vet_transition_vectors": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, C.c_int, _P]),
     "vet_spatial": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, _P]),
     "vet_transition": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, C.c_int, _P]),
     "vet_spatial_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P]),

@@ -20,6 +20,7 @@
 #include "vet_stream_tma.cuh"
 #include "vet_tables.cuh"
 #include "vet_transition.cuh"
+#include "vet_vectors.cuh"
 #include "vet_whist.cuh"
 
 namespace {
@@ -47,7 +48,8 @@ struct TileSet {
   int n = 0;  // tile_count as configured
   int T = 0;  // number of lattice points
   std::vector<double> h_centres;  // [T,3]
-  double* d_unit = nullptr;       // [T,3] centres / ||centre||
+  std::vector<double> h_unit;     // [T,3] centres / ||centre||
+  double* d_unit = nullptr;       // same on the device
   uint16_t* d_lut = nullptr;      // [C]
   uint8_t* d_lut8 = nullptr;      // [C] same table in bytes when T <= 255 (halves the shared-memory LUT)
   std::vector<uint16_t> h_lut;
@@ -89,6 +91,10 @@ struct vet_handle {
   uint32_t* d_nvalid = nullptr;  // [frames] present users per frame
   size_t nvalid_bytes = 0;
   uint32_t* d_work = nullptr;    // work counters of the dynamic schedulers
+  bool direct_only = false;      // video too large for the cell tables: packed input goes decode -> vectors path
+  uint16_t* d_identity = nullptr;  // [maxT] identity LUT (vectors path feeds tile indices to k_transition)
+  void* d_vscratch[3] = {nullptr, nullptr, nullptr};  // idx[F,U] i32, per_k[K,F] f64, vec[F,U,3] f64
+  size_t vscratch_bytes[3] = {0, 0, 0};
   void* d_cells = nullptr;
   size_t cells_bytes = 0;
   uint32_t* d_tables = nullptr;
@@ -219,6 +225,12 @@ struct LaunchTimer {  // records an event pair around one kernel launch when pro
   }
 };
 
+int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st);
+int spatial_direct(vet_handle* h, const void* packed, int dtype, int64_t F, int64_t U, double* entropy, double* per_k,
+                   double* hist0, uint16_t* assign0, cudaStream_t st);
+int transition_direct(vet_handle* h, const void* packed, int dtype, int64_t F, int64_t U, double* entropy, double* per_k,
+                      int32_t* prev_count0, uint16_t* pairs0, int mode, cudaStream_t st);
+
 constexpr size_t kStaticSmemSlack = 1024;
 constexpr int kMaxT = 16384;
 
@@ -308,19 +320,26 @@ int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& 
   return VET_OK;
 }
 
-int build_tile_set(vet_handle* h, TileSet& t) {
+// unit tile centres c/||c|| (EU:59), uploaded as t.d_unit and kept in t.h_unit
+int build_unit_centres(TileSet& t) {
   const int T = t.T;
-  std::vector<double> unit((size_t)T * 3);
+  t.h_unit.resize((size_t)T * 3);
   for (int i = 0; i < T; ++i) {
     const double x = t.h_centres[3 * i], y = t.h_centres[3 * i + 1], z = t.h_centres[3 * i + 2];
     // np.linalg.norm == sqrt(dot(x,x)), ddot as an FMA chain
     const double nrm = std::sqrt(std::fma(z, z, std::fma(y, y, x * x)));
     if (!(nrm > 0)) return fail(VET_ERR_INVALID_ARG, "Vector cannot have zero length (tile %d)", i);
-    unit[3 * i] = x / nrm;
-    unit[3 * i + 1] = y / nrm;
-    unit[3 * i + 2] = z / nrm;
+    t.h_unit[3 * i] = x / nrm;
+    t.h_unit[3 * i + 1] = y / nrm;
+    t.h_unit[3 * i + 2] = z / nrm;
   }
-  if (int rc = upload(&t.d_unit, unit.data(), unit.size())) return rc;
+  return upload(&t.d_unit, t.h_unit.data(), t.h_unit.size());
+}
+
+int build_tile_set(vet_handle* h, TileSet& t) {
+  const int T = t.T;
+  if (int rc = build_unit_centres(t)) return rc;
+  const std::vector<double>& unit = t.h_unit;
   VET_CUDA(cudaMalloc((void**)&t.d_lut, (size_t)h->C * sizeof(uint16_t)));
   const size_t smem = (size_t)T * 3 * sizeof(double);
   VET_CUDA(cudaFuncSetAttribute(vet::k_nearest<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -619,6 +638,11 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
     TileSet& t = h->ts[k];
     t.n = cfg->tile_counts[k];
     t.T = 2 * (t.n / 2) + 1;  // DU:43-45
+    if (cfg->num_tiles) {
+      if (!cfg->centres || !cfg->centres[k] || cfg->num_tiles[k] <= 0)
+        return fail(VET_ERR_INVALID_ARG, "No tile centers provided");  // EU:170-171
+      t.T = cfg->num_tiles[k];
+    }
     if (t.T > kMaxT) return fail(VET_ERR_UNSUPPORTED, "tile_count %d gives %d tiles; at most %d supported", t.n, t.T, kMaxT);
     h->maxT = std::max(h->maxT, t.T);
     if (cfg->centres && cfg->centres[k])
@@ -626,11 +650,11 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
     else
       t.h_centres = make_lattice(t.n);
   }
-  // table regime: the per-frame cell histogram (u32) and the LUT must fit in shared memory
-  if (stream_smem_bytes(h) + kStaticSmemSlack > h->smem_optin || epilogue_smem_bytes(h) + kStaticSmemSlack > h->smem_optin)
-    return fail(VET_ERR_UNSUPPORTED,
-                "video %dx%d has %lld cells; the shared-memory cell histogram supports at most ~%lld cells on this device",
-                h->W, h->H, (long long)h->C, (long long)((h->smem_optin - kStaticSmemSlack) / 6));
+  // table regime: the per-frame cell histogram (u32) and the LUT must fit in shared memory;
+  // larger videos use the direct per-sample path (decode -> vectors)
+  h->direct_only = stream_smem_bytes(h) + kStaticSmemSlack > h->smem_optin ||
+                   epilogue_smem_bytes(h) + kStaticSmemSlack > h->smem_optin;
+  if (h->C >= ((int64_t)1 << 31)) return fail(VET_ERR_UNSUPPORTED, "video %dx%d has too many cells", h->W, h->H);
 
   std::vector<double> lon, lat;
   if (cfg->lon_by_px && cfg->lat_by_py) {
@@ -658,29 +682,34 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   if (int rc = upload(&h->d_sinT, sinT.data(), sinT.size())) return rc;
   if (int rc = upload(&h->d_sinP, sinP.data(), sinP.size())) return rc;
   if (int rc = upload(&h->d_cosP, cosP.data(), cosP.size())) return rc;
-  VET_CUDA(cudaMalloc((void**)&h->d_cellvec, (size_t)h->C * 3 * sizeof(double)));
   VET_CUDA(cudaMalloc((void**)&h->d_flags, sizeof(uint32_t)));
   VET_CUDA(cudaMemset(h->d_flags, 0, sizeof(uint32_t)));
   VET_CUDA(cudaMalloc((void**)&h->d_work, sizeof(uint32_t) * vet::kMaxTileCounts));
-  VET_CUDA(cudaFuncSetAttribute(vet::k_whist, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                vet::kWhStages * vet::kChunkBytes));
-  vet::k_cell_vectors<<<std::min<int64_t>((h->C + 255) / 256, 1024), 256>>>(h->d_cosT, h->d_sinT, h->d_sinP, h->d_cosP,
-                                                                             h->W, h->H, h->d_cellvec);
-  h->launches++;
-  VET_CUDA(cudaGetLastError());
-  for (int k = 0; k < h->K; ++k)
-    if (int rc = build_tile_set(h, h->ts[k])) return rc;
-
-  VET_CUDA(cudaFuncSetAttribute(vet::k_stream_simple<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)stream_smem_bytes(h)));
-  VET_CUDA(cudaFuncSetAttribute(vet::k_stream_simple<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)stream_smem_bytes(h)));
-  VET_CUDA(cudaFuncSetAttribute(vet::k_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)epilogue_smem_bytes(h)));
   {
-    const bool lut8 = h->ts[0].d_lut8 != nullptr;
-    const size_t sm = stream_tma_smem_bytes(h, lut8);
-    if (sm + kStaticSmemSlack <= h->smem_optin) {
+    std::vector<uint16_t> ident(h->maxT);
+    for (int i = 0; i < h->maxT; ++i) ident[i] = (uint16_t)i;
+    if (int rc = upload(&h->d_identity, ident.data(), ident.size())) return rc;
+  }
+  if (h->direct_only) {
+    for (int k = 0; k < h->K; ++k)
+      if (int rc = build_unit_centres(h->ts[k])) return rc;
+  } else {
+    VET_CUDA(cudaMalloc((void**)&h->d_cellvec, (size_t)h->C * 3 * sizeof(double)));
+    VET_CUDA(cudaFuncSetAttribute(vet::k_whist, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  vet::kWhStages * vet::kChunkBytes));
+    vet::k_cell_vectors<<<std::min<int64_t>((h->C + 255) / 256, 1024), 256>>>(h->d_cosT, h->d_sinT, h->d_sinP, h->d_cosP,
+                                                                               h->W, h->H, h->d_cellvec);
+    h->launches++;
+    VET_CUDA(cudaGetLastError());
+    for (int k = 0; k < h->K; ++k)
+      if (int rc = build_tile_set(h, h->ts[k])) return rc;
+    // The attribute is per function, not per handle: always allow the device maximum so that
+    // handles of different configurations can coexist.
+    const size_t sm = h->smem_optin - kStaticSmemSlack;
+    VET_CUDA(cudaFuncSetAttribute(vet::k_stream_simple<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    VET_CUDA(cudaFuncSetAttribute(vet::k_stream_simple<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    VET_CUDA(cudaFuncSetAttribute(vet::k_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    {
 #define VET_SMEM_ATTR(...) VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tma<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm))
       VET_SMEM_ATTR(float, uint8_t, true, 0);
       VET_SMEM_ATTR(float, uint16_t, true, 0);
@@ -722,6 +751,8 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_nvalid);
   cudaFree(h->d_work);
   cudaFree(h->d_cells);
+  cudaFree(h->d_identity);
+  for (void* p : h->d_vscratch) cudaFree(p);
   cudaFree(h->d_tables);
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);
@@ -748,6 +779,7 @@ extern "C" int vet_lattice(const vet_handle* h, int k, double* centres_host) {
 
 extern "C" int vet_cell_lut(const vet_handle* h, int k, uint16_t* lut_host) {
   if (!h || !lut_host || k < 0 || k >= h->K) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (h->direct_only) return fail(VET_ERR_UNSUPPORTED, "no cell tables for a %dx%d video (direct per-sample mode)", h->W, h->H);
   std::memcpy(lut_host, h->ts[k].h_lut.data(), h->ts[k].h_lut.size() * sizeof(uint16_t));
   return VET_OK;
 }
@@ -810,6 +842,7 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
   if (!packed_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->direct_only) return spatial_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, hist0_dev, assign0_dev, st);
   const int64_t fb = frames_per_batch(h, F, U, false);
   if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->Cpad * 4)) return rc;
   if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
@@ -836,34 +869,13 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
   if (U >= 0xFFFFFFFFll) return fail(VET_ERR_UNSUPPORTED, "too many users");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->direct_only)
+    return transition_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, prev_count0_dev, pairs0_dev, mode, st);
   const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
   const size_t csz = h->C <= 65535 ? 2 : 4;
   if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->Cpad * 4)) return rc;
   if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
   if (int rc = grow(&h->d_cells, &h->cells_bytes, (size_t)fb * U * csz)) return rc;
-  // pair table: capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
-  const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)h->maxT * h->maxT);
-  uint32_t cap = 1024;
-  while ((uint64_t)cap < 2 * max_pairs) cap <<= 1;
-  const size_t tile_bytes = (size_t)h->maxT * (8 + 4 * 4);
-  const size_t smem_tab = tile_bytes + (size_t)cap * 16 + 64;
-  const bool in_smem = smem_tab + kStaticSmemSlack <= h->smem_optin;
-  int blocks = (int)std::min<int64_t>(F - 1, (int64_t)h->sm_count * (in_smem ? 1 : 2));
-  if (!in_smem) {
-    const size_t words = (size_t)blocks * 4 * cap;
-    if (h->tables_words < words) {
-      if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
-      h->d_tables = nullptr;
-      h->tables_words = 0;
-      VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
-      h->tables_words = words;
-    }
-    // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value); kernels leave the tables clean
-    for (int b = 0; b < blocks; ++b) {
-      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
-      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
-    }
-  }
   const size_t esz = dtype == VET_F32 ? 4 : 8;
   const int T0 = h->ts[0].T;
   // batches overlap by one frame (the halo frame of SURVEY 8e)
@@ -888,24 +900,240 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
     a.pairs0 = pairs0_dev ? pairs0_dev + f0 * U * 2 : nullptr;
     a.mode = mode;
     a.flags = h->d_flags;
-    a.cap = cap;
-    a.g_tables = h->d_tables;
-    const int nb = (int)std::min<int64_t>(nf - 1, blocks);
-    if (in_smem) {
-      VET_CUDA(cudaFuncSetAttribute(vet::k_transition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
-      LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
-      vet::k_transition<true><<<nb, 512, smem_tab, st>>>(a, h->maxT);
-    } else {
-      VET_CUDA(cudaFuncSetAttribute(vet::k_transition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(tile_bytes + 64)));
-      LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
-      vet::k_transition<false><<<nb, 512, tile_bytes + 64, st>>>(a, h->maxT);
-    }
-    VET_CUDA(cudaGetLastError());
+    if (int rc = launch_transition(h, a, nf - 1, U, h->maxT, st)) return rc;
     if (nf == F - f0) break;
   }
   return VET_OK;
 }
+
+namespace {
+
+int launch_nearest_i32(vet_handle* h, int k, const double* vec, int64_t n, int32_t* idx, cudaStream_t st) {
+  const TileSet& t = h->ts[k];
+  const size_t smem = (size_t)t.T * 3 * sizeof(double);
+  VET_CUDA(cudaFuncSetAttribute(vet::k_nearest<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = 256;
+  const int64_t rounds = (n + threads / 4 - 1) / (threads / 4);
+  const int blocks = (int)std::min<int64_t>(rounds, (int64_t)h->sm_count * 8);
+  vet::k_nearest<int32_t><<<blocks, threads, smem, st>>>(vec, n, t.d_unit, t.T, idx);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+int spatial_vectors_impl(vet_handle* h, const double* vec, int64_t F, int64_t U, double* entropy, double* per_k,
+                         int64_t per_k_stride, double* hist0, uint16_t* assign0, cudaStream_t st) {
+  const int64_t n = F * U;
+  const bool need_idx = !h->use_weight || assign0;
+  if (need_idx)
+    if (int rc = grow(&h->d_vscratch[0], &h->vscratch_bytes[0], (size_t)n * 4)) return rc;
+  double* pk = per_k;
+  int64_t pk_stride = per_k_stride;
+  if (!pk) {
+    if (int rc = grow(&h->d_vscratch[1], &h->vscratch_bytes[1], (size_t)h->K * F * 8)) return rc;
+    pk = (double*)h->d_vscratch[1];
+    pk_stride = F;
+  }
+  int32_t* idx = (int32_t*)h->d_vscratch[0];
+  for (int k = 0; k < h->K; ++k) {
+    const TileSet& t = h->ts[k];
+    if (!h->use_weight || (k == 0 && assign0)) {
+      if (int rc = launch_nearest_i32(h, k, vec, n, idx, st)) return rc;
+      if (k == 0 && assign0) {
+        vet::k_idx_to_u16<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, st>>>(idx, n, assign0);
+        h->launches++;
+      }
+    }
+    vet::VecSpatialArgs a{};
+    a.vec = vec;
+    a.F = F;
+    a.U = U;
+    a.unit = t.d_unit;
+    a.T = t.T;
+    a.max_d = h->max_d;
+    a.pf = h->pf;
+    a.use_weight = h->use_weight;
+    a.idx = idx;
+    a.per_k = pk + k * pk_stride;
+    a.hist = (k == 0) ? hist0 : nullptr;
+    a.flags = h->d_flags;
+    const size_t smem = (size_t)t.T * 12 + (size_t)vet::kVecChunk * 24 + 16;
+    VET_CUDA(cudaFuncSetAttribute(vet::k_spatial_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vet::k_spatial_vectors<<<(int)std::min<int64_t>(F, (int64_t)h->sm_count * 4), 256, smem, st>>>(a);
+    h->launches++;
+    VET_CUDA(cudaGetLastError());
+  }
+  vet::k_average_rows<<<(int)std::min<int64_t>((F + 255) / 256, 1024), 256, 0, st>>>(pk, h->K, F, pk_stride, entropy);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+int transition_vectors_impl(vet_handle* h, const double* vec, int64_t F, int64_t U, double* entropy, double* per_k,
+                            int64_t per_k_stride, int32_t* prev_count0, uint16_t* pairs0, int mode, cudaStream_t st) {
+  const int64_t n = F * U;
+  if (int rc = grow(&h->d_vscratch[0], &h->vscratch_bytes[0], (size_t)n * 4)) return rc;
+  double* pk = per_k;
+  int64_t pk_stride = per_k_stride;
+  if (!pk) {
+    if (int rc = grow(&h->d_vscratch[1], &h->vscratch_bytes[1], (size_t)h->K * (F - 1) * 8)) return rc;
+    pk = (double*)h->d_vscratch[1];
+    pk_stride = F - 1;
+  }
+  int32_t* idx = (int32_t*)h->d_vscratch[0];
+  for (int k = 0; k < h->K; ++k) {
+    if (int rc = launch_nearest_i32(h, k, vec, n, idx, st)) return rc;
+    vet::TransitionArgs a{};
+    a.cell32 = idx;  // tile indices play the role of cell ids, mapped through the identity LUT
+    a.F = F;
+    a.U = U;
+    a.K = 1;
+    a.T[0] = h->ts[k].T;
+    a.lut[0] = h->d_identity;
+    a.entropy = pk + k * pk_stride;  // K == 1: the "mean" is the tile count's own entropy
+    a.per_k = nullptr;
+    a.prev_count0 = (k == 0) ? prev_count0 : nullptr;
+    a.pairs0 = (k == 0) ? pairs0 : nullptr;
+    a.mode = mode;
+    a.flags = h->d_flags;
+    if (int rc = launch_transition(h, a, F - 1, U, h->ts[k].T, st)) return rc;
+  }
+  vet::k_average_rows<<<(int)std::min<int64_t>((F - 1 + 255) / 256, 1024), 256, 0, st>>>(pk, h->K, F - 1, pk_stride, entropy);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+// decode a frame batch of packed samples into the vector scratch (direct mode)
+int decode_batch(vet_handle* h, const void* packed, int dtype, int64_t n, cudaStream_t st) {
+  if (int rc = grow(&h->d_vscratch[2], &h->vscratch_bytes[2], (size_t)n * 24)) return rc;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
+  if (dtype == VET_F32)
+    vet::k_decode<float><<<blocks, 256, 0, st>>>((const float*)packed, n, h->W, h->H, h->d_cosT, h->d_sinT, h->d_sinP,
+                                                 h->d_cosP, (double*)h->d_vscratch[2], nullptr, h->d_flags);
+  else
+    vet::k_decode<double><<<blocks, 256, 0, st>>>((const double*)packed, n, h->W, h->H, h->d_cosT, h->d_sinT, h->d_sinP,
+                                                  h->d_cosP, (double*)h->d_vscratch[2], nullptr, h->d_flags);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+int spatial_direct(vet_handle* h, const void* packed, int dtype, int64_t F, int64_t U, double* entropy, double* per_k,
+                   double* hist0, uint16_t* assign0, cudaStream_t st) {
+  const size_t esz = dtype == VET_F32 ? 4 : 8;
+  const int T0 = h->ts[0].T;
+  const int64_t fb = std::min<int64_t>(F, std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / ((size_t)U * 24))));
+  for (int64_t f0 = 0; f0 < F; f0 += fb) {
+    const int64_t nf = std::min(fb, F - f0);
+    if (int rc = decode_batch(h, (const char*)packed + (size_t)f0 * U * 3 * esz, dtype, nf * U, st)) return rc;
+    if (int rc = spatial_vectors_impl(h, (const double*)h->d_vscratch[2], nf, U, entropy + f0, per_k ? per_k + f0 : nullptr, F,
+                                      hist0 ? hist0 + f0 * T0 : nullptr, assign0 ? assign0 + f0 * U : nullptr, st))
+      return rc;
+  }
+  return VET_OK;
+}
+
+int transition_direct(vet_handle* h, const void* packed, int dtype, int64_t F, int64_t U, double* entropy, double* per_k,
+                      int32_t* prev_count0, uint16_t* pairs0, int mode, cudaStream_t st) {
+  const size_t esz = dtype == VET_F32 ? 4 : 8;
+  const int T0 = h->ts[0].T;
+  const int64_t fb = std::min<int64_t>(F, std::max<int64_t>(2, (int64_t)(((size_t)1 << 30) / ((size_t)U * 24))));
+  for (int64_t f0 = 0; f0 < F - 1; f0 += fb - 1) {  // batches overlap by the halo frame
+    const int64_t nf = std::min(fb, F - f0);
+    if (int rc = decode_batch(h, (const char*)packed + (size_t)f0 * U * 3 * esz, dtype, nf * U, st)) return rc;
+    if (int rc = transition_vectors_impl(h, (const double*)h->d_vscratch[2], nf, U, entropy + f0,
+                                         per_k ? per_k + f0 : nullptr, F - 1, prev_count0 ? prev_count0 + f0 * T0 : nullptr,
+                                         pairs0 ? pairs0 + f0 * U * 2 : nullptr, mode, st))
+      return rc;
+    if (nf == F - f0) break;
+  }
+  return VET_OK;
+}
+
+}  // namespace
+
+extern "C" int vet_angular_distances(vet_handle* h, int k, const double* vec_dev, int64_t n, double* d_dev, void* stream) {
+  if (!h || k < 0 || k >= h->K || n < 0 || (n > 0 && (!vec_dev || !d_dev))) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return VET_OK;
+  DeviceGuard guard(h->device);
+  const TileSet& t = h->ts[k];
+  const int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)h->sm_count * 8);
+  vet::k_angular_distances<<<blocks, 256, 0, (cudaStream_t)stream>>>(vec_dev, n, t.d_unit, t.T, d_dev);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+extern "C" int vet_spatial_vectors(vet_handle* h, const double* vec_dev, int64_t F, int64_t U, double* entropy_dev,
+                                   double* per_k_dev, double* hist0_dev, uint16_t* assign0_dev, void* stream) {
+  if (!h || F < 0 || U < 0) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (F == 0) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:168-169
+  if (!vec_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  DeviceGuard guard(h->device);
+  return spatial_vectors_impl(h, vec_dev, F, U, entropy_dev, per_k_dev, F, hist0_dev, assign0_dev, (cudaStream_t)stream);
+}
+
+extern "C" int vet_transition_vectors(vet_handle* h, const double* vec_dev, int64_t F, int64_t U, double* entropy_dev,
+                                      double* per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode,
+                                      void* stream) {
+  if (!h || F < 0 || U < 0) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
+  if (F <= 1) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:239-240
+  if (!vec_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  if (U >= 0xFFFFFFFFll) return fail(VET_ERR_UNSUPPORTED, "too many users");
+  DeviceGuard guard(h->device);
+  return transition_vectors_impl(h, vec_dev, F, U, entropy_dev, per_k_dev, F - 1, prev_count0_dev, pairs0_dev, mode,
+                                 (cudaStream_t)stream);
+}
+
+namespace {
+
+// Sizes the (prev,cur) pair tables, picks the shared- or global-memory variant and launches
+// k_transition for `rows` frame pairs.
+int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st) {
+  // capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
+  const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)Tmax * Tmax);
+  uint32_t cap = 1024;
+  while ((uint64_t)cap < 2 * max_pairs) cap <<= 1;
+  const size_t tile_bytes = (size_t)Tmax * (8 + 4 * 4);
+  const size_t smem_tab = tile_bytes + (size_t)cap * 16 + 64;
+  const bool in_smem = smem_tab + kStaticSmemSlack <= h->smem_optin;
+  const int blocks = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * (in_smem ? 1 : 2));
+  if (!in_smem) {
+    const size_t words = (size_t)blocks * 4 * cap;
+    if (h->tables_words < words) {
+      if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
+      h->d_tables = nullptr;
+      h->tables_words = 0;
+      VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
+      h->tables_words = words;
+    }
+    // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value); kernels leave the tables clean
+    for (int b = 0; b < blocks; ++b) {
+      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+    }
+  }
+  a.cap = cap;
+  a.g_tables = h->d_tables;
+  if (in_smem) {
+    VET_CUDA(cudaFuncSetAttribute(vet::k_transition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
+    LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+    vet::k_transition<true><<<blocks, 512, smem_tab, st>>>(a, Tmax);
+  } else {
+    VET_CUDA(cudaFuncSetAttribute(vet::k_transition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(tile_bytes + 64)));
+    LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+    vet::k_transition<false><<<blocks, 512, tile_bytes + 64, st>>>(a, Tmax);
+  }
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+}  // namespace
 
 extern "C" int vet_poll_flags(vet_handle* h, void* stream, uint32_t* flags) {
   if (!h || !flags) return fail(VET_ERR_INVALID_ARG, "null argument");
@@ -969,6 +1197,34 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
   if (!packed_host || !entropy_host) return fail(VET_ERR_INVALID_ARG, "null buffer");
   DeviceGuard guard(h->device);
   const size_t esz = dtype == VET_F32 ? 4 : 8;
+  if (h->direct_only) {  // large-video mode: plain upload, direct kernels, download
+    const int T0d = h->ts[0].T;
+    void* d_in = nullptr;
+    double *d_e = nullptr, *d_p = nullptr, *d_h = nullptr;
+    uint16_t* d_a = nullptr;
+    VET_CUDA(cudaMalloc(&d_in, (size_t)F * U * 3 * esz));
+    VET_CUDA(cudaMalloc((void**)&d_e, (size_t)F * 8));
+    if (per_k_host) VET_CUDA(cudaMalloc((void**)&d_p, (size_t)F * h->K * 8));
+    if (hist0_host) VET_CUDA(cudaMalloc((void**)&d_h, (size_t)F * T0d * 8));
+    if (assign0_host) VET_CUDA(cudaMalloc((void**)&d_a, (size_t)F * U * 2));
+    cudaMemcpyAsync(d_in, packed_host, (size_t)F * U * 3 * esz, cudaMemcpyHostToDevice, h->s_exec);
+    int rc = spatial_direct(h, d_in, dtype, F, U, d_e, d_p, d_h, d_a, h->s_exec);
+    if (rc == VET_OK) {
+      cudaMemcpyAsync(entropy_host, d_e, (size_t)F * 8, cudaMemcpyDeviceToHost, h->s_exec);
+      if (per_k_host) cudaMemcpyAsync(per_k_host, d_p, (size_t)F * h->K * 8, cudaMemcpyDeviceToHost, h->s_exec);
+      if (hist0_host) cudaMemcpyAsync(hist0_host, d_h, (size_t)F * T0d * 8, cudaMemcpyDeviceToHost, h->s_exec);
+      if (assign0_host) cudaMemcpyAsync(assign0_host, d_a, (size_t)F * U * 2, cudaMemcpyDeviceToHost, h->s_exec);
+    }
+    cudaError_t e = cudaStreamSynchronize(h->s_exec);
+    cudaFree(d_in);
+    cudaFree(d_e);
+    cudaFree(d_p);
+    cudaFree(d_h);
+    cudaFree(d_a);
+    if (rc != VET_OK) return rc;
+    if (e != cudaSuccess) return fail(VET_ERR_CUDA, "host-buffer pipeline failed: %s", cudaGetErrorString(e));
+    return VET_OK;
+  }
   const int64_t fb = host_batch_frames(F, U, esz);
   const size_t in_bytes = (size_t)fb * U * 3 * esz;
   if (h->in_bytes < in_bytes) {

@@ -66,9 +66,11 @@ class Engine:
 
     def __init__(self, video_width: int, video_height: int, tile_counts: Sequence[int],
                  entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None,
-                 native_tables: bool = False):
+                 native_tables: bool = False, centres: Optional[Sequence[np.ndarray]] = None):
         """native_tables=True lets the library derive the lattice and axis tables itself
-        (libm) instead of receiving the numpy-made ones; used by tests to show both agree."""
+        (libm) instead of receiving the numpy-made ones; used by tests to show both agree.
+        centres: optional list of [T_k,3] arrays of ARBITRARY tile centres (the reference's
+        free functions take any List[Vector]); tile_counts is then only a label."""
         self._h = None
         lib = N.load_library()
         if not torch.cuda.is_available():
@@ -89,7 +91,13 @@ class Engine:
         if not self.tile_counts or any(c <= 0 for c in self.tile_counts):
             raise ValidationError("Tile counts must be positive")
         K = len(self.tile_counts)
-        self._centres = [np.ascontiguousarray(_tables.fibonacci_lattice(c)) for c in self.tile_counts]
+        if centres is not None:
+            if len(centres) != K or any(len(c) == 0 for c in centres):
+                raise ValidationError("No tile centers provided")  # EU:170-171
+            self._centres = [np.ascontiguousarray(np.asarray(c, dtype=np.float64).reshape(-1, 3)) for c in centres]
+        else:
+            self._centres = [np.ascontiguousarray(_tables.fibonacci_lattice(c)) for c in self.tile_counts]
+        ntiles = (C.c_int32 * K)(*[len(c) for c in self._centres]) if centres is not None else None
         lon, lat = _tables.axis_tables(self.video_width, self.video_height)
         tc = (C.c_int32 * K)(*self.tile_counts)
         cptrs = (C.POINTER(C.c_double) * K)(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in self._centres])
@@ -99,7 +107,8 @@ class Engine:
             use_weight_distribution=int(bool(ec.use_weight_distribution)),
             centres=None if native_tables else cptrs,
             lon_by_px=None if native_tables else lon.ctypes.data_as(C.POINTER(C.c_double)),
-            lat_by_py=None if native_tables else lat.ctypes.data_as(C.POINTER(C.c_double)))
+            lat_by_py=None if native_tables else lat.ctypes.data_as(C.POINTER(C.c_double)),
+            num_tiles=ntiles)
         h = C.c_void_p()
         _check(lib.vet_create(C.byref(h), C.byref(cfg)))
         self._h = h
@@ -205,6 +214,52 @@ class Engine:
         w = torch.empty(v.shape[:-1] + (self.num_tiles[k],), dtype=torch.float64, device=self.device)
         _check(self._lib.vet_tile_weights(self._h, k, v.data_ptr(), n, w.data_ptr(), self._stream()))
         return w
+
+    def angular_distances(self, vectors: torch.Tensor, k: int = 0) -> torch.Tensor:
+        """find_angular_distances (EU:70-87) as [..., T_k] float64 radians."""
+        v = vectors.to(device=self.device, dtype=torch.float64).contiguous()
+        n = v.numel() // 3
+        d = torch.empty(v.shape[:-1] + (self.num_tiles[k],), dtype=torch.float64, device=self.device)
+        _check(self._lib.vet_angular_distances(self._h, k, v.data_ptr(), n, d.data_ptr(), self._stream()))
+        return d
+
+    def spatial_vectors(self, vectors: torch.Tensor, want_per_k: bool = True, want_hist0: bool = True,
+                        want_assign0: bool = True) -> SpatialResult:
+        """compute_spatial_entropy (EU:147-211) on vectors[F,U,3] float64 (NaN = absent user)."""
+        v = vectors.to(device=self.device, dtype=torch.float64).contiguous()
+        if v.dim() != 3 or v.shape[-1] != 3:
+            raise ValueError("vectors must be [F, U, 3]")
+        F, U = int(v.shape[0]), int(v.shape[1])
+        K, T0, dev = len(self.tile_counts), self.num_tiles[0], self.device
+        out = SpatialResult(
+            entropy=torch.empty(F, dtype=torch.float64, device=dev),
+            per_k=torch.empty((K, F), dtype=torch.float64, device=dev) if want_per_k else None,
+            hist0=torch.empty((F, T0), dtype=torch.float64, device=dev) if want_hist0 else None,
+            assign0=torch.empty((F, U), dtype=torch.uint16, device=dev) if want_assign0 else None)
+        _check(self._lib.vet_spatial_vectors(self._h, v.data_ptr(), F, U, out.entropy.data_ptr(), _ptr(out.per_k),
+                                             _ptr(out.hist0), _ptr(out.assign0), self._stream()))
+        return out
+
+    def transition_vectors(self, vectors: torch.Tensor, mode: str = "literal", want_per_k: bool = True,
+                           want_prev_count0: bool = True, want_pairs0: bool = True) -> TransitionResult:
+        """compute_transition_entropy (EU:213-332) on vectors[F,U,3]; row r pairs frames (r, r+1)."""
+        v = vectors.to(device=self.device, dtype=torch.float64).contiguous()
+        if v.dim() != 3 or v.shape[-1] != 3:
+            raise ValueError("vectors must be [F, U, 3]")
+        if mode not in ("literal", "textbook"):
+            raise ValueError("mode must be 'literal' or 'textbook'")
+        F, U = int(v.shape[0]), int(v.shape[1])
+        R = max(F - 1, 0)
+        K, T0, dev = len(self.tile_counts), self.num_tiles[0], self.device
+        out = TransitionResult(
+            entropy=torch.empty(R, dtype=torch.float64, device=dev),
+            per_k=torch.empty((K, R), dtype=torch.float64, device=dev) if want_per_k else None,
+            prev_count0=torch.empty((R, T0), dtype=torch.int32, device=dev) if want_prev_count0 else None,
+            pairs0=torch.empty((R, U, 2), dtype=torch.uint16, device=dev) if want_pairs0 else None)
+        m = N.VET_TRANSITION_LITERAL if mode == "literal" else N.VET_TRANSITION_TEXTBOOK
+        _check(self._lib.vet_transition_vectors(self._h, v.data_ptr(), F, U, out.entropy.data_ptr(), _ptr(out.per_k),
+                                                _ptr(out.prev_count0), _ptr(out.pairs0), m, self._stream()))
+        return out
 
     # -- stages 1-3 fused -----------------------------------------------------------
     def spatial(self, packed: torch.Tensor, want_per_k: bool = True, want_hist0: bool = True,
@@ -324,7 +379,8 @@ _ENGINES: Dict[tuple, Engine] = {}
 
 
 def get_engine(video_width: int, video_height: int, tile_counts: Sequence[int],
-               entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None) -> Engine:
+               entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None,
+               centres: Optional[Sequence[np.ndarray]] = None) -> Engine:
     """Engine cache keyed by (device, configuration): building the tables costs a
     few milliseconds, analyzers and the functional API share them."""
     ec = entropy_config or EntropyConfig()
@@ -332,11 +388,14 @@ def get_engine(video_width: int, video_height: int, tile_counts: Sequence[int],
         raise RuntimeError("viewport_entropy_toolkit_b200 needs a CUDA device; there is no CPU path")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ckey = None if centres is None else tuple(np.ascontiguousarray(c, dtype=np.float64).tobytes() for c in centres)
     key = (idx, int(video_width), int(video_height), tuple(int(c) for c in tile_counts), float(ec.fov_angle),
-           bool(ec.use_weight_distribution), float(ec.power_factor))
+           bool(ec.use_weight_distribution), float(ec.power_factor), ckey)
     eng = _ENGINES.get(key)
     if eng is None:
-        eng = Engine(video_width, video_height, tile_counts, ec, torch.device("cuda", idx))
+        if len(_ENGINES) >= 32:  # bound the cache (functional calls with ad-hoc centre lists)
+            _ENGINES.pop(next(iter(_ENGINES))).close()
+        eng = Engine(video_width, video_height, tile_counts, ec, torch.device("cuda", idx), centres=centres)
         _ENGINES[key] = eng
     return eng
 
