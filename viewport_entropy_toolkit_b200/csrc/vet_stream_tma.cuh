@@ -82,6 +82,71 @@ __device__ __forceinline__ bool unit_range_fast(double v) {
   return (unsigned long long)__double_as_longlong(v) <= 0x3FF0000000000000ull;
 }
 
+// Producer side of the streaming pipeline (one elected lane): walks the CTA's work items
+// and fills the stage ring with 16 B-aligned supersets of each 24 KB tile.
+template <typename TIN>
+__device__ __forceinline__ void stream_producer(const StreamArgs& a, int64_t total_bytes, unsigned char* s_stage,
+                                                unsigned long long* s_full, unsigned long long* s_empty) {
+  constexpr int kSampleBytes = 3 * (int)sizeof(TIN);
+  const int64_t items = a.F * a.chunks_per_frame;
+  const unsigned char* __restrict__ gbase = static_cast<const unsigned char*>(a.packed);
+  const int64_t total16 = total_bytes & ~(int64_t)15;  // bulk copies never read past this
+  uint32_t n = 0;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t f = item / a.chunks_per_frame;
+    const int64_t u0 = (item % a.chunks_per_frame) * a.chunk_users;
+    const int64_t u1 = min(a.U, u0 + a.chunk_users);
+    int64_t b = (f * a.U + u0) * kSampleBytes;
+    const int64_t bend = (f * a.U + u1) * kSampleBytes;
+    for (; b < bend; b += kTileBytes, ++n) {
+      const int stage = n % kStages;
+      mbar_wait(smem_u32(&s_empty[stage]), ((n / kStages) & 1u) ^ 1u);
+      const int64_t a0 = b & ~(int64_t)15;
+      const int64_t a1 = min((min(b + kTileBytes, bend) + 15) & ~(int64_t)15, total16);
+      const uint32_t bytes = a1 > a0 ? (uint32_t)(a1 - a0) : 0u;
+      const uint32_t bar = smem_u32(&s_full[stage]);
+      mbar_expect_tx(bar, bytes);
+      if (bytes) bulk_g2s(smem_u32(s_stage + stage * kStageBytes), gbase + a0, bytes, bar);
+    }
+  }
+}
+
+// Loads this thread's kPerThread samples of the current tile from the stage buffer
+// (fast path: a full tile that was fetched completely; else bounds-checked, with the last
+// bytes of a tensor whose size is not a multiple of 16 read straight from global memory).
+template <typename TIN, int kPerThread>
+__device__ __forceinline__ void load_tile_samples(const TIN* sbuf, const unsigned char* gbase, int64_t scur, int64_t b0,
+                                                  int nsamp, bool full_tile, int64_t total16, int ctid, TIN (&mu)[kPerThread],
+                                                  TIN (&mv)[kPerThread]) {
+  constexpr int kSampleBytes = 3 * (int)sizeof(TIN);
+  if (full_tile) {
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int s = ctid + j * (kConsumerWarps * 32);
+      mu[j] = sbuf[3 * s + 1];
+      mv[j] = sbuf[3 * s + 2];
+    }
+  } else {
+    const int64_t a1 = min((b0 + (int64_t)nsamp * kSampleBytes + 15) & ~(int64_t)15, total16);
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int s = ctid + j * (kConsumerWarps * 32);
+      mu[j] = (TIN)0;
+      mv[j] = (TIN)0;
+      if (s < nsamp) {
+        if (b0 + (int64_t)(s + 1) * kSampleBytes <= a1) {
+          mu[j] = sbuf[3 * s + 1];
+          mv[j] = sbuf[3 * s + 2];
+        } else {
+          const TIN* p = reinterpret_cast<const TIN*>(gbase) + 3 * (scur + s);
+          mu[j] = p[1];
+          mv[j] = p[2];
+        }
+      }
+    }
+  }
+}
+
 // CELLS: 0 = no cell-id output, 1 = uint16 cell ids, 2 = int32 cell ids (transition stage input)
 template <typename TIN, typename TLUT, bool ASSIGN, int CELLS>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs A) {
@@ -118,27 +183,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
   const int64_t total16 = A.total_bytes & ~(int64_t)15;  // bulk copies never read past this
 
   if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
-      uint32_t n = 0;
-      for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int64_t f = item / a.chunks_per_frame;
-        const int64_t u0 = (item % a.chunks_per_frame) * a.chunk_users;
-        const int64_t u1 = min(a.U, u0 + a.chunk_users);
-        int64_t b = (f * a.U + u0) * kSampleBytes;
-        const int64_t bend = (f * a.U + u1) * kSampleBytes;
-        for (; b < bend; b += kTileBytes, ++n) {
-          const int stage = n % kStages;
-          mbar_wait(smem_u32(&s_empty[stage]), ((n / kStages) & 1u) ^ 1u);
-          const int64_t a0 = b & ~(int64_t)15;
-          int64_t a1 = min((min(b + kTileBytes, bend) + 15) & ~(int64_t)15, total16);
-          const uint32_t bytes = a1 > a0 ? (uint32_t)(a1 - a0) : 0u;
-          const uint32_t bar = smem_u32(&s_full[stage]);
-          mbar_expect_tx(bar, bytes);
-          if (bytes) bulk_g2s(smem_u32(s_stage + stage * kStageBytes), gbase + a0, bytes, bar);
-        }
-      }
-    }
+    if (lane == 0) stream_producer<TIN>(a, A.total_bytes, s_stage, s_full, s_empty);
     return;
   }
 
@@ -166,32 +211,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
       uint16_t* __restrict__ out_c16 = CELLS == 1 ? a.cell16 + scur : nullptr;
       int32_t* __restrict__ out_c32 = CELLS == 2 ? a.cell32 + scur : nullptr;
       TIN mu[kPerThread], mv[kPerThread];
-      if (full_tile) {
-#pragma unroll
-        for (int j = 0; j < kPerThread; ++j) {
-          const int s = ctid + j * (kConsumerWarps * 32);
-          mu[j] = sbuf[3 * s + 1];
-          mv[j] = sbuf[3 * s + 2];
-        }
-      } else {
-        const int64_t a1 = min((b0 + (int64_t)nsamp * kSampleBytes + 15) & ~(int64_t)15, total16);
-#pragma unroll
-        for (int j = 0; j < kPerThread; ++j) {
-          const int s = ctid + j * (kConsumerWarps * 32);
-          mu[j] = (TIN)0;
-          mv[j] = (TIN)0;
-          if (s < nsamp) {
-            if (b0 + (int64_t)(s + 1) * kSampleBytes <= a1) {
-              mu[j] = sbuf[3 * s + 1];
-              mv[j] = sbuf[3 * s + 2];
-            } else {  // the last bytes of a tensor whose size is not a multiple of 16
-              const TIN* p = reinterpret_cast<const TIN*>(gbase) + 3 * (scur + s);
-              mu[j] = p[1];
-              mv[j] = p[2];
-            }
-          }
-        }
-      }
+      load_tile_samples<TIN, kPerThread>(sbuf, gbase, scur, b0, nsamp, full_tile, total16, ctid, mu, mv);
 #pragma unroll
       for (int j = 0; j < kPerThread; ++j) {
         const int s = ctid + j * (kConsumerWarps * 32);
@@ -241,6 +261,143 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs 
           atomicAdd(&row1[c], v);
           s_hist[c] = 0u;
         }
+      }
+    }
+    consumer_sync();
+  }
+  if (bad) atomicOr(a.flags, (uint32_t)VET_FLAG_OUT_OF_RANGE);
+}
+
+// ---------------------------------------------------------------------------------------
+// Direct unweighted variant: per-sample tile lookups for EVERY tile count and privatised
+// per-frame TILE histograms (a few KB) instead of the 81 KB cell histogram.  Used when the
+// frames are small against the cell grid (U < ~2C) or there is a single tile count: no cell
+// histogram is written or re-read, the frame result is sum(T_k) integers.
+struct StreamTilesArgs {
+  StreamArgs s;
+  int64_t total_bytes;
+  int K;
+  int sumT;                            // sum of T_k
+  int T[kMaxTileCounts];
+  int hist_off[kMaxTileCounts];        // offset of tile count k inside a frame's histogram row
+  int shist_off[kMaxTileCounts];       // offset of tile count k inside the shared-memory histogram area
+  int rep_shift[kMaxTileCounts];       // log2 of the number of interleaved copies of histogram k in shared memory:
+                                       // small histograms are replicated per lane group to cut same-address conflicts
+  int shist_words;                     // total words of the shared-memory histogram area
+  int lut_off[kMaxTileCounts];         // byte offset of LUT k inside the shared-memory LUT area
+  int lut_wide[kMaxTileCounts];        // 1 = uint16 entries, 0 = uint8
+  const void* lut[kMaxTileCounts];     // global LUTs (uint8 when T <= 255 else uint16)
+  int lut_bytes;                       // total bytes of the shared-memory LUT area
+  uint32_t* ihist;                     // [F, sumT] integer tile histograms (pre-zeroed when chunks_per_frame > 1)
+};
+
+template <typename TIN, bool ASSIGN>
+__global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tiles(StreamTilesArgs A) {
+  constexpr int kTileSamples = kTileBytes / (3 * (int)sizeof(TIN));
+  constexpr int kPerThread = kTileSamples / (kConsumerWarps * 32);
+  constexpr int kSampleBytes = 3 * (int)sizeof(TIN);
+  const StreamArgs& a = A.s;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* s_stage = smem_raw;
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kStages * kStageBytes);  // [shist_words]
+  unsigned char* s_lut = reinterpret_cast<unsigned char*>(s_hist + ((A.shist_words + 3) & ~3));
+  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
+  __shared__ uint32_t s_nvalid;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_empty[i]), kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_nvalid = 0u;
+  }
+  for (int t = threadIdx.x; t < A.shist_words; t += blockDim.x) s_hist[t] = 0u;
+  for (int k = 0; k < A.K; ++k) {
+    const int nb = a.C * (A.lut_wide[k] ? 2 : 1);
+    const unsigned char* __restrict__ g = static_cast<const unsigned char*>(A.lut[k]);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_lut[A.lut_off[k] + i] = g[i];
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (lane == 0) stream_producer<TIN>(a, A.total_bytes, s_stage, s_full, s_empty);
+    return;
+  }
+
+  const int64_t items = a.F * a.chunks_per_frame;
+  const unsigned char* __restrict__ gbase = static_cast<const unsigned char*>(a.packed);
+  const int64_t total16 = A.total_bytes & ~(int64_t)15;
+  const int ctid = threadIdx.x - 32;
+  const float Wf = (float)a.W, Hf = (float)a.H;
+  const int W1 = a.W + 1;
+  uint32_t n = 0;
+  uint32_t bad = 0;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t f = item / a.chunks_per_frame;
+    const int64_t u0 = (item % a.chunks_per_frame) * a.chunk_users;
+    const int64_t u1 = min(a.U, u0 + a.chunk_users);
+    int64_t scur = f * a.U + u0;
+    const int64_t send = f * a.U + u1;
+    uint32_t nv = 0;
+    for (; scur < send; scur += kTileSamples, ++n) {
+      const int stage = n % kStages;
+      const int64_t b0 = scur * kSampleBytes;
+      const int nsamp = (int)min((int64_t)kTileSamples, send - scur);
+      const bool full_tile = (nsamp == kTileSamples) && (b0 + kTileBytes <= total16);
+      mbar_wait(smem_u32(&s_full[stage]), (n / kStages) & 1u);
+      const TIN* sbuf = reinterpret_cast<const TIN*>(s_stage + stage * kStageBytes + (int)(b0 & 15));
+      uint16_t* __restrict__ out_assign = ASSIGN ? a.assign0 + scur : nullptr;
+      TIN mu[kPerThread], mv[kPerThread];
+      load_tile_samples<TIN, kPerThread>(sbuf, gbase, scur, b0, nsamp, full_tile, total16, ctid, mu, mv);
+#pragma unroll
+      for (int j = 0; j < kPerThread; ++j) {
+        const int s = ctid + j * (kConsumerWarps * 32);
+        if (full_tile || s < nsamp) {
+          bool ok = unit_range_fast(mu[j]) && unit_range_fast(mv[j]);
+          if (!ok) {
+            const int st = classify_slow(mu[j], mv[j]);
+            ok = st == kOk;
+            if (st == kOutOfRange) bad = 1;
+          }
+          uint32_t t0 = VET_MISSING;
+          if (ok) {
+            const int cell = pixel_of(mv[j], Hf, a.H) * W1 + pixel_of(mu[j], Wf, a.W);
+            ++nv;
+            for (int k = 0; k < A.K; ++k) {
+              const unsigned char* l = s_lut + A.lut_off[k];
+              const uint32_t t = A.lut_wide[k] ? (uint32_t) reinterpret_cast<const uint16_t*>(l)[cell] : (uint32_t)l[cell];
+              const int rs = A.rep_shift[k];
+              atomicAdd(&s_hist[A.shist_off[k] + (int)(t << rs) + (lane & ((1 << rs) - 1))], 1u);
+              if (k == 0) t0 = t;
+            }
+          }
+          if (ASSIGN) out_assign[s] = (uint16_t)t0;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));
+    }
+    nv = __reduce_add_sync(kFull, nv);
+    if (lane == 0 && nv) atomicAdd(&s_nvalid, nv);
+    consumer_sync();
+    if (ctid == 0) {
+      if (a.chunks_per_frame == 1) a.nvalid[f] = s_nvalid;
+      else if (s_nvalid) atomicAdd(&a.nvalid[f], s_nvalid);
+      s_nvalid = 0u;
+    }
+    uint32_t* __restrict__ row = A.ihist + f * (int64_t)A.sumT;
+    for (int k = 0; k < A.K; ++k) {
+      const int rs = A.rep_shift[k];
+      for (int t = ctid; t < A.T[k]; t += kConsumerWarps * 32) {
+        uint32_t v = 0;
+        for (int r = 0; r < (1 << rs); ++r) {
+          v += s_hist[A.shist_off[k] + (t << rs) + r];
+          s_hist[A.shist_off[k] + (t << rs) + r] = 0u;
+        }
+        if (a.chunks_per_frame == 1) row[A.hist_off[k] + t] = v;
+        else if (v) atomicAdd(&row[A.hist_off[k] + t], v);
       }
     }
     consumer_sync();

@@ -221,7 +221,11 @@ struct EntropyRowsArgs {
   int64_t F;
   int K;
   int T[kMaxTileCounts];
-  const double* hist[kMaxTileCounts];  // [F,T_k]
+  const double* hist[kMaxTileCounts];  // [F,T_k] weighted histograms (fp64), or null when ihist is used
+  const uint32_t* ihist;               // [F,istride] integer tile histograms of the direct unweighted path
+  int64_t istride;
+  int ioff[kMaxTileCounts];            // offset of tile count k inside an ihist row
+  double* hist0_out;                   // [F,T_0] (ihist mode only): tile_counts[0] histogram as float64, or null
   const uint32_t* nvalid;              // [F] present users per frame
   int use_weight;
   double* entropy;   // [F]
@@ -240,13 +244,15 @@ __global__ void k_entropy_rows(EntropyRowsArgs a) {
     double esum = 0.0;
     for (int k = 0; k < a.K; ++k) {
       const int T = a.T[k];
-      const double* __restrict__ row = a.hist[k] + f * (int64_t)T;
+      const double* __restrict__ row = a.ihist ? nullptr : a.hist[k] + f * (int64_t)T;
+      const uint32_t* __restrict__ irow = a.ihist ? a.ihist + f * a.istride + a.ioff[k] : nullptr;
       double part = 0.0;
-      for (int t = lane; t < T; t += 32) part += row[t];
+      for (int t = lane; t < T; t += 32) part += irow ? (double)irow[t] : row[t];
       const double total = a.use_weight ? warp_sum(part) : (double)nv;
       double acc = 0.0;
       for (int t = lane; t < T; t += 32) {
-        const double w = row[t];
+        const double w = irow ? (double)irow[t] : row[t];
+        if (irow && k == 0 && a.hist0_out) a.hist0_out[f * (int64_t)T + t] = w;
         if (w > 0.0) {
           const double p = w / total;
           acc -= p * log2(p);
