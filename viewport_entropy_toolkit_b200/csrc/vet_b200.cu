@@ -61,9 +61,14 @@ struct TileSet {
   int G = 0;
   int32_t* d_group_tiles = nullptr;    // [G,8]
   uint32_t* d_group_chunk0 = nullptr;  // [G+1]
-  double* d_chunks = nullptr;          // [nchunks][kTG][kQ][kChunkUnits]
+  double* d_chunks = nullptr;          // [nchunks][TG][Q][kChunkUnits]
   uint32_t* d_units = nullptr;         // [nchunks*kChunkUnits + pad]
   uint32_t nchunks = 0;
+  std::vector<uint32_t> h_group_chunk0;  // host copy (item costs of the schedule)
+  // per-CTA item schedule of k_whist, cached for the last frame count it was built for
+  uint32_t* d_sched = nullptr;
+  int64_t sched_F = -1;
+  int sched_blocks = 0, sched_max_items = 0;
   double* d_hist = nullptr;            // [frames,T] scratch rows (grown on demand)
   size_t hist_bytes = 0;
 };
@@ -237,10 +242,61 @@ int transition_direct(vet_handle* h, const void* packed, int dtype, int64_t F, i
 constexpr size_t kStaticSmemSlack = 1024;
 constexpr int kMaxT = 16384;
 
-// Clusters the tiles into groups of kTG spatial neighbours and lays every group's
+// Blocking of k_whist: "wide" = 8 tiles x 8 frames per warp, "tall" = 4 tiles x 16 frames.
+bool whist_tall() {
+  static const bool tall = [] {
+    const char* e = getenv("VET_WHIST_SHAPE");
+    return e && std::string(e) == "tall";  // measured: wide 0.49 ms, tall 0.67 ms on configs[2]
+  }();
+  return tall;
+}
+
+// Longest-processing-time schedule of the (frame block, group) items of k_whist over the
+// CTAs (items differ in size: a group's cost is its number of weight chunks); each CTA's
+// list is then put in frame-block-major order for L2 locality.
+int build_whist_schedule(TileSet& t, int64_t fblocks, int blocks) {
+  struct Item {
+    uint32_t id, cost;
+  };
+  std::vector<Item> items;
+  items.reserve((size_t)fblocks * t.G);
+  for (int64_t fb = 0; fb < fblocks; ++fb)
+    for (int g = 0; g < t.G; ++g)
+      items.push_back({(uint32_t)(fb * t.G + g), t.h_group_chunk0[g + 1] - t.h_group_chunk0[g] + 2});
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+  std::vector<std::vector<uint32_t>> lists(blocks);
+  std::vector<std::pair<uint64_t, int>> load(blocks);  // min-heap on (load, cta)
+  for (int b = 0; b < blocks; ++b) load[b] = {0, b};
+  auto cmp = [](const std::pair<uint64_t, int>& a, const std::pair<uint64_t, int>& b) { return a > b; };
+  std::make_heap(load.begin(), load.end(), cmp);
+  for (const Item& it : items) {
+    std::pop_heap(load.begin(), load.end(), cmp);
+    auto& top = load.back();
+    lists[top.second].push_back(it.id);
+    top.first += it.cost;
+    std::push_heap(load.begin(), load.end(), cmp);
+  }
+  size_t max_items = 1;
+  for (auto& l : lists) {
+    std::sort(l.begin(), l.end());
+    max_items = std::max(max_items, l.size());
+  }
+  std::vector<uint32_t> flat((size_t)blocks * max_items, 0xFFFFFFFFu);
+  for (int b = 0; b < blocks; ++b) std::copy(lists[b].begin(), lists[b].end(), flat.begin() + (size_t)b * max_items);
+  if (t.d_sched) cudaFree(t.d_sched);
+  t.d_sched = nullptr;
+  if (int rc = upload(&t.d_sched, flat.data(), flat.size())) return rc;
+  t.sched_blocks = blocks;
+  t.sched_max_items = (int)max_items;
+  return VET_OK;
+}
+
+// Clusters the tiles into groups of TG spatial neighbours and lays every group's
 // weights out as dense [cells][kTG] blocks over the union of the members' supports
 // (see vet_whist.cuh).  Values are the device-computed ones of the column table.
+template <typename S>
 int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& col_ptr, const std::vector<double>& unit) {
+  constexpr int kTG = S::TG, kQ = S::Q, kChunkCells = S::kChunkCells;
   const int T = t.T;
   std::vector<uint32_t> cell_idx(std::max<uint64_t>(t.nnz, 1));
   std::vector<double> w_val(std::max<uint64_t>(t.nnz, 1));
@@ -260,9 +316,9 @@ int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& 
         const double d = unit[3 * seed] * unit[3 * j] + unit[3 * seed + 1] * unit[3 * j + 1] + unit[3 * seed + 2] * unit[3 * j + 2];
         cand.emplace_back(-d, j);
       }
-    const size_t take = std::min<size_t>(vet::kTG, cand.size());
+    const size_t take = std::min<size_t>(kTG, cand.size());
     std::partial_sort(cand.begin(), cand.begin() + take, cand.end());
-    for (int m = 0; m < vet::kTG; ++m) {
+    for (int m = 0; m < kTG; ++m) {
       if ((size_t)m < take) {
         group_tiles.push_back(cand[m].second);
         used[cand[m].second] = 1;
@@ -271,21 +327,21 @@ int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& 
       }
     }
   }
-  const int G = (int)(group_tiles.size() / vet::kTG);
+  const int G = (int)(group_tiles.size() / kTG);
   std::vector<uint32_t> chunk0(G + 1, 0);
-  std::vector<double> chunks;       // [nchunks][kTG][kQ][kChunkUnits]
+  std::vector<double> chunks;       // [nchunks][TG][Q][kChunkUnits]
   std::vector<uint32_t> units_all;  // [nchunks][kChunkUnits] first cell of each load unit
-  const int64_t n_units_total = (h->Cpad + vet::kQ - 1) / vet::kQ;
+  const int64_t n_units_total = (h->Cpad + kQ - 1) / kQ;
   std::vector<int32_t> slot(n_units_total, -1);
   std::vector<uint32_t> units;
-  const size_t chunk_doubles = (size_t)vet::kChunkCells * vet::kTG;
+  const size_t chunk_doubles = (size_t)kChunkCells * kTG;
   for (int g = 0; g < G; ++g) {
     units.clear();
-    for (int m = 0; m < vet::kTG; ++m) {
-      const int tile = group_tiles[g * vet::kTG + m];
+    for (int m = 0; m < kTG; ++m) {
+      const int tile = group_tiles[g * kTG + m];
       if (tile < 0) continue;
       for (uint32_t j = col_ptr[tile]; j < col_ptr[tile + 1]; ++j) {
-        const uint32_t u = cell_idx[j] / vet::kQ;
+        const uint32_t u = cell_idx[j] / kQ;
         if (slot[u] < 0) {
           slot[u] = 0;
           units.push_back(u);
@@ -294,20 +350,20 @@ int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& 
     }
     std::sort(units.begin(), units.end());
     for (size_t i = 0; i < units.size(); ++i) slot[units[i]] = (int32_t)i;
-    const uint32_t nch = (uint32_t)((units.size() + vet::kChunkUnits - 1) / vet::kChunkUnits);
+    const uint32_t nch = (uint32_t)std::max<size_t>(1, (units.size() + vet::kChunkUnits - 1) / vet::kChunkUnits);
     chunk0[g] = (uint32_t)(chunks.size() / chunk_doubles);
     const size_t base = chunks.size();
-    chunks.resize(base + (size_t)nch * chunk_doubles, 0.0);           // zero weights for padding
-    units_all.resize((size_t)(chunk0[g] + nch) * vet::kChunkUnits, 0);  // padding units point at cells 0..kQ-1
-    for (size_t i = 0; i < units.size(); ++i) units_all[(size_t)chunk0[g] * vet::kChunkUnits + i] = units[i] * vet::kQ;
-    for (int m = 0; m < vet::kTG; ++m) {
-      const int tile = group_tiles[g * vet::kTG + m];
+    chunks.resize(base + (size_t)nch * chunk_doubles, 0.0);             // zero weights for padding
+    units_all.resize((size_t)(chunk0[g] + nch) * vet::kChunkUnits, 0);  // padding units point at cell 0
+    for (size_t i = 0; i < units.size(); ++i) units_all[(size_t)chunk0[g] * vet::kChunkUnits + i] = units[i] * kQ;
+    for (int m = 0; m < kTG; ++m) {
+      const int tile = group_tiles[g * kTG + m];
       if (tile < 0) continue;
       for (uint32_t j = col_ptr[tile]; j < col_ptr[tile + 1]; ++j) {
-        const size_t i = (size_t)slot[cell_idx[j] / vet::kQ];
-        const int q = (int)(cell_idx[j] % vet::kQ);
+        const size_t i = (size_t)slot[cell_idx[j] / kQ];
+        const int q = (int)(cell_idx[j] % kQ);
         double* ch = chunks.data() + base + (i / vet::kChunkUnits) * chunk_doubles;
-        ch[(m * vet::kQ + q) * vet::kChunkUnits + i % vet::kChunkUnits] = w_val[j];
+        ch[(m * kQ + q) * vet::kChunkUnits + i % vet::kChunkUnits] = w_val[j];
       }
     }
     for (uint32_t u : units) slot[u] = -1;
@@ -318,6 +374,7 @@ int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& 
   t.nchunks = chunk0[G];
   if (int rc = upload(&t.d_group_tiles, group_tiles.data(), group_tiles.size())) return rc;
   if (int rc = upload(&t.d_group_chunk0, chunk0.data(), chunk0.size())) return rc;
+  t.h_group_chunk0 = chunk0;
   if (int rc = upload(&t.d_chunks, chunks.data(), chunks.size())) return rc;
   if (int rc = upload(&t.d_units, units_all.data(), units_all.size())) return rc;
   return VET_OK;
@@ -384,7 +441,9 @@ int build_tile_set(vet_handle* h, TileSet& t) {
                                             t.d_cell_idx, t.d_w_val);
     h->launches++;
     VET_CUDA(cudaGetLastError());
-    if (int rc = build_weight_groups(h, t, ptr, unit)) return rc;
+    if (int rc = whist_tall() ? build_weight_groups<vet::WhistTall>(h, t, ptr, unit)
+                              : build_weight_groups<vet::WhistWide>(h, t, ptr, unit))
+      return rc;
   }
   return VET_OK;
 }
@@ -400,6 +459,7 @@ void free_tile_set(TileSet& t) {
   cudaFree(t.d_group_chunk0);
   cudaFree(t.d_chunks);
   cudaFree(t.d_units);
+  cudaFree(t.d_sched);
   cudaFree(t.d_hist);
 }
 
@@ -631,13 +691,22 @@ int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* 
   e.per_k = per_k;
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
-  const int64_t fblocks = (F + vet::kWhWarps * vet::kFW - 1) / (vet::kWhWarps * vet::kFW);
+  const bool tall = whist_tall();
+  const int frames_per_cta = tall ? vet::WhistTall::kFramesPerCta : vet::WhistWide::kFramesPerCta;
+  const size_t wh_smem = (size_t)vet::kWhStages * (tall ? vet::WhistTall::kChunkBytes : vet::WhistWide::kChunkBytes);
+  const int64_t fblocks = (F + frames_per_cta - 1) / frames_per_cta;
   for (int k = 0; k < h->K; ++k) {
     TileSet& t = h->ts[k];
     double* hist = (k == 0 && hist0) ? hist0 : nullptr;
     if (!hist) {
       if (int rc = grow((void**)&t.d_hist, &t.hist_bytes, (size_t)F * t.T * 8)) return rc;
       hist = t.d_hist;
+    }
+    const int blocks = (int)std::min<int64_t>(fblocks * t.G, h->sm_count);
+    if (t.sched_F != F || t.sched_blocks != blocks) {
+      VET_CUDA(cudaStreamSynchronize(st));  // the previous schedule may still be in use
+      if (int rc = build_whist_schedule(t, fblocks, blocks)) return rc;
+      t.sched_F = F;
     }
     vet::WhistArgs a{};
     a.cnt = h->d_cnt;
@@ -650,11 +719,14 @@ int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* 
     a.chunks = reinterpret_cast<const unsigned char*>(t.d_chunks);
     a.units = t.d_units;
     a.hist = hist;
-    a.items = fblocks * t.G;
-    const int blocks = (int)std::min<int64_t>(a.items, h->sm_count);
+    a.cta_items = t.d_sched;
+    a.max_items = t.sched_max_items;
     {
       LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-      vet::k_whist<<<blocks, vet::kWhThreads, vet::kWhStages * vet::kChunkBytes, st>>>(a);
+      if (tall)
+        vet::k_whist<vet::WhistTall><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
+      else
+        vet::k_whist<vet::WhistWide><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
     }
     VET_CUDA(cudaGetLastError());
     e.T[k] = t.T;
@@ -817,8 +889,10 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
       if (int rc = build_unit_centres(h->ts[k])) return rc;
   } else {
     VET_CUDA(cudaMalloc((void**)&h->d_cellvec, (size_t)h->C * 3 * sizeof(double)));
-    VET_CUDA(cudaFuncSetAttribute(vet::k_whist, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  vet::kWhStages * vet::kChunkBytes));
+    VET_CUDA(cudaFuncSetAttribute(vet::k_whist<vet::WhistWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  vet::kWhStages * vet::WhistWide::kChunkBytes));
+    VET_CUDA(cudaFuncSetAttribute(vet::k_whist<vet::WhistTall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  vet::kWhStages * vet::WhistTall::kChunkBytes));
     vet::k_cell_vectors<<<std::min<int64_t>((h->C + 255) / 256, 1024), 256>>>(h->d_cosT, h->d_sinT, h->d_sinP, h->d_cosP,
                                                                                h->W, h->H, h->d_cellvec);
     h->launches++;
@@ -967,7 +1041,7 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
   cudaStream_t st = (cudaStream_t)stream;
   if (h->direct_only) return spatial_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, hist0_dev, assign0_dev, st);
   const int64_t fb = frames_per_batch(h, F, U, false);
-  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->Cpad * 4)) return rc;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)(fb + vet::kWhRowPad) * h->Cpad * 4)) return rc;
   if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
   const size_t esz = dtype == VET_F32 ? 4 : 8;
   const int T0 = h->ts[0].T;
@@ -1004,7 +1078,7 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
     return transition_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, prev_count0_dev, pairs0_dev, mode, st);
   const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
   const size_t csz = h->C <= 65535 ? 2 : 4;
-  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fb * h->Cpad * 4)) return rc;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)(fb + vet::kWhRowPad) * h->Cpad * 4)) return rc;
   if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
   if (int rc = grow(&h->d_cells, &h->cells_bytes, (size_t)fb * U * csz)) return rc;
   const size_t esz = dtype == VET_F32 ? 4 : 8;
@@ -1400,7 +1474,7 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
     cudaStreamWaitEvent(h->s_exec, in_done[b], 0);
     cudaStreamWaitEvent(h->s_exec, out_done[b], 0);  // assignment buffer b must have been downloaded
     const int64_t fbs = frames_per_batch(h, nf, U, false);
-    rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)fbs * h->Cpad * 4);
+    rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)(fbs + vet::kWhRowPad) * h->Cpad * 4);
     if (rc == VET_OK) rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fbs * 4);
     for (int64_t g0 = 0; g0 < nf && rc == VET_OK; g0 += fbs) {
       const int64_t ng = std::min(fbs, nf - g0);

@@ -30,32 +30,42 @@
 
 namespace vet {
 
-constexpr int kTG = 8;             // tiles per group
-constexpr int kFW = 8;             // frames per consumer warp
 constexpr int kWhWarps = 8;        // warps per CTA, two per SM sub-partition; lane 0 of warp 0 doubles as the
                                    // weight-chunk producer (256 threads -> 255 registers each)
-constexpr int kQ = 2;              // cells per load unit: counts are fetched as aligned pairs (LDG.64)
 constexpr int kDepth = 4;          // depth of the register ring: counts are fetched kDepth-1 warp steps ahead
 constexpr int kChunkUnits = 32 * kDepth;  // load units per staged weight chunk = kDepth warp steps (the ring is
                                           // unrolled over them, so its rotation costs no register moves)
-constexpr int kChunkCells = kChunkUnits * kQ;
-constexpr int kChunkBytes = kChunkCells * kTG * 8;  // weights [8 tiles][kQ][64 units] f64
 constexpr int kWhStages = 3;
 constexpr int kWhThreads = kWhWarps * 32;
-constexpr int kUnitPad = 2 * kDepth * 32;   // the unit list is readable this far past its end (prefetch runs ahead)
+constexpr int kWhRowPad = 128;     // frames per CTA of the tallest shape: the count scratch has this many spare rows
+constexpr int kUnitPad = 2 * kDepth * 32;  // the unit list is readable this far past its end (prefetch runs ahead)
+
+// Blocking of the contraction: TG tiles per group x FW frames per warp (TG*FW = 64 register
+// accumulators), Q cells per load unit.
+template <int TG_, int FW_, int Q_>
+struct WhistShape {
+  static constexpr int TG = TG_, FW = FW_, Q = Q_;
+  static constexpr int kChunkCells = kChunkUnits * Q;
+  static constexpr int kChunkBytes = kChunkCells * TG * 8;  // weights [TG][Q][kChunkUnits] f64
+  static constexpr int kFramesPerCta = kWhWarps * FW;
+  static_assert(TG * FW == 64, "the warp reduction below is written for 64 accumulators");
+};
+using WhistWide = WhistShape<8, 8, 2>;    // 8 tiles x 8 frames, counts as aligned pairs
+using WhistTall = WhistShape<4, 16, 1>;   // 4 tiles x 16 frames: 25 % less padding in the dense blocks
 
 struct WhistArgs {
-  const uint32_t* cnt;     // [F,cpad]
+  const uint32_t* cnt;     // [F + kWhRowPad, cpad]: readable past F (rows of a partial last frame block)
   int64_t F;
   int cpad;
   int T;
   int G;                         // tile groups
-  const int32_t* group_tiles;    // [G,8] tile index or -1
+  const int32_t* group_tiles;    // [G,TG] tile index or -1
   const uint32_t* group_chunk0;  // [G+1] first chunk of each group
   const unsigned char* chunks;   // [nchunks][kChunkBytes]
-  const uint32_t* units;         // [nchunks*kChunkUnits + kUnitPad] first cell of every load unit (multiple of kQ)
+  const uint32_t* units;         // [nchunks*kChunkUnits + kUnitPad] first cell of every load unit (multiple of Q)
   double* hist;                  // [F,T]
-  int64_t items;                 // frame blocks * G
+  const uint32_t* cta_items;     // [gridDim.x, max_items] (frame block * G + group) per CTA, 0xFFFFFFFF = none:
+  int max_items;                 // host-side longest-processing-time schedule (items differ in size)
 };
 
 // exact u32 -> f64.  VET_CVT_MAGIC: 2^52 + v has v in its low mantissa bits, one DADD on
@@ -82,9 +92,46 @@ __device__ __forceinline__ void butterfly_step(double* flat, int lane) {
   }
 }
 
-__device__ __forceinline__ uint2 ldg_pair(const uint32_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+template <int Q>
+struct CountUnit;
+template <>
+struct CountUnit<1> {
+  uint32_t v;
+  __device__ __forceinline__ void load(const uint32_t* p) { v = __ldg(p); }
+  __device__ __forceinline__ uint32_t get(int) const { return v; }
+};
+template <>
+struct CountUnit<2> {
+  uint2 v;
+  __device__ __forceinline__ void load(const uint32_t* p) { v = __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ __forceinline__ uint32_t get(int j) const { return j == 0 ? v.x : v.y; }
+};
 
+// (Skipping the half of a tile group that cannot see a run of cells -- 18 % fewer DFMAs on
+// configs[2] -- was measured SLOWER on B200, 0.57 vs 0.49 ms, per step or per chunk: the
+// halved DFMA-per-load ratio and the extra code paths cost more than the saved math.)
+
+// DFMAs of one warp step restricted to tiles [T0, T1) of the group.
+template <typename S, int T0, int T1>
+__device__ __forceinline__ void whist_step(const double* sW, int s, int lane, const CountUnit<S::Q> (&use)[S::FW],
+                                           double (&acc)[S::TG][S::FW]) {
+#pragma unroll
+  for (int j = 0; j < S::Q; ++j) {
+    double w[S::TG];
+#pragma unroll
+    for (int t = T0; t < T1; ++t) w[t] = sW[(t * S::Q + j) * kChunkUnits + s * 32 + lane];
+#pragma unroll
+    for (int r = 0; r < S::FW; ++r) {
+      const double v = u32_to_f64(use[r].get(j));
+#pragma unroll
+      for (int t = T0; t < T1; ++t) acc[t][r] = fma(v, w[t], acc[t][r]);
+    }
+  }
+}
+
+template <typename S>
 __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
+  constexpr int TG = S::TG, FW = S::FW, Q = S::Q;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kWhStages], s_empty[kWhStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,13 +144,15 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
   }
   __syncthreads();
 
-  // Static round-robin over (frame block, group) items, frame-block major so that CTAs
-  // running at the same time share the block's CNT rows in L2.  No CTA-wide barrier
-  // after this point: warps only meet through the weight-chunk mbarriers.
+  // Items (frame block, group) come from a host-made per-CTA list balanced by size; within a
+  // CTA they are frame-block major so that CTAs running together share CNT rows in L2.  No
+  // CTA-wide barrier after this point: warps only meet through the weight-chunk mbarriers.
   uint32_t n = 0;  // chunk sequence number (stage = n % kWhStages), identical in every warp
-  for (int64_t item = blockIdx.x; item < a.items; item += gridDim.x) {
-    const int g = (int)(item % a.G);
-    const int64_t fb = item / a.G;
+  for (int it = 0; it < a.max_items; ++it) {
+    const uint32_t item = a.cta_items[(size_t)blockIdx.x * a.max_items + it];
+    if (item == 0xFFFFFFFFu) break;
+    const int g = (int)(item % (uint32_t)a.G);
+    const int64_t fb = item / (uint32_t)a.G;
     const uint32_t c0 = a.group_chunk0[g], c1 = a.group_chunk0[g + 1];
     // weight chunk `c` of this item goes to stage (n0 + c - c0) % kWhStages; issued by lane 0 of warp 0
     const uint32_t n0 = n;
@@ -113,36 +162,34 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
         const int stage = m % kWhStages;
         mbar_wait(smem_u32(&s_empty[stage]), ((m / kWhStages) & 1u) ^ 1u);
         const uint32_t bar = smem_u32(&s_full[stage]);
-        mbar_expect_tx(bar, kChunkBytes);
-        bulk_g2s(smem_u32(smem_raw + stage * kChunkBytes), a.chunks + (size_t)c * kChunkBytes, kChunkBytes, bar);
+        mbar_expect_tx(bar, S::kChunkBytes);
+        bulk_g2s(smem_u32(smem_raw + stage * S::kChunkBytes), a.chunks + (size_t)c * S::kChunkBytes, S::kChunkBytes, bar);
       }
     };
 #pragma unroll
     for (int i = 0; i < kWhStages - 1; ++i) produce(c0 + i);
 
-    const int64_t f0 = fb * (kWhWarps * kFW) + warp * kFW;
-    // element offsets of this warp's frame rows; frames past the end alias the last frame (results discarded)
-    uint32_t roff[kFW];
+    const int64_t f0 = fb * S::kFramesPerCta + warp * FW;
+    // first row of this warp's frames; rows past F exist in the scratch (zero-cost padding, results discarded)
+    const uint32_t* __restrict__ row0 = a.cnt + f0 * (int64_t)a.cpad;
+    double acc[TG][FW];
 #pragma unroll
-    for (int r = 0; r < kFW; ++r) roff[r] = (uint32_t)(min(f0 + r, a.F - 1) * (int64_t)a.cpad);
-    double acc[kTG][kFW];
+    for (int t = 0; t < TG; ++t)
 #pragma unroll
-    for (int t = 0; t < kTG; ++t)
-#pragma unroll
-      for (int r = 0; r < kFW; ++r) acc[t][r] = 0.0;
+      for (int r = 0; r < FW; ++r) acc[t][r] = 0.0;
 
-    // Register pipeline over warp steps (32 load units each).  While step S runs its 128
-    // DFMAs, the counts of steps S+1 .. S+kDepth-1 are in flight in the ring and the unit
-    // indices of steps up to S+2(kDepth-1) in uring, so L2/DRAM latency is covered by
-    // kDepth-1 steps of FP64 work without staging the counts in shared memory.
+    // Register pipeline over warp steps (32 load units each).  While step S runs its DFMAs,
+    // the counts of steps S+1 .. S+kDepth-1 are in flight in the ring and the unit indices of
+    // steps up to S+2(kDepth-1) in uring, so L2/DRAM latency is covered by kDepth-1 steps of
+    // FP64 work without staging the counts in shared memory.
     const uint32_t* __restrict__ up = a.units + (size_t)c0 * kChunkUnits + lane;
-    uint2 ring[kDepth][kFW];
+    CountUnit<Q> ring[kDepth][FW];
     uint32_t uring[kDepth];
 #pragma unroll
     for (int i = 0; i < kDepth - 1; ++i) {
-      const uint32_t u = __ldg(up + 32 * i);
+      const uint32_t* p = row0 + __ldg(up + 32 * i);
 #pragma unroll
-      for (int r = 0; r < kFW; ++r) ring[i][r] = ldg_pair(a.cnt + roff[r] + u);
+      for (int r = 0; r < FW; ++r, p += a.cpad) ring[i][r].load(p);
     }
 #pragma unroll
     for (int x = kDepth - 1; x < 2 * kDepth - 2; ++x) uring[x % kDepth] = __ldg(up + 32 * x);
@@ -152,36 +199,18 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
       produce(c + kWhStages - 1);
       const int stage = n % kWhStages;
       mbar_wait(smem_u32(&s_full[stage]), (n / kWhStages) & 1u);
-      const double* sW = reinterpret_cast<const double*>(smem_raw + stage * kChunkBytes);
+      const double* sW = reinterpret_cast<const double*>(smem_raw + stage * S::kChunkBytes);
 #pragma unroll
       for (int s = 0; s < kDepth; ++s) {
         // issue the count loads of step S+kDepth-1 and the unit load of step S+2(kDepth-1)
-        const uint32_t u = uring[(s + kDepth - 1) % kDepth];
-#pragma unroll
+        const uint32_t* p = row0 + uring[(s + kDepth - 1) % kDepth];
 #ifndef VET_DBG_NO_CNT_LOADS
-        for (int r = 0; r < kFW; ++r) ring[(s + kDepth - 1) % kDepth][r] = ldg_pair(a.cnt + roff[r] + u);
-#else
-        for (int r = 0; r < kFW; ++r) ring[(s + kDepth - 1) % kDepth][r].x += u;
+#pragma unroll
+        for (int r = 0; r < FW; ++r, p += a.cpad) ring[(s + kDepth - 1) % kDepth][r].load(p);
 #endif
         uring[(s + kDepth - 2) % kDepth] = __ldg(up);
         up += 32;
-        // step S out of ring[s]
-#pragma unroll
-        for (int j = 0; j < kQ; ++j) {
-          double w[kTG];
-#pragma unroll
-#ifndef VET_DBG_NO_W_LOADS
-          for (int t = 0; t < kTG; ++t) w[t] = sW[(t * kQ + j) * kChunkUnits + s * 32 + lane];
-#else
-          for (int t = 0; t < kTG; ++t) w[t] = 1.0 + t + j + (double)n;
-#endif
-#pragma unroll
-          for (int r = 0; r < kFW; ++r) {
-            const double v = u32_to_f64(j == 0 ? ring[s][r].x : ring[s][r].y);
-#pragma unroll
-            for (int t = 0; t < kTG; ++t) acc[t][r] = fma(v, w[t], acc[t][r]);
-          }
-        }
+        whist_step<S, 0, TG>(sW, s, lane, ring[s], acc);  // step S out of ring[s]
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));
@@ -197,7 +226,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
     butterfly_step<1, 2>(flat, lane);
     int base = 0;
     {
-      int span = kTG * kFW;
+      int span = 64;
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         span >>= 1;
@@ -206,9 +235,9 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int id = base + j;  // = t * kFW + r
-      const int t = id / kFW, r = id % kFW;
-      const int tile = a.group_tiles[g * kTG + t];
+      const int id = base + j;  // = t * FW + r
+      const int t = id / FW, r = id % FW;
+      const int tile = a.group_tiles[g * TG + t];
       const int64_t f = f0 + r;
       if (tile >= 0 && f < a.F) a.hist[f * (int64_t)a.T + tile] = flat[j];
     }
