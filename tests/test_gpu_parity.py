@@ -261,6 +261,8 @@ def test_spatial_vs_oracle(vet, cfg):
     dict(F=4, U=3000, tcs=[200, 500, 1000], iid=False),
     dict(F=3, U=6000, tcs=[200], iid=True),                 # many distinct pairs: global pair table
     dict(F=5, U=900, tcs=[50, 20], iid=True, missing=0.3),
+    dict(F=3, U=9000, tcs=[200, 500, 1000], iid=False),     # fast paths: dense table (201) + shared-memory hash (501, 1001)
+    dict(F=3, U=20000, tcs=[1000, 200], iid=True, missing=0.1),  # hash overflow -> in-kernel fallback to the global table
 ])
 @pytest.mark.parametrize("mode", ["literal", "textbook"])
 def test_transition_vs_oracle(vet, cfg, mode):

@@ -20,6 +20,7 @@
 #include "vet_stream_tma.cuh"
 #include "vet_tables.cuh"
 #include "vet_transition.cuh"
+#include "vet_transition2.cuh"
 #include "vet_vectors.cuh"
 #include "vet_whist.cuh"
 
@@ -107,6 +108,8 @@ struct vet_handle {
   size_t cells_bytes = 0;
   uint32_t* d_tables = nullptr;
   size_t tables_words = 0;
+  uint32_t tables_cap = 0;  // slot count the tables are currently laid out (and cleared) for
+  int tables_blocks = 0;    // number of per-CTA tables cleared for that layout
   // host-buffer path
   void* d_in[2] = {nullptr, nullptr};
   size_t in_bytes = 0;
@@ -1309,22 +1312,59 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
   const int blocks = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * (in_smem ? 1 : 2));
   if (!in_smem) {
     const size_t words = (size_t)blocks * 4 * cap;
-    if (h->tables_words < words) {
-      if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
-      h->d_tables = nullptr;
-      h->tables_words = 0;
-      VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
-      h->tables_words = words;
-    }
-    // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value); kernels leave the tables clean
-    for (int b = 0; b < blocks; ++b) {
-      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
-      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+    if (h->tables_words < words || h->tables_cap != cap) {
+      if (h->tables_words < words) {
+        if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
+        h->d_tables = nullptr;
+        h->tables_words = 0;
+        VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
+        h->tables_words = words;
+      }
+      // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value).  Done once per layout:
+      // the kernels reset every slot they touch, so the tables stay clean between calls.
+      for (int b = 0; b < blocks; ++b) {
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+      }
+      h->tables_cap = cap;
+      h->tables_blocks = blocks;
+    } else if (h->tables_blocks < blocks) {
+      for (int b = h->tables_blocks; b < blocks; ++b) {
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+      }
+      h->tables_blocks = blocks;
     }
   }
   a.cap = cap;
   a.g_tables = h->d_tables;
-  if (in_smem) {
+  static const bool force_v1 = [] {
+    const char* e = getenv("VET_TRANSITION_IMPL");
+    return e && std::string(e) == "v1";
+  }();
+  if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1) {
+    // fast paths: dense T*T table or shared-memory hash per tile count, global table as the in-kernel fallback
+    vet::Transition2Args A2{};
+    A2.t = a;
+    const size_t budget = h->smem_optin - kStaticSmemSlack;
+    size_t table_words = 0;
+    for (int k = 0; k < a.K; ++k) {
+      const size_t dense_words = (size_t)a.T[k] * a.T[k];
+      if (tile_bytes + dense_words * 4 + 64 <= budget) {
+        A2.mode[k] = vet::kTrDense;
+        table_words = std::max(table_words, dense_words);
+      } else if (tile_bytes + (size_t)3 * vet::kHashSlots * 4 + 64 <= budget) {
+        A2.mode[k] = vet::kTrHash;
+        table_words = std::max(table_words, (size_t)3 * vet::kHashSlots);
+      } else {
+        A2.mode[k] = vet::kTrGlobal;
+      }
+    }
+    const size_t smem2 = tile_bytes + table_words * 4 + 64;
+    VET_CUDA(cudaFuncSetAttribute(vet::k_transition2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+    vet::k_transition2<<<blocks, vet::kTrThreads, smem2, st>>>(A2, Tmax);
+  } else if (in_smem) {
     VET_CUDA(cudaFuncSetAttribute(vet::k_transition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
     LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
     vet::k_transition<true><<<blocks, 512, smem_tab, st>>>(a, Tmax);
