@@ -683,65 +683,85 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
   return VET_OK;
 }
 
-int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, int64_t per_k_stride,
-                             double* hist0, cudaStream_t st) {
+// k_whist for tile count k over F frames of the cell histogram `cnt` -> hist[F,T_k]
+int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st) {
+  TileSet& t = h->ts[k];
+  const bool tall = whist_tall();
+  const int frames_per_cta = tall ? vet::WhistTall::kFramesPerCta : vet::WhistWide::kFramesPerCta;
+  const size_t wh_smem = (size_t)vet::kWhStages * (tall ? vet::WhistTall::kChunkBytes : vet::WhistWide::kChunkBytes);
+  const int64_t fblocks = (F + frames_per_cta - 1) / frames_per_cta;
+  const int blocks = (int)std::min<int64_t>(fblocks * t.G, h->sm_count);
+  if (t.sched_F != F || t.sched_blocks != blocks) {
+    VET_CUDA(cudaStreamSynchronize(st));  // the previous schedule may still be in use
+    if (int rc = build_whist_schedule(t, fblocks, blocks)) return rc;
+    t.sched_F = F;
+  }
+  vet::WhistArgs a{};
+  a.cnt = cnt;
+  a.F = F;
+  a.cpad = h->Cpad;
+  a.T = t.T;
+  a.G = t.G;
+  a.group_tiles = t.d_group_tiles;
+  a.group_chunk0 = t.d_group_chunk0;
+  a.chunks = reinterpret_cast<const unsigned char*>(t.d_chunks);
+  a.units = t.d_units;
+  a.hist = hist;
+  a.cta_items = t.d_sched;
+  a.max_items = t.sched_max_items;
+  {
+    LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
+    if (tall)
+      vet::k_whist<vet::WhistTall><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
+    else
+      vet::k_whist<vet::WhistWide><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
+  }
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+// weighted histograms' scratch rows of tile count k (k == 0 may write straight into the caller's hist0)
+int whist_rows(vet_handle* h, int k, int64_t F, double* hist0, double** out) {
+  TileSet& t = h->ts[k];
+  if (k == 0 && hist0) {
+    *out = hist0;
+    return VET_OK;
+  }
+  if (int rc = grow((void**)&t.d_hist, &t.hist_bytes, (size_t)F * t.T * 8)) return rc;
+  *out = t.d_hist;
+  return VET_OK;
+}
+
+int launch_weighted_rows(vet_handle* h, int64_t F, double* const* hists, const uint32_t* nvalid, double* entropy, double* per_k,
+                         int64_t per_k_stride, cudaStream_t st) {
   vet::EntropyRowsArgs e{};
   e.F = F;
   e.K = h->K;
-  e.nvalid = h->d_nvalid;
+  for (int k = 0; k < h->K; ++k) {
+    e.T[k] = h->ts[k].T;
+    e.hist[k] = hists[k];
+  }
+  e.nvalid = nvalid;
   e.use_weight = 1;
   e.entropy = entropy;
   e.per_k = per_k;
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
-  const bool tall = whist_tall();
-  const int frames_per_cta = tall ? vet::WhistTall::kFramesPerCta : vet::WhistWide::kFramesPerCta;
-  const size_t wh_smem = (size_t)vet::kWhStages * (tall ? vet::WhistTall::kChunkBytes : vet::WhistWide::kChunkBytes);
-  const int64_t fblocks = (F + frames_per_cta - 1) / frames_per_cta;
-  for (int k = 0; k < h->K; ++k) {
-    TileSet& t = h->ts[k];
-    double* hist = (k == 0 && hist0) ? hist0 : nullptr;
-    if (!hist) {
-      if (int rc = grow((void**)&t.d_hist, &t.hist_bytes, (size_t)F * t.T * 8)) return rc;
-      hist = t.d_hist;
-    }
-    const int blocks = (int)std::min<int64_t>(fblocks * t.G, h->sm_count);
-    if (t.sched_F != F || t.sched_blocks != blocks) {
-      VET_CUDA(cudaStreamSynchronize(st));  // the previous schedule may still be in use
-      if (int rc = build_whist_schedule(t, fblocks, blocks)) return rc;
-      t.sched_F = F;
-    }
-    vet::WhistArgs a{};
-    a.cnt = h->d_cnt;
-    a.F = F;
-    a.cpad = h->Cpad;
-    a.T = t.T;
-    a.G = t.G;
-    a.group_tiles = t.d_group_tiles;
-    a.group_chunk0 = t.d_group_chunk0;
-    a.chunks = reinterpret_cast<const unsigned char*>(t.d_chunks);
-    a.units = t.d_units;
-    a.hist = hist;
-    a.cta_items = t.d_sched;
-    a.max_items = t.sched_max_items;
-    {
-      LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-      if (tall)
-        vet::k_whist<vet::WhistTall><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
-      else
-        vet::k_whist<vet::WhistWide><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
-    }
-    VET_CUDA(cudaGetLastError());
-    e.T[k] = t.T;
-    e.hist[k] = hist;
-  }
-  {
-    LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-    const int blocks = (int)std::min<int64_t>((F + 7) / 8, (int64_t)h->sm_count * 8);
-    vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e);
-  }
+  LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
+  const int blocks = (int)std::min<int64_t>((F + 7) / 8, (int64_t)h->sm_count * 8);
+  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e);
   VET_CUDA(cudaGetLastError());
   return VET_OK;
+}
+
+int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, int64_t per_k_stride,
+                             double* hist0, cudaStream_t st) {
+  double* hists[vet::kMaxTileCounts];
+  for (int k = 0; k < h->K; ++k) {
+    if (int rc = whist_rows(h, k, F, hist0, &hists[k])) return rc;
+    if (int rc = launch_whist(h, k, F, h->d_cnt, hists[k], st)) return rc;
+  }
+  return launch_weighted_rows(h, F, hists, h->d_nvalid, entropy, per_k, per_k_stride, st);
 }
 
 int launch_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, int64_t per_k_stride, double* hist0,

@@ -21,10 +21,19 @@
 
 namespace vet {
 
-constexpr int kStages = 4;
+#ifndef VET_STREAM_STAGES
+#define VET_STREAM_STAGES 4
+#endif
+#ifndef VET_STREAM_CWARPS
+#define VET_STREAM_CWARPS 16
+#endif
+#ifndef VET_STREAM_MINBLOCKS
+#define VET_STREAM_MINBLOCKS 1
+#endif
+constexpr int kStages = VET_STREAM_STAGES;
 constexpr int kTileBytes = 24576;              // payload per stage: 2048 fp32 samples / 1024 fp64 samples
 constexpr int kStageBytes = kTileBytes + 32;   // + 16 B alignment head and tail
-constexpr int kConsumerWarps = 16;
+constexpr int kConsumerWarps = VET_STREAM_CWARPS;
 constexpr int kStreamThreads = (kConsumerWarps + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -149,7 +158,7 @@ __device__ __forceinline__ void load_tile_samples(const TIN* sbuf, const unsigne
 
 // CELLS: 0 = no cell-id output, 1 = uint16 cell ids, 2 = int32 cell ids (transition stage input)
 template <typename TIN, typename TLUT, bool ASSIGN, int CELLS>
-__global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tma(StreamTmaArgs A) {
+__global__ void __launch_bounds__(kStreamThreads, VET_STREAM_MINBLOCKS) k_stream_tma(StreamTmaArgs A) {
   constexpr int kTileSamples = kTileBytes / (3 * (int)sizeof(TIN));
   constexpr int kPerThread = kTileSamples / (kConsumerWarps * 32);
   constexpr int kSampleBytes = 3 * (int)sizeof(TIN);

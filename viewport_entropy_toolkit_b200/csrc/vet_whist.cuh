@@ -30,7 +30,10 @@
 
 namespace vet {
 
-constexpr int kWhWarps = 8;        // warps per CTA, two per SM sub-partition; lane 0 of warp 0 doubles as the
+#ifndef VET_WHIST_WARPS
+#define VET_WHIST_WARPS 8
+#endif
+constexpr int kWhWarps = VET_WHIST_WARPS;        // warps per CTA, two per SM sub-partition; lane 0 of warp 0 doubles as the
                                    // weight-chunk producer (256 threads -> 255 registers each)
 constexpr int kDepth = 4;          // depth of the register ring: counts are fetched kDepth-1 warp steps ahead
 constexpr int kChunkUnits = 32 * kDepth;  // load units per staged weight chunk = kDepth warp steps (the ring is
