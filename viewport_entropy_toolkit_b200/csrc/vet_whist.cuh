@@ -75,7 +75,9 @@ struct WhistArgs {
 // the FP64 pipe plus two register moves; otherwise I2F.F64.U32 on the conversion unit,
 // which runs beside the FP64 pipe.
 __device__ __forceinline__ double u32_to_f64(uint32_t v) {
-#ifdef VET_CVT_MAGIC
+#ifdef VET_DBG_NO_CVT
+  return __hiloint2double(0x3ff00000, (int)v);  // timing experiment only: wrong values, no conversion
+#elif defined(VET_CVT_MAGIC)
   return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
 #else
   return (double)v;
