@@ -238,9 +238,13 @@ def test_transition_quirks_vs_reference(vet):
     dict(F=3, U=1500, tcs=[250, 1000], use_w=True, fov=120.0, iid=False),
     dict(F=5, U=700, tcs=[50], use_w=True, fov=360.0, pf=3.0, iid=True),
     dict(F=5, U=700, tcs=[50], use_w=True, fov=10.0, pf=0.5, iid=True),         # most users outside every FOV
+    dict(F=7, U=2501, tcs=[200, 50], use_w=True, fov=90.0, iid=True, missing=0.05),   # odd U: unaligned tile heads, tensor tail
+    dict(F=5, U=4099, tcs=[1000], use_w=False, fov=120.0, iid=True),              # single tile count: direct tile-histogram kernel, u16 LUT
+    dict(F=9, U=3001, tcs=[20, 50, 250, 1000], use_w=False, fov=120.0, iid=False, dtype=np.float64),  # mixed u8/u16 LUTs, f64 input
 ])
 def test_spatial_vs_oracle(vet, cfg):
-    p = synth(cfg["F"], cfg["U"], 900 + cfg["U"], cfg.get("iid", False), cfg.get("missing", 0.0))
+    p = synth(cfg["F"], cfg["U"], 900 + cfg["U"], cfg.get("iid", False), cfg.get("missing", 0.0),
+              dtype=cfg.get("dtype", np.float32))
     pf = cfg.get("pf", 2.0)
     e = engine(vet, cfg["tcs"], cfg["fov"], cfg["use_w"], pf)
     sp = e.spatial(dev(p))

@@ -1,0 +1,34 @@
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
+every kernel family once, sizes of a few thousand samples."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+import torch
+from viewport_entropy_toolkit_b200 import Engine, EntropyConfig
+
+rng = np.random.default_rng(3)
+
+
+def packed(F, U, dtype=np.float32):
+    p = np.stack([np.zeros((F, U)), rng.uniform(0, 1, (F, U)), rng.uniform(0, 1, (F, U))], -1).astype(dtype)
+    p[0, 0, 1] = np.nan
+    return torch.from_numpy(p).cuda()
+
+
+e = Engine(100, 200, [200, 20], EntropyConfig(fov_angle=90.0))
+r = e.spatial(packed(70, 2501))                     # k_stream_tma (odd U: unaligned tile heads) + k_whist + k_entropy_rows
+t = e.transition(packed(4, 9000))                   # k_stream_tma<cells> + k_transition2 (dense)
+e.close()
+e = Engine(100, 200, [20, 50, 1000], EntropyConfig(use_weight_distribution=False))
+r2 = e.spatial(packed(9, 3001, np.float64))         # k_stream_tiles (direct unweighted) + k_entropy_rows
+r3 = e.spatial(packed(3, 90001))                    # cells path: k_stream_tma + k_epilogue, several chunks per frame
+t2 = e.transition(packed(3, 20000))                 # k_transition2 hash + overflow -> global fallback
+t3 = e.transition(packed(5, 700), mode="textbook")  # k_transition (shared-memory table)
+e.close()
+e = Engine(200, 400, [20], EntropyConfig())
+r4 = e.spatial(packed(2, 300))                      # direct regime: k_decode + k_nearest + k_spatial_vectors
+e.close()
+torch.cuda.synchronize()
+print("sanitize case ok", float(r.entropy[0]), float(t.entropy[0]), float(r2.entropy[0]), float(r3.entropy[0]),
+      float(t2.entropy[0]), float(t3.entropy[0]), float(r4.entropy[0]))
