@@ -403,7 +403,7 @@ int build_tile_set(vet_handle* h, TileSet& t) {
   const int T = t.T;
   if (int rc = build_unit_centres(t)) return rc;
   const std::vector<double>& unit = t.h_unit;
-  VET_CUDA(cudaMalloc((void**)&t.d_lut, (size_t)h->C * sizeof(uint16_t)));
+  VET_CUDA(cudaMalloc((void**)&t.d_lut, (size_t)h->C * sizeof(uint16_t) + 16));  // readable in 16 B units
   const size_t smem = (size_t)T * 3 * sizeof(double);
   VET_CUDA(cudaFuncSetAttribute(vet::k_nearest<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = 256;
@@ -415,7 +415,7 @@ int build_tile_set(vet_handle* h, TileSet& t) {
   t.h_lut.resize(h->C);
   VET_CUDA(cudaMemcpy(t.h_lut.data(), t.d_lut, (size_t)h->C * sizeof(uint16_t), cudaMemcpyDeviceToHost));
   if (T <= 255) {
-    std::vector<uint8_t> l8(h->C);
+    std::vector<uint8_t> l8(h->C + 16, 0);  // padded: the kernels copy it in 16 B units
     for (int64_t c = 0; c < h->C; ++c) l8[c] = (uint8_t)t.h_lut[c];
     if (int rc = upload(&t.d_lut8, l8.data(), l8.size())) return rc;
   }
@@ -468,7 +468,7 @@ void free_tile_set(TileSet& t) {
 
 size_t stream_smem_bytes(const vet_handle* h) { return (size_t)h->Cpad * 4 + (size_t)h->C * 2 + 16; }
 size_t stream_tma_smem_bytes(const vet_handle* h, bool lut8) {
-  return (size_t)vet::kStages * vet::kStageBytes + (size_t)h->Cpad * 4 + (size_t)h->C * (lut8 ? 1 : 2) + 16;
+  return (size_t)vet::kStages * vet::kStageBytes + (size_t)h->Cpad * 4 + (size_t)h->C * (lut8 ? 1 : 2) + 32;
 }
 size_t epilogue_smem_bytes(const vet_handle* h) {
   return (size_t)h->Cpad * 4 + (size_t)h->maxT * 8 + (size_t)h->maxT * 4 + 16;

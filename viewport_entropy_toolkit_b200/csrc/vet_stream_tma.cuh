@@ -91,6 +91,16 @@ __device__ __forceinline__ bool unit_range_fast(double v) {
   return (unsigned long long)__double_as_longlong(v) <= 0x3FF0000000000000ull;
 }
 
+// Cooperative 16-byte copy global -> shared of `bytes` (rounded up to 16; both buffers are
+// allocated with that padding).  Element-wise copies of the LUTs showed up as 30 % of the
+// short direct-unweighted kernel (dependent byte loads in the prologue).
+__device__ __forceinline__ void copy_to_smem16(void* dst, const void* __restrict__ src, int bytes) {
+  const int n16 = (bytes + 15) >> 4;
+  const uint4* __restrict__ s = static_cast<const uint4*>(src);
+  uint4* d = static_cast<uint4*>(dst);
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
 // Producer side of the streaming pipeline (one elected lane): walks the CTA's work items
 // and fills the stage ring with 16 B-aligned supersets of each 24 KB tile.
 template <typename TIN>
@@ -181,10 +191,7 @@ __global__ void __launch_bounds__(kStreamThreads, VET_STREAM_MINBLOCKS) k_stream
   }
   for (int c = threadIdx.x; c < A.cpad; c += blockDim.x) s_hist[c] = 0u;
   if (threadIdx.x == 0) s_nvalid = 0u;
-  if (ASSIGN) {
-    const TLUT* __restrict__ g_lut = static_cast<const TLUT*>(A.lut0_typed);
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_lut[c] = g_lut[c];
-  }
+  if (ASSIGN) copy_to_smem16(s_lut, A.lut0_typed, a.C * (int)sizeof(TLUT));
   __syncthreads();
 
   const int64_t items = a.F * a.chunks_per_frame;
@@ -323,11 +330,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tiles(StreamTilesA
     s_nvalid = 0u;
   }
   for (int t = threadIdx.x; t < A.shist_words; t += blockDim.x) s_hist[t] = 0u;
-  for (int k = 0; k < A.K; ++k) {
-    const int nb = a.C * (A.lut_wide[k] ? 2 : 1);
-    const unsigned char* __restrict__ g = static_cast<const unsigned char*>(A.lut[k]);
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_lut[A.lut_off[k] + i] = g[i];
-  }
+  for (int k = 0; k < A.K; ++k) copy_to_smem16(s_lut + A.lut_off[k], A.lut[k], a.C * (A.lut_wide[k] ? 2 : 1));
   __syncthreads();
 
   if (warp == 0) {
