@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--transition", action="store_true", help="also run the transition stage inside the step")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads reported under 'extra'")
+    ap.add_argument("--gather-hist0", action="store_true",
+                    help="N > 1: also all-gather the hist0[F,T0] rows (5.8 MB per rank), not only entropy[F]")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -270,8 +272,9 @@ def main():
         if args.transition:
             eng.transition(packed, want_per_k=False, want_pairs0=False)
         if world > 1:  # the path's only exchange: the all-gather of the per-frame results
-            pending[slot] = [dist.all_gather_into_tensor(gathered[slot][0], o.entropy, async_op=True),
-                             dist.all_gather_into_tensor(gathered[slot][1], o.hist0, async_op=True)]
+            pending[slot] = [dist.all_gather_into_tensor(gathered[slot][0], o.entropy, async_op=True)]
+            if args.gather_hist0:  # hist0 / assign0 normally stay on the rank that owns the frames
+                pending[slot].append(dist.all_gather_into_tensor(gathered[slot][1], o.hist0, async_op=True))
 
     def drain_all():
         for s_ in range(len(outs)):
@@ -403,7 +406,7 @@ def main():
                        "tiles": eng.num_tiles, "fov": wl["fov"], "power_factor": wl["pf"], "weighted": wl["use_w"],
                        "video": "100x200", "input": "float32[F,U,3] resident in HBM", "outputs": "entropy[F], hist0[F,T0], assign0[F,U] u16",
                        "l2": "input 4.32 GB per step >> 126 MB L2 (no flush needed)" if F * U * 12 > 2e9 else "input larger than L2" if F * U * 12 > 1.3e8 else "input smaller than L2",
-                       "transition": bool(args.transition), "sharding": "frames (one shard of the workload shape per rank); per-frame entropy and hist0 rows all-gathered every step, asynchronously (overlapping the next step), all waited for inside the timed region"},
+                       "transition": bool(args.transition), "sharding": "frames (one shard of the workload shape per rank); per-frame entropy all-gathered every step" + (" together with the hist0 rows" if args.gather_hist0 else " (hist0 and assign0 stay on the owning rank)") + ", asynchronously (overlapping the next step), all waited for inside the timed region"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "extra": extra,
         }))
