@@ -246,12 +246,15 @@ constexpr size_t kStaticSmemSlack = 1024;
 constexpr int kMaxT = 16384;
 
 // Blocking of k_whist: "wide" = 8 tiles x 8 frames per warp, "tall" = 4 tiles x 16 frames.
-bool whist_tall() {
-  static const bool tall = [] {
+// 0 = wide (default), 1 = tall, 2 = quad
+int whist_shape() {
+  static const int shape = [] {
     const char* e = getenv("VET_WHIST_SHAPE");
-    return e && std::string(e) == "tall";  // measured: wide 0.49 ms, tall 0.67 ms on configs[2]
+    if (e && std::string(e) == "tall") return 1;  // measured: wide 0.49 ms, tall 0.67 ms on configs[2]
+    if (e && std::string(e) == "quad") return 2;
+    return 0;
   }();
-  return tall;
+  return shape;
 }
 
 // Longest-processing-time schedule of the (frame block, group) items of k_whist over the
@@ -353,26 +356,26 @@ int build_weight_groups(vet_handle* h, TileSet& t, const std::vector<uint32_t>& 
     }
     std::sort(units.begin(), units.end());
     for (size_t i = 0; i < units.size(); ++i) slot[units[i]] = (int32_t)i;
-    const uint32_t nch = (uint32_t)std::max<size_t>(1, (units.size() + vet::kChunkUnits - 1) / vet::kChunkUnits);
+    const uint32_t nch = (uint32_t)std::max<size_t>(1, (units.size() + S::kChunkUnits - 1) / S::kChunkUnits);
     chunk0[g] = (uint32_t)(chunks.size() / chunk_doubles);
     const size_t base = chunks.size();
     chunks.resize(base + (size_t)nch * chunk_doubles, 0.0);             // zero weights for padding
-    units_all.resize((size_t)(chunk0[g] + nch) * vet::kChunkUnits, 0);  // padding units point at cell 0
-    for (size_t i = 0; i < units.size(); ++i) units_all[(size_t)chunk0[g] * vet::kChunkUnits + i] = units[i] * kQ;
+    units_all.resize((size_t)(chunk0[g] + nch) * S::kChunkUnits, 0);  // padding units point at cell 0
+    for (size_t i = 0; i < units.size(); ++i) units_all[(size_t)chunk0[g] * S::kChunkUnits + i] = units[i] * kQ;
     for (int m = 0; m < kTG; ++m) {
       const int tile = group_tiles[g * kTG + m];
       if (tile < 0) continue;
       for (uint32_t j = col_ptr[tile]; j < col_ptr[tile + 1]; ++j) {
         const size_t i = (size_t)slot[cell_idx[j] / kQ];
         const int q = (int)(cell_idx[j] % kQ);
-        double* ch = chunks.data() + base + (i / vet::kChunkUnits) * chunk_doubles;
-        ch[(m * kQ + q) * vet::kChunkUnits + i % vet::kChunkUnits] = w_val[j];
+        double* ch = chunks.data() + base + (i / S::kChunkUnits) * chunk_doubles;
+        ch[(m * kQ + q) * S::kChunkUnits + i % S::kChunkUnits] = w_val[j];
       }
     }
     for (uint32_t u : units) slot[u] = -1;
   }
   chunk0[G] = (uint32_t)(chunks.size() / chunk_doubles);
-  units_all.resize((size_t)chunk0[G] * vet::kChunkUnits + vet::kUnitPad, 0);
+  units_all.resize((size_t)chunk0[G] * S::kChunkUnits + vet::kUnitPad, 0);
   t.G = G;
   t.nchunks = chunk0[G];
   if (int rc = upload(&t.d_group_tiles, group_tiles.data(), group_tiles.size())) return rc;
@@ -444,7 +447,9 @@ int build_tile_set(vet_handle* h, TileSet& t) {
                                             t.d_cell_idx, t.d_w_val);
     h->launches++;
     VET_CUDA(cudaGetLastError());
-    if (int rc = whist_tall() ? build_weight_groups<vet::WhistTall>(h, t, ptr, unit)
+    const int shape = whist_shape();
+    if (int rc = shape == 1   ? build_weight_groups<vet::WhistTall>(h, t, ptr, unit)
+                 : shape == 2 ? build_weight_groups<vet::WhistQuad>(h, t, ptr, unit)
                               : build_weight_groups<vet::WhistWide>(h, t, ptr, unit))
       return rc;
   }
@@ -686,9 +691,11 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
 // k_whist for tile count k over F frames of the cell histogram `cnt` -> hist[F,T_k]
 int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st) {
   TileSet& t = h->ts[k];
-  const bool tall = whist_tall();
-  const int frames_per_cta = tall ? vet::WhistTall::kFramesPerCta : vet::WhistWide::kFramesPerCta;
-  const size_t wh_smem = (size_t)vet::kWhStages * (tall ? vet::WhistTall::kChunkBytes : vet::WhistWide::kChunkBytes);
+  const int shape = whist_shape();
+  const int frames_per_cta = shape == 1 ? vet::WhistTall::kFramesPerCta : vet::WhistWide::kFramesPerCta;
+  const size_t wh_smem = (size_t)vet::kWhStages * (shape == 1   ? vet::WhistTall::kChunkBytes
+                                                   : shape == 2 ? vet::WhistQuad::kChunkBytes
+                                                                : vet::WhistWide::kChunkBytes);
   const int64_t fblocks = (F + frames_per_cta - 1) / frames_per_cta;
   const int blocks = (int)std::min<int64_t>(fblocks * t.G, h->sm_count);
   if (t.sched_F != F || t.sched_blocks != blocks) {
@@ -711,8 +718,10 @@ int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* h
   a.max_items = t.sched_max_items;
   {
     LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-    if (tall)
+    if (shape == 1)
       vet::k_whist<vet::WhistTall><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
+    else if (shape == 2)
+      vet::k_whist<vet::WhistQuad><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
     else
       vet::k_whist<vet::WhistWide><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
   }
@@ -916,6 +925,8 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
                                   vet::kWhStages * vet::WhistWide::kChunkBytes));
     VET_CUDA(cudaFuncSetAttribute(vet::k_whist<vet::WhistTall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   vet::kWhStages * vet::WhistTall::kChunkBytes));
+    VET_CUDA(cudaFuncSetAttribute(vet::k_whist<vet::WhistQuad>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  vet::kWhStages * vet::WhistQuad::kChunkBytes));
     vet::k_cell_vectors<<<std::min<int64_t>((h->C + 255) / 256, 1024), 256>>>(h->d_cosT, h->d_sinT, h->d_sinP, h->d_cosP,
                                                                                h->W, h->H, h->d_cellvec);
     h->launches++;

@@ -35,26 +35,27 @@ namespace vet {
 #endif
 constexpr int kWhWarps = VET_WHIST_WARPS;        // warps per CTA, two per SM sub-partition; lane 0 of warp 0 doubles as the
                                    // weight-chunk producer (256 threads -> 255 registers each)
-constexpr int kDepth = 4;          // depth of the register ring: counts are fetched kDepth-1 warp steps ahead
-constexpr int kChunkUnits = 32 * kDepth;  // load units per staged weight chunk = kDepth warp steps (the ring is
-                                          // unrolled over them, so its rotation costs no register moves)
 constexpr int kWhStages = 3;
 constexpr int kWhThreads = kWhWarps * 32;
 constexpr int kWhRowPad = 128;     // frames per CTA of the tallest shape: the count scratch has this many spare rows
-constexpr int kUnitPad = 2 * kDepth * 32;  // the unit list is readable this far past its end (prefetch runs ahead)
+constexpr int kUnitPad = 2 * 8 * 32;  // the unit list is readable this far past its end (prefetch runs ahead; depth <= 8)
 
 // Blocking of the contraction: TG tiles per group x FW frames per warp (TG*FW = 64 register
 // accumulators), Q cells per load unit.
-template <int TG_, int FW_, int Q_>
+// DEPTH = depth of the register ring: counts are fetched DEPTH-1 warp steps ahead; a staged
+// weight chunk holds DEPTH warp steps (the ring is unrolled over them, so its rotation costs no moves).
+template <int TG_, int FW_, int Q_, int DEPTH_>
 struct WhistShape {
-  static constexpr int TG = TG_, FW = FW_, Q = Q_;
+  static constexpr int TG = TG_, FW = FW_, Q = Q_, kDepth = DEPTH_;
+  static constexpr int kChunkUnits = 32 * kDepth;  // load units per staged weight chunk
   static constexpr int kChunkCells = kChunkUnits * Q;
   static constexpr int kChunkBytes = kChunkCells * TG * 8;  // weights [TG][Q][kChunkUnits] f64
   static constexpr int kFramesPerCta = kWhWarps * FW;
   static_assert(TG * FW == 64, "the warp reduction below is written for 64 accumulators");
 };
-using WhistWide = WhistShape<8, 8, 2>;    // 8 tiles x 8 frames, counts as aligned pairs
-using WhistTall = WhistShape<4, 16, 1>;   // 4 tiles x 16 frames: 25 % less padding in the dense blocks
+using WhistWide = WhistShape<8, 8, 2, 4>;   // 8 tiles x 8 frames, counts as aligned pairs, 3 steps of prefetch
+using WhistTall = WhistShape<4, 16, 1, 4>;  // 4 tiles x 16 frames: 25 % less padding in the dense blocks
+using WhistQuad = WhistShape<8, 8, 4, 2>;   // counts as aligned quads (LDG.128): half the load instructions
 
 struct WhistArgs {
   const uint32_t* cnt;     // [F + kWhRowPad, cpad]: readable past F (rows of a partial last frame block)
@@ -106,6 +107,12 @@ struct CountUnit<1> {
   __device__ __forceinline__ uint32_t get(int) const { return v; }
 };
 template <>
+struct CountUnit<4> {
+  uint4 v;
+  __device__ __forceinline__ void load(const uint32_t* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ uint32_t get(int j) const { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+};
+template <>
 struct CountUnit<2> {
   uint2 v;
   __device__ __forceinline__ void load(const uint32_t* p) { v = __ldg(reinterpret_cast<const uint2*>(p)); }
@@ -124,7 +131,7 @@ __device__ __forceinline__ void whist_step(const double* sW, int s, int lane, co
   for (int j = 0; j < S::Q; ++j) {
     double w[S::TG];
 #pragma unroll
-    for (int t = T0; t < T1; ++t) w[t] = sW[(t * S::Q + j) * kChunkUnits + s * 32 + lane];
+    for (int t = T0; t < T1; ++t) w[t] = sW[(t * S::Q + j) * S::kChunkUnits + s * 32 + lane];
 #pragma unroll
     for (int r = 0; r < S::FW; ++r) {
       const double v = u32_to_f64(use[r].get(j));
@@ -136,7 +143,7 @@ __device__ __forceinline__ void whist_step(const double* sW, int s, int lane, co
 
 template <typename S>
 __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
-  constexpr int TG = S::TG, FW = S::FW, Q = S::Q;
+  constexpr int TG = S::TG, FW = S::FW, Q = S::Q, kD = S::kDepth;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kWhStages], s_empty[kWhStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,21 +191,21 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
       for (int r = 0; r < FW; ++r) acc[t][r] = 0.0;
 
     // Register pipeline over warp steps (32 load units each).  While step S runs its DFMAs,
-    // the counts of steps S+1 .. S+kDepth-1 are in flight in the ring and the unit indices of
-    // steps up to S+2(kDepth-1) in uring, so L2/DRAM latency is covered by kDepth-1 steps of
+    // the counts of steps S+1 .. S+S::kDepth-1 are in flight in the ring and the unit indices of
+    // steps up to S+2(S::kDepth-1) in uring, so L2/DRAM latency is covered by S::kDepth-1 steps of
     // FP64 work without staging the counts in shared memory.
-    const uint32_t* __restrict__ up = a.units + (size_t)c0 * kChunkUnits + lane;
-    CountUnit<Q> ring[kDepth][FW];
-    uint32_t uring[kDepth];
+    const uint32_t* __restrict__ up = a.units + (size_t)c0 * S::kChunkUnits + lane;
+    CountUnit<Q> ring[S::kDepth][FW];
+    uint32_t uring[S::kDepth];
 #pragma unroll
-    for (int i = 0; i < kDepth - 1; ++i) {
+    for (int i = 0; i < S::kDepth - 1; ++i) {
       const uint32_t* p = row0 + __ldg(up + 32 * i);
 #pragma unroll
       for (int r = 0; r < FW; ++r, p += a.cpad) ring[i][r].load(p);
     }
 #pragma unroll
-    for (int x = kDepth - 1; x < 2 * kDepth - 2; ++x) uring[x % kDepth] = __ldg(up + 32 * x);
-    up += 32 * (2 * kDepth - 2);
+    for (int x = S::kDepth - 1; x < 2 * S::kDepth - 2; ++x) uring[x % S::kDepth] = __ldg(up + 32 * x);
+    up += 32 * (2 * S::kDepth - 2);
 
     for (uint32_t c = c0; c < c1; ++c, ++n) {
       produce(c + kWhStages - 1);
@@ -206,14 +213,14 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
       mbar_wait(smem_u32(&s_full[stage]), (n / kWhStages) & 1u);
       const double* sW = reinterpret_cast<const double*>(smem_raw + stage * S::kChunkBytes);
 #pragma unroll
-      for (int s = 0; s < kDepth; ++s) {
-        // issue the count loads of step S+kDepth-1 and the unit load of step S+2(kDepth-1)
-        const uint32_t* p = row0 + uring[(s + kDepth - 1) % kDepth];
+      for (int s = 0; s < S::kDepth; ++s) {
+        // issue the count loads of step S+S::kDepth-1 and the unit load of step S+2(S::kDepth-1)
+        const uint32_t* p = row0 + uring[(s + S::kDepth - 1) % S::kDepth];
 #ifndef VET_DBG_NO_CNT_LOADS
 #pragma unroll
-        for (int r = 0; r < FW; ++r, p += a.cpad) ring[(s + kDepth - 1) % kDepth][r].load(p);
+        for (int r = 0; r < FW; ++r, p += a.cpad) ring[(s + S::kDepth - 1) % S::kDepth][r].load(p);
 #endif
-        uring[(s + kDepth - 2) % kDepth] = __ldg(up);
+        uring[(s + S::kDepth - 2) % S::kDepth] = __ldg(up);
         up += 32;
         whist_step<S, 0, TG>(sW, s, lane, ring[s], acc);  // step S out of ring[s]
       }
