@@ -268,9 +268,10 @@ def main():
         counter[0] += 1
         drain(slot)  # the all-gather that last read this slot's buffers
         o = outs[slot]
-        eng.spatial(packed, out=o)
-        if args.transition:
-            eng.transition(packed, want_per_k=False, want_pairs0=False)
+        if args.transition:  # both analyzers in one pass over the input (configs[4])
+            eng.analyze(packed, want_per_k=False, want_pairs0=False)
+        else:
+            eng.spatial(packed, out=o)
         if world > 1:  # the path's only exchange: the all-gather of the per-frame results
             pending[slot] = [dist.all_gather_into_tensor(gathered[slot][0], o.entropy, async_op=True)]
             if args.gather_hist0:  # hist0 / assign0 normally stay on the rank that owns the frames

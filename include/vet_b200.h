@@ -164,6 +164,16 @@ int vet_transition(vet_handle* h, const void* packed_dev, int dtype, int64_t F, 
                    double* entropy_dev, double* per_k_dev, int32_t* prev_count0_dev,
                    uint16_t* pairs0_dev, int mode, void* stream);
 
+/* Both analyzers in ONE pass over the packed tensor (BASELINE configs[4]: "weighted spatial +
+ * transition entropy"): the streaming kernel emits the cell histogram, the tile assignment and the
+ * cell ids together, then the spatial epilogue and the transition kernel run on them.  Outputs as in
+ * vet_spatial (sp_*, hist0, assign0) and vet_transition (tr_*, prev_count0, pairs0); optional ones may
+ * be NULL.  Equivalent to calling vet_spatial and vet_transition, minus one read of the input. */
+int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U,
+                double* sp_entropy_dev, double* sp_per_k_dev, double* hist0_dev, uint16_t* assign0_dev,
+                double* tr_entropy_dev, double* tr_per_k_dev, int32_t* prev_count0_dev,
+                uint16_t* pairs0_dev, int mode, void* stream);
+
 /* Host-buffer variants (the reference-facing call: numpy in, numpy out).  The
  * packed tensor is streamed to the device in frame batches through pinned
  * staging buffers, copies overlapped with the kernels; results are copied

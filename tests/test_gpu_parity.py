@@ -524,3 +524,23 @@ def test_analyzers_end_to_end_vs_reference(vet, tmp_path):
             assert np.array_equal(pc, ref["tr_prev_count0"][r])
     sa.create_visualization("e2e_test")
     assert (tmp_path / "out" / "e2e_test.csv").exists()
+
+
+@pytest.mark.parametrize("use_w,tcs", [(True, [200, 20]), (False, [50, 200, 1000]), (False, [200])])
+def test_analyze_equals_separate_stages(vet, use_w, tcs):
+    """vet_analyze (one pass over the input) == vet_spatial + vet_transition: integer outputs bit for bit,
+    entropies to 1e-12 (the unweighted stand-alone path reduces in a different order)."""
+    p = synth(7, 9001, 31337, missing=0.05)
+    e = engine(vet, tcs, fov=90.0, use_w=use_w)
+    sp, tr = e.analyze(dev(p))
+    assert e.poll_flags() == 0
+    sp_ref = e.spatial(dev(p))
+    tr_ref = e.transition(dev(p))
+    for a, b in ((sp.assign0, sp_ref.assign0), (tr.entropy, tr_ref.entropy), (tr.per_k, tr_ref.per_k),
+                 (tr.prev_count0, tr_ref.prev_count0), (tr.pairs0, tr_ref.pairs0)):
+        assert np.array_equal(a.cpu().numpy(), b.cpu().numpy(), equal_nan=True)
+    for a, b in ((sp.entropy, sp_ref.entropy), (sp.per_k, sp_ref.per_k), (sp.hist0, sp_ref.hist0)):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-12, atol=0)
+    ref = orc.spatial_analyzer(p, W0, H0, tcs, 90.0, use_w, 2.0)
+    np.testing.assert_allclose(sp.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL)
+    e.close()

@@ -62,6 +62,7 @@ SYMBOLS = {
     "vet_transition_vectors": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, C.c_int, _P]),
     "vet_spatial": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, _P]),
     "vet_transition": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, C.c_int, _P]),
+    "vet_analyze": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "vet_spatial_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P]),
     "vet_transition_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, C.c_int]),
     "vet_poll_flags": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),

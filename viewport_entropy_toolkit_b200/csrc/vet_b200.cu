@@ -108,6 +108,8 @@ struct vet_handle {
   size_t cells_bytes = 0;
   uint32_t* d_tables = nullptr;
   size_t tables_words = 0;
+  uint32_t* d_pairs = nullptr;  // [CTAs, U] packed (prev, cur) tiles of the frame pair in flight (k_transition2)
+  size_t pairs_bytes = 0;
   uint32_t tables_cap = 0;  // slot count the tables are currently laid out (and cleared) for
   int tables_blocks = 0;    // number of per-CTA tables cleared for that layout
   // host-buffer path
@@ -540,13 +542,20 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
     const dim3 grid(blocks), block(vet::kStreamThreads);
 #define VET_LAUNCH_STREAM(TIN, TLUT, ASSIGN, CELLS) vet::k_stream_tma<TIN, TLUT, ASSIGN, CELLS><<<grid, block, smem, st>>>(A)
     const int cmode = a.cell16 ? 1 : (a.cell32 ? 2 : 0);
-    if (assign0) {  // spatial stage: assignments, no cell ids
+#define VET_LAUNCH_ASSIGN(TIN, CELLS)                              \
+  do {                                                             \
+    if (lut8) VET_LAUNCH_STREAM(TIN, uint8_t, true, CELLS);        \
+    else VET_LAUNCH_STREAM(TIN, uint16_t, true, CELLS);            \
+  } while (0)
+    if (assign0) {  // spatial stage (cmode 0) or both analyzers in one pass (cell ids as well)
       if (dtype == VET_F32) {
-        if (lut8) VET_LAUNCH_STREAM(float, uint8_t, true, 0);
-        else VET_LAUNCH_STREAM(float, uint16_t, true, 0);
+        if (cmode == 0) VET_LAUNCH_ASSIGN(float, 0);
+        else if (cmode == 1) VET_LAUNCH_ASSIGN(float, 1);
+        else VET_LAUNCH_ASSIGN(float, 2);
       } else {
-        if (lut8) VET_LAUNCH_STREAM(double, uint8_t, true, 0);
-        else VET_LAUNCH_STREAM(double, uint16_t, true, 0);
+        if (cmode == 0) VET_LAUNCH_ASSIGN(double, 0);
+        else if (cmode == 1) VET_LAUNCH_ASSIGN(double, 1);
+        else VET_LAUNCH_ASSIGN(double, 2);
       }
     } else if (dtype == VET_F32) {
       if (cmode == 0) VET_LAUNCH_STREAM(float, uint8_t, false, 0);
@@ -557,6 +566,7 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
       else if (cmode == 1) VET_LAUNCH_STREAM(double, uint8_t, false, 1);
       else VET_LAUNCH_STREAM(double, uint8_t, false, 2);
     }
+#undef VET_LAUNCH_ASSIGN
 #undef VET_LAUNCH_STREAM
   } else {
     const size_t smem = stream_smem_bytes(h);
@@ -945,6 +955,14 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
       VET_SMEM_ATTR(float, uint16_t, true, 0);
       VET_SMEM_ATTR(double, uint8_t, true, 0);
       VET_SMEM_ATTR(double, uint16_t, true, 0);
+      VET_SMEM_ATTR(float, uint8_t, true, 1);
+      VET_SMEM_ATTR(float, uint16_t, true, 1);
+      VET_SMEM_ATTR(double, uint8_t, true, 1);
+      VET_SMEM_ATTR(double, uint16_t, true, 1);
+      VET_SMEM_ATTR(float, uint8_t, true, 2);
+      VET_SMEM_ATTR(float, uint16_t, true, 2);
+      VET_SMEM_ATTR(double, uint8_t, true, 2);
+      VET_SMEM_ATTR(double, uint16_t, true, 2);
       VET_SMEM_ATTR(float, uint8_t, false, 0);
       VET_SMEM_ATTR(float, uint8_t, false, 1);
       VET_SMEM_ATTR(float, uint8_t, false, 2);
@@ -985,6 +1003,7 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_ihist);
   for (void* p : h->d_vscratch) cudaFree(p);
   cudaFree(h->d_tables);
+  cudaFree(h->d_pairs);
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);
   for (void* p : h->d_hout) cudaFree(p);
@@ -1140,6 +1159,66 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
     a.mode = mode;
     a.flags = h->d_flags;
     if (int rc = launch_transition(h, a, nf - 1, U, h->maxT, st)) return rc;
+    if (nf == F - f0) break;
+  }
+  return VET_OK;
+}
+
+extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* sp_entropy_dev,
+                           double* sp_per_k_dev, double* hist0_dev, uint16_t* assign0_dev, double* tr_entropy_dev,
+                           double* tr_per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode, void* stream) {
+  if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
+  if (F == 0) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");
+  if (!packed_dev || !sp_entropy_dev || (F > 1 && !tr_entropy_dev)) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  if (U >= 0xFFFFFFFFll) return fail(VET_ERR_UNSUPPORTED, "too many users");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->direct_only || F == 1) {  // no shared pass to gain: run the two stages one after the other
+    if (int rc = vet_spatial(h, packed_dev, dtype, F, U, sp_entropy_dev, sp_per_k_dev, hist0_dev, assign0_dev, stream)) return rc;
+    return vet_transition(h, packed_dev, dtype, F, U, tr_entropy_dev, tr_per_k_dev, prev_count0_dev, pairs0_dev, mode, stream);
+  }
+  const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
+  const size_t csz = h->C <= 65535 ? 2 : 4;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)(fb + vet::kWhRowPad) * h->Cpad * 4)) return rc;
+  if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
+  if (int rc = grow(&h->d_cells, &h->cells_bytes, (size_t)fb * U * csz)) return rc;
+  // the streaming kernel always writes assignments here (its LUT copy is what selects the fused variant)
+  uint16_t* assign = assign0_dev;
+  if (!assign) {
+    if (int rc = grow(&h->d_vscratch[0], &h->vscratch_bytes[0], (size_t)fb * U * 2)) return rc;
+  }
+  const size_t esz = dtype == VET_F32 ? 4 : 8;
+  const int T0 = h->ts[0].T;
+  for (int64_t f0 = 0; f0 < F; f0 += fb - 1) {  // batches overlap by the halo frame of the transition stage
+    const int64_t nf = std::min(fb, F - f0);
+    const char* in = (const char*)packed_dev + (size_t)f0 * U * 3 * esz;
+    uint16_t* asg = assign ? assign + f0 * U : (uint16_t*)h->d_vscratch[0];
+    if (int rc = launch_stream(h, in, dtype, nf, U, asg, true, st)) return rc;
+    if (int rc = launch_epilogue(h, nf, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
+                                 hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
+      return rc;
+    if (nf >= 2) {
+      vet::TransitionArgs a{};
+      a.cell16 = csz == 2 ? (const uint16_t*)h->d_cells : nullptr;
+      a.cell32 = csz == 4 ? (const int32_t*)h->d_cells : nullptr;
+      a.F = nf;
+      a.U = U;
+      a.K = h->K;
+      for (int k = 0; k < h->K; ++k) {
+        a.T[k] = h->ts[k].T;
+        a.lut[k] = h->ts[k].d_lut;
+      }
+      a.entropy = tr_entropy_dev + f0;
+      a.per_k = tr_per_k_dev ? tr_per_k_dev + f0 : nullptr;
+      a.per_k_stride = F - 1;
+      a.prev_count0 = prev_count0_dev ? prev_count0_dev + f0 * T0 : nullptr;
+      a.pairs0 = pairs0_dev ? pairs0_dev + f0 * U * 2 : nullptr;
+      a.mode = mode;
+      a.flags = h->d_flags;
+      if (int rc = launch_transition(h, a, nf - 1, U, h->maxT, st)) return rc;
+    }
     if (nf == F - f0) break;
   }
   return VET_OK;
@@ -1391,7 +1470,26 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         A2.mode[k] = vet::kTrGlobal;
       }
     }
-    const size_t smem2 = tile_bytes + table_words * 4 + 64;
+    // LUT staging area after the table area, for the tile counts whose LUT still fits
+    const size_t lut_off = (tile_bytes + table_words * 4 + 64 + 15) & ~(size_t)15;
+    size_t lut_area = 0;
+    for (int k = 0; k < a.K; ++k) {
+      // a.lut[k] is one of the handle's uint16 LUTs (or the identity table of the vectors path)
+      const uint8_t* l8 = nullptr;
+      for (int j = 0; j < h->K; ++j)
+        if (h->ts[j].d_lut == a.lut[k]) l8 = h->ts[j].d_lut8;
+      const bool is_cell_lut = a.lut[k] != h->d_identity;
+      const size_t bytes = (((size_t)h->C * (l8 ? 1 : 2)) + 15) & ~(size_t)15;
+      A2.lut8[k] = l8;
+      A2.lut_smem[k] = (is_cell_lut && lut_off + bytes <= budget) ? 1 : 0;
+      if (A2.lut_smem[k]) lut_area = std::max(lut_area, bytes);
+    }
+    A2.lut_area_off = (int)lut_off;
+    const size_t smem2 = lut_off + lut_area;
+    // packed (prev | cur << 16) per user, one row per CTA
+    if (int rc = grow((void**)&h->d_pairs, &h->pairs_bytes, (size_t)blocks * U * 4)) return rc;
+    A2.pair_scratch = h->d_pairs;
+    A2.t.C = (int)h->C;
     VET_CUDA(cudaFuncSetAttribute(vet::k_transition2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
     vet::k_transition2<<<blocks, vet::kTrThreads, smem2, st>>>(A2, Tmax);

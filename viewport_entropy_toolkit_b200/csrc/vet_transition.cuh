@@ -61,6 +61,7 @@ struct TransitionArgs {
   const uint16_t* cell16;  // [F,U] cell ids (0xFFFF = missing) or null
   const int32_t* cell32;   // [F,U] (-1 = missing) or null
   int64_t F, U;            // rows r in [0, F-1) pair frames (r, r+1)
+  int C;                   // cells per LUT (k_transition2 stages LUTs in shared memory)
   int K;
   int T[kMaxTileCounts];
   const uint16_t* lut[kMaxTileCounts];

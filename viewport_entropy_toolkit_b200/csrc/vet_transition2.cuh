@@ -25,6 +25,10 @@ enum : int { kTrDense = 0, kTrHash = 1, kTrGlobal = 2 };
 struct Transition2Args {
   TransitionArgs t;               // shared fields; t.cap / t.g_tables describe the per-CTA global fallback table
   int mode[kMaxTileCounts];       // kTrDense / kTrHash / kTrGlobal per tile count
+  int lut_smem[kMaxTileCounts];   // 1: the tile count's LUT is staged in shared memory (uint8 when T <= 255 else uint16)
+  const uint8_t* lut8[kMaxTileCounts];  // uint8 LUTs (null when T > 255)
+  int lut_area_off;               // byte offset of the LUT staging area inside dynamic shared memory
+  uint32_t* pair_scratch;         // [gridDim.x, U] (prev | cur << 16) of the current frame pair and tile count
 };
 
 // per previous tile: users, first user, distinct keys, count of the latest key, latest key
@@ -43,13 +47,29 @@ __device__ __forceinline__ void clear_tiles(const TileArrays& ta, int T) {
   }
 }
 
-// Walks the users of a frame pair kUnr at a time per thread: all cell ids first, then all tile
-// lookups, then the action -- 2*kUnr independent loads in flight per thread instead of a
-// dependent load -> lookup -> atomic chain per user (the passes are latency bound otherwise).
+// Tile lookup of one cell id: shared-memory LUT (uint8 / uint16) when it was staged, else the
+// global uint16 LUT.  A 32-lane gather in a 20-40 KB global table touches ~30 cache lines (one
+// L1 wavefront each); in shared memory it costs its bank-conflict degree (3-4).
+struct LutView {
+  const uint8_t* s8;
+  const uint16_t* s16;
+  const uint16_t* g16;
+  __device__ __forceinline__ uint32_t operator()(int cell) const {
+    if (s8) return s8[cell];
+    if (s16) return s16[cell];
+    return g16[cell];
+  }
+};
+
 constexpr int kUnr = 8;
-template <typename F>
-__device__ __forceinline__ void for_common_users(const TransitionArgs& a, const uint16_t* __restrict__ lut, int64_t prow,
-                                                 int64_t crow, bool also_missing, F&& fn) {
+constexpr uint32_t kNoPair = 0xFFFFFFFFu;
+
+// pass 1: looks every common user's (prev, cur) tiles up ONCE, stores them packed for the later
+// passes, counts users per previous tile and finds each tile's first user (EU:271-276, 289-292).
+// kUnr users per thread: all cell ids first, then all lookups, then the atomics, so 2*kUnr
+// independent loads are in flight per thread.
+__device__ __forceinline__ void pass_count(const TransitionArgs& a, const LutView& lut, int64_t prow, int64_t crow,
+                                           const TileArrays& ta, uint32_t* __restrict__ pairs, bool write_pairs0) {
   for (int64_t u0 = 0; u0 < a.U; u0 += (int64_t)blockDim.x * kUnr) {
     int cp[kUnr], cc[kUnr];
 #pragma unroll
@@ -62,40 +82,43 @@ __device__ __forceinline__ void for_common_users(const TransitionArgs& a, const 
         cc[j] = load_cell(a, crow + u);
       }
     }
-    uint32_t p[kUnr], c[kUnr];
+    uint32_t pc[kUnr];
 #pragma unroll
-    for (int j = 0; j < kUnr; ++j) {
-      const bool ok = cp[j] >= 0 && cc[j] >= 0;
-      p[j] = ok ? (uint32_t)lut[cp[j]] : (uint32_t)VET_MISSING;
-      c[j] = ok ? (uint32_t)lut[cc[j]] : (uint32_t)VET_MISSING;
-    }
+    for (int j = 0; j < kUnr; ++j) pc[j] = (cp[j] >= 0 && cc[j] >= 0) ? (lut(cp[j]) | (lut(cc[j]) << 16)) : kNoPair;
 #pragma unroll
     for (int j = 0; j < kUnr; ++j) {
       const int64_t u = u0 + threadIdx.x + (int64_t)j * blockDim.x;
-      if (u < a.U && (also_missing || p[j] != (uint32_t)VET_MISSING)) fn((uint32_t)u, p[j], c[j]);
+      if (u >= a.U) continue;
+      pairs[u] = pc[j];
+      if (pc[j] != kNoPair) {
+        const uint32_t p = pc[j] & 0xFFFFu;
+        atomicAdd(&ta.m[p], 1u);
+        atomicMin(&ta.first[p], (uint32_t)u);
+      }
+      if (write_pairs0) *reinterpret_cast<uint32_t*>(a.pairs0 + 2 * (prow + u)) = pc[j];  // (prev, cur) or (0xFFFF, 0xFFFF)
     }
   }
 }
 
-// pass 1: users per previous tile and the first user of each (EU:271-276, 289-292)
-__device__ __forceinline__ void pass_count(const TransitionArgs& a, const uint16_t* __restrict__ lut, int64_t prow, int64_t crow,
-                                           const TileArrays& ta, bool write_pairs) {
-  for_common_users(a, lut, prow, crow, write_pairs, [&](uint32_t u, uint32_t p, uint32_t c) {
-    if (p != (uint32_t)VET_MISSING) {
-      atomicAdd(&ta.m[p], 1u);
-      atomicMin(&ta.first[p], u);
+// later passes: the packed pairs of the common users, kUnr per thread
+template <typename F>
+__device__ __forceinline__ void for_pairs(const TransitionArgs& a, const uint32_t* __restrict__ pairs, F&& fn) {
+  for (int64_t u0 = 0; u0 < a.U; u0 += (int64_t)blockDim.x * kUnr) {
+    uint32_t pc[kUnr];
+#pragma unroll
+    for (int j = 0; j < kUnr; ++j) {
+      const int64_t u = u0 + threadIdx.x + (int64_t)j * blockDim.x;
+      pc[j] = u < a.U ? __ldcg(pairs + u) : kNoPair;
     }
-    if (write_pairs) {
-      a.pairs0[2 * (prow + u) + 0] = (uint16_t)p;
-      a.pairs0[2 * (prow + u) + 1] = (uint16_t)c;
-    }
-  });
+#pragma unroll
+    for (int j = 0; j < kUnr; ++j)
+      if (pc[j] != kNoPair) fn((uint32_t)(u0 + threadIdx.x + (int64_t)j * blockDim.x), pc[j] & 0xFFFFu, pc[j] >> 16);
+  }
 }
 
 // pass 3: occurrences of the latest key among the non-first users (EU:308, stale weight)
-__device__ __forceinline__ void pass_latest(const TransitionArgs& a, const uint16_t* __restrict__ lut, int64_t prow,
-                                            int64_t crow, const TileArrays& ta) {
-  for_common_users(a, lut, prow, crow, false, [&](uint32_t u, uint32_t p, uint32_t c) {
+__device__ __forceinline__ void pass_latest(const TransitionArgs& a, const uint32_t* __restrict__ pairs, const TileArrays& ta) {
+  for_pairs(a, pairs, [&](uint32_t u, uint32_t p, uint32_t c) {
     if (ta.first[p] != u && (uint32_t)ta.latest[p] == c) atomicAdd(&ta.wcnt[p], 1u);
   });
 }
@@ -168,15 +191,30 @@ __global__ void __launch_bounds__(kTrThreads, 1) k_transition2(Transition2Args A
   stb.list = s_tab + 2 * kHashSlots;
   stb.mask = kHashSlots - 1;
 
+  uint32_t* __restrict__ pairs = A.pair_scratch + (size_t)blockIdx.x * a.U;
+  unsigned char* s_lutarea = smem_raw + A.lut_area_off;
+  int staged_k = -1;
   for (int64_t r = blockIdx.x; r < a.F - 1; r += gridDim.x) {
     const int64_t prow = r * a.U, crow = (r + 1) * a.U;
     double esum = 0.0;
     for (int k = 0; k < a.K; ++k) {
       const int T = a.T[k];
-      const uint16_t* __restrict__ lut = a.lut[k];
+      LutView lut{nullptr, nullptr, a.lut[k]};
+      if (A.lut_smem[k]) {
+        const bool narrow = A.lut8[k] != nullptr;
+        if (staged_k != k) {  // with one tile count the LUT is staged once for the whole launch
+          const int bytes = a.C * (narrow ? 1 : 2);
+          const uint4* __restrict__ src = reinterpret_cast<const uint4*>(narrow ? (const void*)A.lut8[k] : (const void*)a.lut[k]);
+          uint4* dst = reinterpret_cast<uint4*>(s_lutarea);
+          for (int i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+          staged_k = k;
+        }
+        if (narrow) lut.s8 = s_lutarea;
+        else lut.s16 = reinterpret_cast<const uint16_t*>(s_lutarea);
+      }
       clear_tiles(ta, T);
       __syncthreads();
-      pass_count(a, lut, prow, crow, ta, k == 0 && a.pairs0 != nullptr);
+      pass_count(a, lut, prow, crow, ta, pairs, k == 0 && a.pairs0 != nullptr);
       __syncthreads();
       unsigned long long tloc = 0;
       for (int t = threadIdx.x; t < T; t += blockDim.x) tloc += ta.m[t];
@@ -185,7 +223,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) k_transition2(Transition2Args A
       int mode = A.mode[k];
       if (mode == kTrDense) {
         // pass 2: smallest non-first user index of every (prev,cur)
-        for_common_users(a, lut, prow, crow, false, [&](uint32_t u, uint32_t p, uint32_t c) {
+        for_pairs(a, pairs, [&](uint32_t u, uint32_t p, uint32_t c) {
           if (ta.first[p] != u) atomicMin(&s_tab[p * (uint32_t)T + c], u);
         });
         __syncthreads();
@@ -212,7 +250,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) k_transition2(Transition2Args A
         __syncthreads();
       } else {
         if (mode == kTrHash) {
-          for_common_users(a, lut, prow, crow, false, [&](uint32_t u, uint32_t p, uint32_t c) {
+          for_pairs(a, pairs, [&](uint32_t u, uint32_t p, uint32_t c) {
             if (ta.first[p] == u || *(volatile uint32_t*)&s_overflow) return;
             const uint32_t key = p * (uint32_t)T + c;
             uint32_t slot = (key * 2654435761u) & stb.mask;
@@ -247,7 +285,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) k_transition2(Transition2Args A
           }
         }
         if (mode == kTrGlobal) {
-          for_common_users(a, lut, prow, crow, false, [&](uint32_t u, uint32_t p, uint32_t c) {
+          for_pairs(a, pairs, [&](uint32_t u, uint32_t p, uint32_t c) {
             if (ta.first[p] != u) pair_insert<false>(gtb, p * (uint32_t)T + c, u, &s_used, false);
           });
           __syncthreads();
@@ -277,7 +315,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) k_transition2(Transition2Args A
         __syncthreads();
         if (threadIdx.x == 0) s_used = 0u;
       }
-      pass_latest(a, lut, prow, crow, ta);
+      pass_latest(a, pairs, ta);
       __syncthreads();
       double e = literal_entropy(ta, T, total, s_red);
       if (total == 0.0) {

@@ -304,6 +304,36 @@ class Engine:
                                         _ptr(out.prev_count0), _ptr(out.pairs0), m, self._stream()))
         return out
 
+    # -- both analyzers in one pass ----------------------------------------------------------
+    def analyze(self, packed: torch.Tensor, mode: str = "literal", want_per_k: bool = True, want_hist0: bool = True,
+                want_assign0: bool = True, want_prev_count0: bool = True,
+                want_pairs0: bool = True) -> Tuple[SpatialResult, TransitionResult]:
+        """SpatialEntropyAnalyzer.compute_entropy and TransitionEntropyAnalyzer.compute_entropy on
+        the same packed tensor with a single read of the input (vet_analyze)."""
+        p, dt = self._packed(packed)
+        if p.dim() != 3:
+            raise ValueError("packed must be [F, U, 3]")
+        if mode not in ("literal", "textbook"):
+            raise ValueError("mode must be 'literal' or 'textbook'")
+        F, U = int(p.shape[0]), int(p.shape[1])
+        R = max(F - 1, 0)
+        K, T0, dev = len(self.tile_counts), self.num_tiles[0], self.device
+        sp = SpatialResult(
+            entropy=torch.empty(F, dtype=torch.float64, device=dev),
+            per_k=torch.empty((K, F), dtype=torch.float64, device=dev) if want_per_k else None,
+            hist0=torch.empty((F, T0), dtype=torch.float64, device=dev) if want_hist0 else None,
+            assign0=torch.empty((F, U), dtype=torch.uint16, device=dev) if want_assign0 else None)
+        tr = TransitionResult(
+            entropy=torch.empty(R, dtype=torch.float64, device=dev),
+            per_k=torch.empty((K, R), dtype=torch.float64, device=dev) if want_per_k else None,
+            prev_count0=torch.empty((R, T0), dtype=torch.int32, device=dev) if want_prev_count0 else None,
+            pairs0=torch.empty((R, U, 2), dtype=torch.uint16, device=dev) if want_pairs0 else None)
+        m = N.VET_TRANSITION_LITERAL if mode == "literal" else N.VET_TRANSITION_TEXTBOOK
+        _check(self._lib.vet_analyze(self._h, p.data_ptr(), dt, F, U, sp.entropy.data_ptr(), _ptr(sp.per_k), _ptr(sp.hist0),
+                                     _ptr(sp.assign0), tr.entropy.data_ptr(), _ptr(tr.per_k), _ptr(tr.prev_count0),
+                                     _ptr(tr.pairs0), m, self._stream()))
+        return sp, tr
+
     # -- host-buffer (numpy) variants -----------------------------------------------------
     def spatial_host(self, packed: np.ndarray, want_per_k: bool = True, want_hist0: bool = True,
                      want_assign0: bool = True, reuse_buffers: bool = False) -> Dict[str, Optional[np.ndarray]]:
