@@ -97,6 +97,7 @@ struct vet_handle {
   uint32_t* d_nvalid = nullptr;  // [frames] present users per frame
   size_t nvalid_bytes = 0;
   uint32_t* d_work = nullptr;    // work counters of the dynamic schedulers
+  uint32_t* d_lut_packed = nullptr;  // [C] byte k = tile under tile count k (K <= 4 and every T <= 255), else null
   uint32_t* d_ihist = nullptr;   // [frames, sum T_k] integer tile histograms (direct unweighted path)
   size_t ihist_bytes = 0;
   int sumT = 0;
@@ -618,6 +619,8 @@ TilesPlan plan_tiles(const vet_handle* h, const void* packed, int64_t U) {
   p.A.K = h->K;
   p.A.sumT = hoff;
   p.A.shist_words = soff;
+  p.A.lut_packed = h->d_lut_packed;
+  if (h->d_lut_packed) off = (int)(((size_t)h->C * 4 + 15) & ~(size_t)15);
   p.A.lut_bytes = off;
   p.smem = (size_t)vet::kStages * vet::kStageBytes + (size_t)((soff + 3) & ~3) * 4 + off + 16;
   p.ok = p.smem + kStaticSmemSlack <= h->smem_optin;
@@ -652,23 +655,30 @@ int launch_stream_tiles(vet_handle* h, TilesPlan& p, const void* packed, int dty
   const int blocks = (int)std::min<int64_t>(F * a.chunks_per_frame, h->sm_count);
   const int sm = (int)(h->smem_optin - kStaticSmemSlack);
   LaunchTimer lt(h, VET_KERNEL_STREAM, st);
+#define VET_LAUNCH_TILES(TIN, ASSIGN, KP)                                                                              \
+  do {                                                                                                                  \
+    VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tiles<TIN, ASSIGN, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+    vet::k_stream_tiles<TIN, ASSIGN, KP><<<blocks, vet::kStreamThreads, p.smem, st>>>(p.A);                             \
+  } while (0)
+#define VET_LAUNCH_TILES_K(TIN, ASSIGN)                        \
+  do {                                                         \
+    switch (h->d_lut_packed ? h->K : 0) {                      \
+      case 1: VET_LAUNCH_TILES(TIN, ASSIGN, 1); break;         \
+      case 2: VET_LAUNCH_TILES(TIN, ASSIGN, 2); break;         \
+      case 3: VET_LAUNCH_TILES(TIN, ASSIGN, 3); break;         \
+      case 4: VET_LAUNCH_TILES(TIN, ASSIGN, 4); break;         \
+      default: VET_LAUNCH_TILES(TIN, ASSIGN, 0); break;        \
+    }                                                          \
+  } while (0)
   if (dtype == VET_F32) {
-    if (assign0) {
-      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tiles<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      vet::k_stream_tiles<float, true><<<blocks, vet::kStreamThreads, p.smem, st>>>(p.A);
-    } else {
-      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tiles<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      vet::k_stream_tiles<float, false><<<blocks, vet::kStreamThreads, p.smem, st>>>(p.A);
-    }
+    if (assign0) VET_LAUNCH_TILES_K(float, true);
+    else VET_LAUNCH_TILES_K(float, false);
   } else {
-    if (assign0) {
-      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tiles<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      vet::k_stream_tiles<double, true><<<blocks, vet::kStreamThreads, p.smem, st>>>(p.A);
-    } else {
-      VET_CUDA(cudaFuncSetAttribute(vet::k_stream_tiles<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      vet::k_stream_tiles<double, false><<<blocks, vet::kStreamThreads, p.smem, st>>>(p.A);
-    }
+    if (assign0) VET_LAUNCH_TILES_K(double, true);
+    else VET_LAUNCH_TILES_K(double, false);
   }
+#undef VET_LAUNCH_TILES_K
+#undef VET_LAUNCH_TILES
   VET_CUDA(cudaGetLastError());
   return VET_OK;
 }
@@ -943,6 +953,12 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
     VET_CUDA(cudaGetLastError());
     for (int k = 0; k < h->K; ++k)
       if (int rc = build_tile_set(h, h->ts[k])) return rc;
+    if (h->K <= 4 && h->maxT <= 255) {
+      std::vector<uint32_t> packed_lut(h->C + 4, 0);
+      for (int k = 0; k < h->K; ++k)
+        for (int64_t c = 0; c < h->C; ++c) packed_lut[c] |= (uint32_t)h->ts[k].h_lut[c] << (8 * k);
+      if (int rc = upload(&h->d_lut_packed, packed_lut.data(), packed_lut.size())) return rc;
+    }
     // The attribute is per function, not per handle: always allow the device maximum so that
     // handles of different configurations can coexist.
     const size_t sm = h->smem_optin - kStaticSmemSlack;
@@ -1001,6 +1017,7 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_cells);
   cudaFree(h->d_identity);
   cudaFree(h->d_ihist);
+  cudaFree(h->d_lut_packed);
   for (void* p : h->d_vscratch) cudaFree(p);
   cudaFree(h->d_tables);
   cudaFree(h->d_pairs);

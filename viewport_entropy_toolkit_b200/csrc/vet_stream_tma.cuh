@@ -304,10 +304,14 @@ struct StreamTilesArgs {
   int lut_wide[kMaxTileCounts];        // 1 = uint16 entries, 0 = uint8
   const void* lut[kMaxTileCounts];     // global LUTs (uint8 when T <= 255 else uint16)
   int lut_bytes;                       // total bytes of the shared-memory LUT area
+  const uint32_t* lut_packed;          // [C] byte k = tile of tile count k (K <= 4, every T <= 255), or null
   uint32_t* ihist;                     // [F, sumT] integer tile histograms (pre-zeroed when chunks_per_frame > 1)
 };
 
-template <typename TIN, bool ASSIGN>
+// KP > 0: packed variant for KP <= 4 tile counts that all fit a byte: ONE 32-bit shared-memory load
+// yields the sample's tile under every tile count and the per-count loop is unrolled (the generic
+// loop spends ~25 instructions per sample and tile count on parameter loads and address math).
+template <typename TIN, bool ASSIGN, int KP>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tiles(StreamTilesArgs A) {
   constexpr int kTileSamples = kTileBytes / (3 * (int)sizeof(TIN));
   constexpr int kPerThread = kTileSamples / (kConsumerWarps * 32);
@@ -330,7 +334,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tiles(StreamTilesA
     s_nvalid = 0u;
   }
   for (int t = threadIdx.x; t < A.shist_words; t += blockDim.x) s_hist[t] = 0u;
-  for (int k = 0; k < A.K; ++k) copy_to_smem16(s_lut + A.lut_off[k], A.lut[k], a.C * (A.lut_wide[k] ? 2 : 1));
+  if (KP > 0) {
+    copy_to_smem16(s_lut, A.lut_packed, a.C * 4);
+  } else {
+    for (int k = 0; k < A.K; ++k) copy_to_smem16(s_lut + A.lut_off[k], A.lut[k], a.C * (A.lut_wide[k] ? 2 : 1));
+  }
   __syncthreads();
 
   if (warp == 0) {
@@ -344,6 +352,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tiles(StreamTilesA
   const int ctid = threadIdx.x - 32;
   const float Wf = (float)a.W, Hf = (float)a.H;
   const int W1 = a.W + 1;
+  uint32_t* hk[KP > 0 ? KP : 1];  // packed variant: base of every tile count's histogram, in registers
+#pragma unroll
+  for (int k = 0; k < (KP > 0 ? KP : 1); ++k) hk[k] = s_hist + A.shist_off[k];
+  const uint32_t* s_lut32 = reinterpret_cast<const uint32_t*>(s_lut);
   uint32_t n = 0;
   uint32_t bad = 0;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
@@ -377,6 +389,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tiles(StreamTilesA
           if (ok) {
             const int cell = pixel_of(mv[j], Hf, a.H) * W1 + pixel_of(mu[j], Wf, a.W);
             ++nv;
+            if (KP > 0) {
+              const uint32_t w = s_lut32[cell];
+              t0 = w & 0xFFu;
+#pragma unroll
+              for (int k = 0; k < KP; ++k) atomicAdd(hk[k] + ((w >> (8 * k)) & 0xFFu), 1u);
+            } else
             for (int k = 0; k < A.K; ++k) {
               const unsigned char* l = s_lut + A.lut_off[k];
               const uint32_t t = A.lut_wide[k] ? (uint32_t) reinterpret_cast<const uint16_t*>(l)[cell] : (uint32_t)l[cell];
