@@ -332,8 +332,16 @@ def main():
     stream_ms = k_ms / max(k_n, 1)
     launch_bytes = ALG_BYTES_PER_SAMPLE * F * U  # one launch of the streaming kernel covers the whole batch
     achieved = launch_bytes / (stream_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+    # DRAM bytes of one launch from the committed ncu --set full capture (profiles/), configs[2] only
+    traffic = None
+    try:
+        tr_rec = json.loads((ROOT / "profiles" / "r01e_traffic.json").read_text())
+        if args.workload == tr_rec["workload"]:
+            traffic = tr_rec["dram_bytes_read"] + tr_rec["dram_bytes_write"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_stream_tma", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": stream_ms, "launches": k_n,
                 "step_share": {k: prof[k][0] / ms for k in prof if prof[k][1]},
                 "whole_step_frac": (ALG_BYTES_PER_SAMPLE * F * U / (ms / args.steps * 1e-3) / 1e9) / peak_gbs,

@@ -544,3 +544,67 @@ def test_analyze_equals_separate_stages(vet, use_w, tcs):
     ref = orc.spatial_analyzer(p, W0, H0, tcs, 90.0, use_w, 2.0)
     np.testing.assert_allclose(sp.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL)
     e.close()
+
+
+@pytest.mark.parametrize("use_w", [True, False])
+def test_many_frames_cross_internal_batches(vet, use_w):
+    """More frames than one internal scratch batch holds (the cell-histogram scratch is capped at
+    1 GiB = ~13k frames): batch offsets, unaligned batch bases and the transition halo frame."""
+    F, U = 27001, 5
+    p = synth(F, U, 777, iid=True, missing=0.1)
+    e = engine(vet, [20], fov=100.0, use_w=use_w)
+    sp, tr = e.analyze(dev(p))
+    sp2 = e.spatial(dev(p))
+    assert e.poll_flags() == 0
+    px, py, ok = orc.decode(p[..., 1], p[..., 2], W0, H0)
+    lut = orc.cell_luts(W0, H0, [20])[0]
+    assign = np.where(ok, lut[py * 101 + px], 0xFFFF).astype(np.uint16)
+    assert np.array_equal(sp.assign0.cpu().numpy(), assign) and np.array_equal(sp2.assign0.cpu().numpy(), assign)
+    sel = np.r_[0:40, 13100:13140, F - 40:F]          # around the batch boundaries and both ends
+    ref = orc.spatial_analyzer(p[sel], W0, H0, [20], 100.0, use_w, 2.0)
+    np.testing.assert_allclose(sp.entropy.cpu().numpy()[sel], ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    np.testing.assert_allclose(sp2.entropy.cpu().numpy()[sel], ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    np.testing.assert_allclose(sp.hist0.cpu().numpy()[sel], ref["hist0"], rtol=RTOL, atol=ATOL)
+    pairs = tr.pairs0.cpu().numpy()
+    both = ok[:-1] & ok[1:]
+    assert np.array_equal(pairs[..., 0], np.where(both, assign[:-1], 0xFFFF))
+    assert np.array_equal(pairs[..., 1], np.where(both, assign[1:], 0xFFFF))
+    rows = np.r_[0:30, 13090:13140, F - 31:F - 1]
+    for r in rows:
+        if both[r].sum() == 0:
+            continue
+        e_ref, m_ref = orc.transition_entropy(assign[r][both[r]].astype(int), assign[r + 1][both[r]].astype(int), 21)
+        np.testing.assert_allclose(float(tr.entropy[r]), e_ref, rtol=RTOL, atol=ATOL, equal_nan=True)
+        assert np.array_equal(tr.prev_count0[r].cpu().numpy(), m_ref)
+    e.poll_flags()
+    e.close()
+
+
+def test_full_size_properties_configs2(vet):
+    """BASELINE configs[2] at FULL size (100k users x 3600 frames, 201 tiles, fov=90): checks that do
+    not need the oracle -- every assignment equals the exhaustive LUT of its cell, entropies lie in
+    [0,1], reruns are bit-identical, and sampled frames match an independent dense evaluation."""
+    import bench
+    F, U = 3600, 100_000
+    p = bench.synth_on_device(torch, F, U, 20260000 + 3000, torch.device("cuda"))
+    e = engine(vet, [200], fov=90.0)
+    a = e.spatial(p)
+    assert e.poll_flags() == 0
+    b = e.spatial(p)
+    assert torch.equal(a.entropy, b.entropy) and torch.equal(a.hist0, b.hist0) and torch.equal(a.assign0, b.assign0)
+    del b
+    ent = a.entropy.cpu().numpy()
+    assert np.isfinite(ent).all() and ((ent > 0) & (ent <= 1)).all()
+    lut = torch.from_numpy(e.cell_lut(0).astype(np.int16)).cuda().ravel()
+    for f0 in range(0, F, 600):     # in slabs to bound the temporaries
+        sl = p[f0:f0 + 600]
+        cell = (sl[..., 2].double() * 200).to(torch.int64) * 101 + (sl[..., 1].double() * 100).to(torch.int64)
+        assert torch.equal(a.assign0[f0:f0 + 600].to(torch.int16), lut[cell])
+        del cell
+    for f in (0, 1799, 3599):       # weighted histogram of whole frames vs the dense per-user weight kernel
+        vec, _ = e.decode(p[f:f + 1])
+        dense = torch.zeros(201, dtype=torch.float64, device="cuda")
+        for u0 in range(0, U, 25_000):
+            dense += e.tile_weights(vec[0, u0:u0 + 25_000], 0).sum(0)
+        np.testing.assert_allclose(a.hist0[f].cpu().numpy(), dense.cpu().numpy(), rtol=RTOL, atol=ATOL)
+    e.close()
