@@ -23,6 +23,7 @@
 #include "vet_transition2.cuh"
 #include "vet_vectors.cuh"
 #include "vet_whist.cuh"
+#include "vet_whist_i8.cuh"
 
 namespace {
 
@@ -72,6 +73,12 @@ struct TileSet {
   int sched_blocks = 0, sched_max_items = 0;
   double* d_hist = nullptr;            // [frames,T] scratch rows (grown on demand)
   size_t hist_bytes = 0;
+  // int8 tensor-core path (vet_whist_i8.cuh), built on first use
+  bool i8_built = false;
+  int i8_blocks = 0;                   // N blocks of 48 tiles
+  uint8_t* d_w8 = nullptr;             // [i8_blocks*240, kp] weight slices, row nb*240 + s*48 + j
+  int2* d_kb_range = nullptr;          // [i8_blocks] K-block range of every N block
+  CUtensorMap tm_w;
 };
 
 }  // namespace
@@ -111,6 +118,14 @@ struct vet_handle {
   size_t tables_words = 0;
   uint32_t* d_pairs = nullptr;  // [CTAs, U] packed (prev, cur) tiles of the frame pair in flight (k_transition2)
   size_t pairs_bytes = 0;
+  // int8 tensor-core weighted histogram: count planes [2][rows_pad][kp], flags [rows_pad/128 + 1]
+  uint8_t* d_planes = nullptr;
+  size_t planes_bytes = 0;
+  uint32_t* d_i8flags = nullptr;
+  size_t i8flags_bytes = 0;
+  CUtensorMap tm_cnt;
+  const void* tm_cnt_base = nullptr;
+  int64_t tm_cnt_rows = 0;
   uint32_t tables_cap = 0;  // slot count the tables are currently laid out (and cleared) for
   int tables_blocks = 0;    // number of per-CTA tables cleared for that layout
   // host-buffer path
@@ -472,6 +487,8 @@ void free_tile_set(TileSet& t) {
   cudaFree(t.d_units);
   cudaFree(t.d_sched);
   cudaFree(t.d_hist);
+  cudaFree(t.d_w8);
+  cudaFree(t.d_kb_range);
 }
 
 size_t stream_smem_bytes(const vet_handle* h) { return (size_t)h->Cpad * 4 + (size_t)h->C * 2 + 16; }
@@ -709,7 +726,8 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
 }
 
 // k_whist for tile count k over F frames of the cell histogram `cnt` -> hist[F,T_k]
-int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st) {
+int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st,
+                 const uint32_t* run_if = nullptr) {
   TileSet& t = h->ts[k];
   const int shape = whist_shape();
   const int frames_per_cta = shape == 1 ? vet::WhistTall::kFramesPerCta : vet::WhistWide::kFramesPerCta;
@@ -736,6 +754,7 @@ int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* h
   a.hist = hist;
   a.cta_items = t.d_sched;
   a.max_items = t.sched_max_items;
+  a.run_if = run_if;
   {
     LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
     if (shape == 1)
@@ -747,6 +766,159 @@ int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* h
   }
   VET_CUDA(cudaGetLastError());
   return VET_OK;
+}
+
+
+// ---- int8 tensor-core weighted histogram (vet_whist_i8.cuh) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static const EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// tensor map of a row-major uint8 matrix [rows, kp] read in boxes of {128 bytes, box_rows} with the 128-byte swizzle
+int make_u8_map(CUtensorMap* m, const void* base, uint64_t kp, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(VET_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  const cuuint64_t dims[2] = {kp, rows};
+  const cuuint64_t strides[1] = {kp};
+  const cuuint32_t box[2] = {(cuuint32_t)vet::kI8BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VET_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return VET_OK;
+}
+
+int64_t i8_kp(const vet_handle* h) { return (h->C + vet::kI8BK - 1) / vet::kI8BK * vet::kI8BK; }
+
+// 0 = heuristic, 1 = always the FP64 kernel, 2 = the tensor-core kernel whenever it applies
+int whist_impl() {
+  const char* e = getenv("VET_WHIST_IMPL");
+  if (e && std::string(e) == "fp64") return 1;
+  if (e && std::string(e) == "i8") return 2;
+  return 0;
+}
+
+bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U) {
+  const int impl = whist_impl();
+  if (impl == 1 || !encode_tiled_fn()) return false;
+  if (U * 255 >= ((int64_t)1 << 31)) return false;  // int32 accumulators: D <= 255 * sum(count plane) <= 255 U
+  if ((size_t)vet::kI8SmemBytes + kStaticSmemSlack > h->smem_optin) return false;
+  if (impl == 2) return true;
+  // one CTA per (128 frames, 48 tiles): worth it once the grid fills a good part of the SMs
+  int64_t ctas = 0;
+  for (int k = 0; k < h->K; ++k) ctas += ((F + vet::kI8M - 1) / vet::kI8M) * ((h->ts[k].T + vet::kI8TilesPerBlock - 1) / vet::kI8TilesPerBlock);
+  return ctas >= h->sm_count / 2;
+}
+
+// Quantised weight slices of tile set t: row nb*240 + s*48 + j of [i8_blocks*240, kp] holds slice s of
+// rint(w(cell, nb*48+j) * 2^39) for every cell; plus the K-block range of every N block.
+int build_i8_tables(vet_handle* h, TileSet& t) {
+  if (t.i8_built) return VET_OK;
+  const int T = t.T;
+  const int64_t kp = i8_kp(h);
+  std::vector<uint32_t> col_ptr(T + 1), cell_idx(std::max<uint64_t>(t.nnz, 1));
+  std::vector<double> w_val(std::max<uint64_t>(t.nnz, 1));
+  VET_CUDA(cudaMemcpy(col_ptr.data(), t.d_col_ptr, (size_t)(T + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (t.nnz) {
+    VET_CUDA(cudaMemcpy(cell_idx.data(), t.d_cell_idx, t.nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    VET_CUDA(cudaMemcpy(w_val.data(), t.d_w_val, t.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  const int nblk = (T + vet::kI8TilesPerBlock - 1) / vet::kI8TilesPerBlock;
+  std::vector<uint8_t> w8((size_t)nblk * vet::kI8N * kp, 0);
+  std::vector<int2> range(nblk);
+  for (int nb = 0; nb < nblk; ++nb) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (int j = 0; j < vet::kI8TilesPerBlock; ++j) {
+      const int tile = nb * vet::kI8TilesPerBlock + j;
+      if (tile >= T) break;
+      for (uint32_t e = col_ptr[tile]; e < col_ptr[tile + 1]; ++e) {
+        const uint32_t c = cell_idx[e];
+        const uint64_t q = (uint64_t)std::llrint(std::ldexp(w_val[e], vet::kI8FracBits));
+        if (!q) continue;
+        lo = std::min(lo, c);
+        hi = std::max(hi, c);
+        for (int s = 0; s < vet::kI8Slices; ++s)
+          w8[((size_t)nb * vet::kI8N + (size_t)s * vet::kI8TilesPerBlock + j) * kp + c] = (uint8_t)(q >> (8 * s));
+      }
+    }
+    if (lo > hi) lo = hi = 0;  // no weight at all: one K block of zeros
+    range[nb] = make_int2((int)(lo / vet::kI8BK), (int)(hi / vet::kI8BK) + 1);
+  }
+  if (int rc = upload(&t.d_w8, w8.data(), w8.size())) return rc;
+  if (int rc = upload(&t.d_kb_range, range.data(), range.size())) return rc;
+  if (int rc = make_u8_map(&t.tm_w, t.d_w8, (uint64_t)kp, (uint64_t)nblk * vet::kI8N, vet::kI8N)) return rc;
+  t.i8_blocks = nblk;
+  t.i8_built = true;
+  return VET_OK;
+}
+
+// cell histogram rows -> byte planes + flags, once per frame batch (shared by all tile counts)
+int launch_cnt_planes(vet_handle* h, int64_t F, const uint32_t* cnt, cudaStream_t st) {
+  const int64_t kp = i8_kp(h);
+  const int64_t rows_pad = (F + vet::kI8M - 1) / vet::kI8M * vet::kI8M;
+  if (int rc = grow((void**)&h->d_planes, &h->planes_bytes, (size_t)2 * rows_pad * kp)) return rc;
+  const size_t flag_bytes = (size_t)(rows_pad / vet::kI8M + 1) * 4;
+  if (int rc = grow((void**)&h->d_i8flags, &h->i8flags_bytes, flag_bytes)) return rc;
+  if (h->tm_cnt_base != h->d_planes || h->tm_cnt_rows != rows_pad) {
+    if (int rc = make_u8_map(&h->tm_cnt, h->d_planes, (uint64_t)kp, (uint64_t)2 * rows_pad, vet::kI8M)) return rc;
+    h->tm_cnt_base = h->d_planes;
+    h->tm_cnt_rows = rows_pad;
+  }
+  VET_CUDA(cudaMemsetAsync(h->d_i8flags, 0, flag_bytes, st));
+  vet::CntPlanesArgs a{};
+  a.cnt = cnt;
+  a.F = F;
+  a.cpad = h->Cpad;
+  a.kp = (int)kp;
+  a.rows_pad = rows_pad;
+  a.planes = h->d_planes;
+  a.hi_flags = h->d_i8flags + 1;
+  a.too_big = h->d_i8flags;
+  LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
+  vet::k_cnt_planes<<<h->sm_count * 8, 256, 0, st>>>(a);
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+// k_whist_i8 for tile count k over the planes of the current batch -> hist[F,T_k]; the FP64 kernel is
+// queued behind it and runs only when the device-side flag says the counts did not fit two byte planes.
+int launch_whist_i8(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st) {
+  TileSet& t = h->ts[k];
+  if (int rc = build_i8_tables(h, t)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VET_CUDA(cudaFuncSetAttribute(vet::k_whist_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, vet::kI8SmemBytes));
+    attr_set = true;
+  }
+  const int64_t rows_pad = h->tm_cnt_rows;
+  vet::WhistI8Args a{};
+  a.F = F;
+  a.T = t.T;
+  a.n_blocks = t.i8_blocks;
+  a.rows_pad = (int)rows_pad;
+  a.kb_range = t.d_kb_range;
+  a.hi_flags = h->d_i8flags + 1;
+  a.too_big = h->d_i8flags;
+  a.hist = hist;
+  {
+    LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
+    const int grid = (int)(rows_pad / vet::kI8M) * t.i8_blocks;
+    vet::k_whist_i8<<<grid, vet::kI8Threads, vet::kI8SmemBytes, st>>>(h->tm_cnt, t.tm_w, a);
+  }
+  VET_CUDA(cudaGetLastError());
+  return launch_whist(h, k, F, cnt, hist, st, h->d_i8flags);
 }
 
 // weighted histograms' scratch rows of tile count k (k == 0 may write straight into the caller's hist0)
@@ -783,19 +955,22 @@ int launch_weighted_rows(vet_handle* h, int64_t F, double* const* hists, const u
   return VET_OK;
 }
 
-int launch_weighted_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, int64_t per_k_stride,
+int launch_weighted_epilogue(vet_handle* h, int64_t F, int64_t U, double* entropy, double* per_k, int64_t per_k_stride,
                              double* hist0, cudaStream_t st) {
   double* hists[vet::kMaxTileCounts];
+  const bool i8 = use_whist_i8(h, F, U);
+  if (i8)
+    if (int rc = launch_cnt_planes(h, F, h->d_cnt, st)) return rc;
   for (int k = 0; k < h->K; ++k) {
     if (int rc = whist_rows(h, k, F, hist0, &hists[k])) return rc;
-    if (int rc = launch_whist(h, k, F, h->d_cnt, hists[k], st)) return rc;
+    if (int rc = i8 ? launch_whist_i8(h, k, F, h->d_cnt, hists[k], st) : launch_whist(h, k, F, h->d_cnt, hists[k], st)) return rc;
   }
   return launch_weighted_rows(h, F, hists, h->d_nvalid, entropy, per_k, per_k_stride, st);
 }
 
-int launch_epilogue(vet_handle* h, int64_t F, double* entropy, double* per_k, int64_t per_k_stride, double* hist0,
+int launch_epilogue(vet_handle* h, int64_t F, int64_t U, double* entropy, double* per_k, int64_t per_k_stride, double* hist0,
                     cudaStream_t st) {
-  if (h->use_weight) return launch_weighted_epilogue(h, F, entropy, per_k, per_k_stride, hist0, st);
+  if (h->use_weight) return launch_weighted_epilogue(h, F, U, entropy, per_k, per_k_stride, hist0, st);
   vet::EpilogueArgs a{};
   a.cnt = h->d_cnt;
   a.F = F;
@@ -1021,6 +1196,8 @@ extern "C" int vet_destroy(vet_handle* h) {
   for (void* p : h->d_vscratch) cudaFree(p);
   cudaFree(h->d_tables);
   cudaFree(h->d_pairs);
+  cudaFree(h->d_planes);
+  cudaFree(h->d_i8flags);
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);
   for (void* p : h->d_hout) cudaFree(p);
@@ -1127,7 +1304,7 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
       continue;
     }
     if (int rc = launch_stream(h, in, dtype, nf, U, assign0_dev ? assign0_dev + f0 * U : nullptr, false, st)) return rc;
-    if (int rc = launch_epilogue(h, nf, entropy_dev + f0, per_k_dev ? per_k_dev + f0 : nullptr, F,
+    if (int rc = launch_epilogue(h, nf, U, entropy_dev + f0, per_k_dev ? per_k_dev + f0 : nullptr, F,
                                  hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
       return rc;
   }
@@ -1213,7 +1390,7 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
     const char* in = (const char*)packed_dev + (size_t)f0 * U * 3 * esz;
     uint16_t* asg = assign ? assign + f0 * U : (uint16_t*)h->d_vscratch[0];
     if (int rc = launch_stream(h, in, dtype, nf, U, asg, true, st)) return rc;
-    if (int rc = launch_epilogue(h, nf, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
+    if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
                                  hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
       return rc;
     if (nf >= 2) {
@@ -1675,7 +1852,7 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
       }
       rc = launch_stream(h, in, dtype, ng, U, d_assign[b] ? d_assign[b] + g0 * U : nullptr, false, h->s_exec);
       if (rc == VET_OK)
-        rc = launch_epilogue(h, ng, d_ent + f0 + g0, d_perk ? d_perk + f0 + g0 : nullptr, F,
+        rc = launch_epilogue(h, ng, U, d_ent + f0 + g0, d_perk ? d_perk + f0 + g0 : nullptr, F,
                              d_hist ? d_hist + (f0 + g0) * T0 : nullptr, h->s_exec);
     }
     cudaEventRecord(exec_done[b], h->s_exec);
