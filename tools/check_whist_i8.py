@@ -69,6 +69,20 @@ def case(name, F, U, tcs, fov=90.0, pf=2.0, hot=0, timing=False):
     del p
 
 
+def dirty_case():
+    """planes 1/2 written by a 'hot' call must be cleaned by the next call on the same rows"""
+    eng = get_engine(100, 200, [200], EntropyConfig(90.0, True, 2.0), dev)
+    hot = bench.synth_on_device(torch, 260, 70000, 11, dev)
+    hot[:, :66000, 1] = 0.25
+    hot[:, :66000, 2] = 0.75
+    cold = bench.synth_on_device(torch, 200, 70000, 12, dev)
+    run(eng, hot, "i8")
+    b = run(eng, cold, "i8")
+    a = run(eng, cold, "fp64")
+    print(json.dumps(dict(case="dirty_rows", hist_max_abs=float((a.hist0 - b.hist0).abs().max()),
+                          entropy_max_rel=float(((a.entropy - b.entropy).abs() / a.entropy.abs()).max()))), flush=True)
+
+
 which = sys.argv[1:] or ["small", "mid"]
 if "small" in which:
     case("small", 300, 5000, [200])
@@ -77,5 +91,7 @@ if "mid" in which:
     case("mid_plane1", 260, 20000, [200], hot=3000)
     case("mid_fallback", 130, 70000, [200], hot=66000)
     case("mid_T1001", 200, 4000, [1000], fov=60.0)
+    case("mid_chunks", 130, 300000, [200], hot=70000)
+    dirty_case()
 if "big" in which:
     case("c3", 3600, 100000, [200], timing=True)

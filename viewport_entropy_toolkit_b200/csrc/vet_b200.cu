@@ -118,14 +118,14 @@ struct vet_handle {
   size_t tables_words = 0;
   uint32_t* d_pairs = nullptr;  // [CTAs, U] packed (prev, cur) tiles of the frame pair in flight (k_transition2)
   size_t pairs_bytes = 0;
-  // int8 tensor-core weighted histogram: count planes [2][rows_pad][kp], flags [rows_pad/128 + 1]
+  // int8 tensor-core weighted histogram: count byte planes [3][plane_rows][kp] (rows of planes 1, 2 are zero
+  // unless marked in d_dirty), per-frame-block flags hi1/hi2 [2][plane_rows/128]
   uint8_t* d_planes = nullptr;
-  size_t planes_bytes = 0;
-  uint32_t* d_i8flags = nullptr;
-  size_t i8flags_bytes = 0;
+  int64_t plane_rows = 0;        // row capacity of the allocation (multiple of 128)
+  uint8_t* d_dirty = nullptr;    // [plane_rows]
+  uint32_t* d_i8flags = nullptr; // [2][plane_rows/128]
   CUtensorMap tm_cnt;
-  const void* tm_cnt_base = nullptr;
-  int64_t tm_cnt_rows = 0;
+  bool planes_from_stream = false;  // the last launch_stream wrote the planes of its batch itself
   uint32_t tables_cap = 0;  // slot count the tables are currently laid out (and cleared) for
   int tables_blocks = 0;    // number of per-CTA tables cleared for that layout
   // host-buffer path
@@ -262,6 +262,13 @@ int transition_direct(vet_handle* h, const void* packed, int dtype, int64_t F, i
 
 constexpr size_t kStaticSmemSlack = 1024;
 constexpr int kMaxT = 16384;
+
+// tensor-core weighted histogram (defined with launch_whist_i8 below)
+bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U);
+int ensure_planes(vet_handle* h, int64_t F, cudaStream_t st);
+int64_t i8_kp(const vet_handle* h);
+uint32_t* i8_hi1(vet_handle* h);
+uint32_t* i8_hi2(vet_handle* h);
 
 // Blocking of k_whist: "wide" = 8 tiles x 8 frames per warp, "tall" = 4 tiles x 16 frames.
 // 0 = wide (default), 1 = tall, 2 = quad
@@ -548,6 +555,7 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
   }
   const int64_t items = F * a.chunks_per_frame;
   const int blocks = (int)std::min<int64_t>(items, h->sm_count);
+  h->planes_from_stream = false;
   if (use_tma_stream(h, packed)) {
     const bool lut8 = h->ts[0].d_lut8 != nullptr;
     vet::StreamTmaArgs A{};
@@ -555,6 +563,18 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
     A.lut0_typed = lut8 ? (const void*)h->ts[0].d_lut8 : (const void*)h->ts[0].d_lut;
     A.total_bytes = F * U * 3 * (int64_t)(dtype == VET_F32 ? 4 : 8);
     A.cpad = h->Cpad;
+    if (h->use_weight && a.chunks_per_frame == 1 && use_whist_i8(h, F, U)) {
+      // frames of one chunk: the kernel writes the byte planes of the tensor-core epilogue instead of `cnt`
+      if (int rc = ensure_planes(h, F, st)) return rc;
+      VET_CUDA(cudaMemsetAsync(h->d_i8flags, 0, (size_t)2 * (h->plane_rows / vet::kI8M) * 4, st));
+      A.planes = h->d_planes;
+      A.kp = (int)i8_kp(h);
+      A.plane_stride = h->plane_rows * (int64_t)A.kp;
+      A.dirty = h->d_dirty;
+      A.hi1 = i8_hi1(h);
+      A.hi2 = i8_hi2(h);
+      h->planes_from_stream = true;
+    }
     const size_t smem = stream_tma_smem_bytes(h, lut8);
     LaunchTimer lt(h, VET_KERNEL_STREAM, st);
     const dim3 grid(blocks), block(vet::kStreamThreads);
@@ -726,8 +746,7 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
 }
 
 // k_whist for tile count k over F frames of the cell histogram `cnt` -> hist[F,T_k]
-int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st,
-                 const uint32_t* run_if = nullptr) {
+int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st) {
   TileSet& t = h->ts[k];
   const int shape = whist_shape();
   const int frames_per_cta = shape == 1 ? vet::WhistTall::kFramesPerCta : vet::WhistWide::kFramesPerCta;
@@ -754,7 +773,6 @@ int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* h
   a.hist = hist;
   a.cta_items = t.d_sched;
   a.max_items = t.sched_max_items;
-  a.run_if = run_if;
   {
     LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
     if (shape == 1)
@@ -864,37 +882,57 @@ int build_i8_tables(vet_handle* h, TileSet& t) {
   return VET_OK;
 }
 
-// cell histogram rows -> byte planes + flags, once per frame batch (shared by all tile counts)
+// Scratch of the tensor-core path for batches of up to F frames: byte planes, dirty marks, flags and the
+// tensor map over the planes.  Planes 1 and 2 start out zero (the invariant the dirty marks protect).
+int ensure_planes(vet_handle* h, int64_t F, cudaStream_t st) {
+  const int64_t kp = i8_kp(h);
+  const int64_t rows = (F + vet::kI8M - 1) / vet::kI8M * vet::kI8M;
+  if (rows <= h->plane_rows) return VET_OK;
+  VET_CUDA(cudaStreamSynchronize(st));
+  cudaFree(h->d_planes);
+  cudaFree(h->d_dirty);
+  cudaFree(h->d_i8flags);
+  h->d_planes = nullptr;
+  h->d_dirty = nullptr;
+  h->d_i8flags = nullptr;
+  h->plane_rows = 0;
+  VET_CUDA(cudaMalloc((void**)&h->d_planes, (size_t)3 * rows * kp));
+  VET_CUDA(cudaMalloc((void**)&h->d_dirty, (size_t)rows));
+  VET_CUDA(cudaMalloc((void**)&h->d_i8flags, (size_t)2 * (rows / vet::kI8M) * 4));
+  VET_CUDA(cudaMemsetAsync(h->d_planes, 0, (size_t)3 * rows * kp, st));
+  VET_CUDA(cudaMemsetAsync(h->d_dirty, 0, (size_t)rows, st));
+  if (int rc = make_u8_map(&h->tm_cnt, h->d_planes, (uint64_t)kp, (uint64_t)3 * rows, vet::kI8M)) return rc;
+  h->plane_rows = rows;
+  return VET_OK;
+}
+uint32_t* i8_hi1(vet_handle* h) { return h->d_i8flags; }
+uint32_t* i8_hi2(vet_handle* h) { return h->d_i8flags + h->plane_rows / vet::kI8M; }
+
+// cell histogram rows -> byte planes, for batches whose frames the streaming kernel split into chunks
 int launch_cnt_planes(vet_handle* h, int64_t F, const uint32_t* cnt, cudaStream_t st) {
   const int64_t kp = i8_kp(h);
-  const int64_t rows_pad = (F + vet::kI8M - 1) / vet::kI8M * vet::kI8M;
-  if (int rc = grow((void**)&h->d_planes, &h->planes_bytes, (size_t)2 * rows_pad * kp)) return rc;
-  const size_t flag_bytes = (size_t)(rows_pad / vet::kI8M + 1) * 4;
-  if (int rc = grow((void**)&h->d_i8flags, &h->i8flags_bytes, flag_bytes)) return rc;
-  if (h->tm_cnt_base != h->d_planes || h->tm_cnt_rows != rows_pad) {
-    if (int rc = make_u8_map(&h->tm_cnt, h->d_planes, (uint64_t)kp, (uint64_t)2 * rows_pad, vet::kI8M)) return rc;
-    h->tm_cnt_base = h->d_planes;
-    h->tm_cnt_rows = rows_pad;
-  }
-  VET_CUDA(cudaMemsetAsync(h->d_i8flags, 0, flag_bytes, st));
+  if (int rc = ensure_planes(h, F, st)) return rc;
+  VET_CUDA(cudaMemsetAsync(h->d_i8flags, 0, (size_t)2 * (h->plane_rows / vet::kI8M) * 4, st));
   vet::CntPlanesArgs a{};
   a.cnt = cnt;
   a.F = F;
   a.cpad = h->Cpad;
   a.kp = (int)kp;
-  a.rows_pad = rows_pad;
+  a.plane_stride = h->plane_rows * kp;
   a.planes = h->d_planes;
-  a.hi_flags = h->d_i8flags + 1;
-  a.too_big = h->d_i8flags;
+  a.dirty = h->d_dirty;
+  a.hi1 = i8_hi1(h);
+  a.hi2 = i8_hi2(h);
   LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
   vet::k_cnt_planes<<<h->sm_count * 8, 256, 0, st>>>(a);
   VET_CUDA(cudaGetLastError());
   return VET_OK;
 }
 
-// k_whist_i8 for tile count k over the planes of the current batch -> hist[F,T_k]; the FP64 kernel is
-// queued behind it and runs only when the device-side flag says the counts did not fit two byte planes.
-int launch_whist_i8(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st) {
+// k_whist_i8 for tile count k over the planes of the current batch -> hist[F,T_k].  Pass 1: count bits
+// [0,16) (plane 1 only for frame blocks flagged hi1); pass 2, CTAs of frame blocks flagged hi2 only:
+// bits [16,24), added to the result.
+int launch_whist_i8(vet_handle* h, int k, int64_t F, double* hist, cudaStream_t st) {
   TileSet& t = h->ts[k];
   if (int rc = build_i8_tables(h, t)) return rc;
   static bool attr_set = false;
@@ -902,23 +940,26 @@ int launch_whist_i8(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double
     VET_CUDA(cudaFuncSetAttribute(vet::k_whist_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, vet::kI8SmemBytes));
     attr_set = true;
   }
-  const int64_t rows_pad = h->tm_cnt_rows;
+  const int fblocks = (int)((F + vet::kI8M - 1) / vet::kI8M);
   vet::WhistI8Args a{};
   a.F = F;
   a.T = t.T;
   a.n_blocks = t.i8_blocks;
-  a.rows_pad = (int)rows_pad;
   a.kb_range = t.d_kb_range;
-  a.hi_flags = h->d_i8flags + 1;
-  a.too_big = h->d_i8flags;
   a.hist = hist;
-  {
+  const int grid = fblocks * t.i8_blocks;
+  for (int pass = 0; pass < 2; ++pass) {
+    a.row_a = pass == 0 ? 0 : (int)(2 * h->plane_rows);
+    a.row_b = (int)h->plane_rows;
+    a.flag_b = pass == 0 ? i8_hi1(h) : nullptr;
+    a.run_if = pass == 0 ? nullptr : i8_hi2(h);
+    a.shift = pass == 0 ? 0 : 16;
+    a.accumulate = pass;
     LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-    const int grid = (int)(rows_pad / vet::kI8M) * t.i8_blocks;
     vet::k_whist_i8<<<grid, vet::kI8Threads, vet::kI8SmemBytes, st>>>(h->tm_cnt, t.tm_w, a);
   }
   VET_CUDA(cudaGetLastError());
-  return launch_whist(h, k, F, cnt, hist, st, h->d_i8flags);
+  return VET_OK;
 }
 
 // weighted histograms' scratch rows of tile count k (k == 0 may write straight into the caller's hist0)
@@ -959,11 +1000,11 @@ int launch_weighted_epilogue(vet_handle* h, int64_t F, int64_t U, double* entrop
                              double* hist0, cudaStream_t st) {
   double* hists[vet::kMaxTileCounts];
   const bool i8 = use_whist_i8(h, F, U);
-  if (i8)
+  if (i8 && !h->planes_from_stream)
     if (int rc = launch_cnt_planes(h, F, h->d_cnt, st)) return rc;
   for (int k = 0; k < h->K; ++k) {
     if (int rc = whist_rows(h, k, F, hist0, &hists[k])) return rc;
-    if (int rc = i8 ? launch_whist_i8(h, k, F, h->d_cnt, hists[k], st) : launch_whist(h, k, F, h->d_cnt, hists[k], st)) return rc;
+    if (int rc = i8 ? launch_whist_i8(h, k, F, hists[k], st) : launch_whist(h, k, F, h->d_cnt, hists[k], st)) return rc;
   }
   return launch_weighted_rows(h, F, hists, h->d_nvalid, entropy, per_k, per_k_stride, st);
 }
@@ -1197,6 +1238,7 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_tables);
   cudaFree(h->d_pairs);
   cudaFree(h->d_planes);
+  cudaFree(h->d_dirty);
   cudaFree(h->d_i8flags);
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);

@@ -75,7 +75,24 @@ struct StreamTmaArgs {
   const void* lut0_typed;   // uint8_t[C] or uint16_t[C]
   int64_t total_bytes;      // bytes of the packed tensor of this call (for the alignment clip)
   int cpad;                 // C rounded up to a multiple of 4 (row pitch of cnt, in cells)
+  // Optional (frames of one chunk only): write the frame's cell histogram as BYTE PLANES for the
+  // tensor-core weighted histogram (vet_whist_i8.cuh) instead of the uint32 row of `cnt`.
+  //   plane p, row f = bits [8p, 8p+8) of every count, kp bytes per row (zero padded)
+  // Planes 1 and 2 are almost always zero: their rows are only touched when the frame has such
+  // counts or when the row is marked dirty (non-zero from an earlier call), so the usual cost is
+  // kp bytes per frame instead of 4 cpad.
+  uint8_t* planes;          // [3][plane_rows][kp] or null
+  int64_t plane_stride;     // bytes between planes
+  int kp;                   // bytes per plane row (multiple of 128)
+  uint8_t* dirty;           // [plane_rows] bit p-1: row f of plane p may be non-zero
+  uint32_t* hi1;            // [plane_rows / 128] frame block has counts >= 256
+  uint32_t* hi2;            // [plane_rows / 128] frame block has counts >= 65536
 };
+
+__device__ __forceinline__ uint32_t pack_bytes(uint4 v, int shift) {
+  return ((v.x >> shift) & 0xFFu) | (((v.y >> shift) & 0xFFu) << 8) | (((v.z >> shift) & 0xFFu) << 16) |
+         (((v.w >> shift) & 0xFFu) << 24);
+}
 
 // Slow-path classification of a sample that failed the fast [0,1] bit test.
 template <typename T>
@@ -179,7 +196,7 @@ __global__ void __launch_bounds__(kStreamThreads, VET_STREAM_MINBLOCKS) k_stream
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + kStages * kStageBytes);
   TLUT* s_lut = reinterpret_cast<TLUT*>(s_hist + A.cpad);
   __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
-  __shared__ uint32_t s_nvalid;
+  __shared__ uint32_t s_nvalid, s_hibits;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -190,7 +207,10 @@ __global__ void __launch_bounds__(kStreamThreads, VET_STREAM_MINBLOCKS) k_stream
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int c = threadIdx.x; c < A.cpad; c += blockDim.x) s_hist[c] = 0u;
-  if (threadIdx.x == 0) s_nvalid = 0u;
+  if (threadIdx.x == 0) {
+    s_nvalid = 0u;
+    s_hibits = 0u;
+  }
   if (ASSIGN) copy_to_smem16(s_lut, A.lut0_typed, a.C * (int)sizeof(TLUT));
   __syncthreads();
 
@@ -264,6 +284,35 @@ __global__ void __launch_bounds__(kStreamThreads, VET_STREAM_MINBLOCKS) k_stream
     uint4* __restrict__ row = reinterpret_cast<uint4*>(a.cnt + f * (int64_t)A.cpad);
     uint4* s_hist4 = reinterpret_cast<uint4*>(s_hist);
     const int n4 = A.cpad >> 2;
+    if (A.planes && a.chunks_per_frame == 1) {
+      const uint32_t was = A.dirty[f];  // uniform over the CTA
+      uint32_t* __restrict__ r0 = reinterpret_cast<uint32_t*>(A.planes + f * (int64_t)A.kp);
+      uint32_t* __restrict__ r1 = reinterpret_cast<uint32_t*>(A.planes + A.plane_stride + f * (int64_t)A.kp);
+      uint32_t* __restrict__ r2 = reinterpret_cast<uint32_t*>(A.planes + 2 * A.plane_stride + f * (int64_t)A.kp);
+      uint32_t hi = 0;
+      for (int c = ctid; c < (A.kp >> 2); c += kConsumerWarps * 32) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c < n4) {
+          v = s_hist4[c];
+          s_hist4[c] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        r0[c] = pack_bytes(v, 0);
+        const uint32_t w1 = pack_bytes(v, 8), w2 = pack_bytes(v, 16);
+        if ((was & 1u) || w1) r1[c] = w1;
+        if ((was & 2u) || w2) r2[c] = w2;
+        hi |= (w1 ? 1u : 0u) | (w2 ? 2u : 0u);
+      }
+      if (hi) atomicOr(&s_hibits, hi);
+      consumer_sync();
+      if (ctid == 0) {
+        const uint32_t now = s_hibits;
+        s_hibits = 0u;
+        if (now != was) A.dirty[f] = (uint8_t)now;
+        if (now & 1u) atomicOr(&A.hi1[f >> 7], 1u);
+        if (now & 2u) atomicOr(&A.hi2[f >> 7], 1u);
+      }
+      continue;
+    }
     if (a.chunks_per_frame == 1) {
       for (int c = ctid; c < n4; c += kConsumerWarps * 32) {
         row[c] = s_hist4[c];

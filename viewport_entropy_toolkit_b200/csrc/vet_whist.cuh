@@ -70,8 +70,6 @@ struct WhistArgs {
   double* hist;                  // [F,T]
   const uint32_t* cta_items;     // [gridDim.x, max_items] (frame block * G + group) per CTA, 0xFFFFFFFF = none:
   int max_items;                 // host-side longest-processing-time schedule (items differ in size)
-  const uint32_t* run_if;        // optional device flag: the kernel does nothing while it is zero (fallback
-                                 // behind the tensor-core kernel of vet_whist_i8.cuh)
 };
 
 // exact u32 -> f64.  VET_CVT_MAGIC: 2^52 + v has v in its low mantissa bits, one DADD on
@@ -146,7 +144,6 @@ __device__ __forceinline__ void whist_step(const double* sW, int s, int lane, co
 template <typename S>
 __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
   constexpr int TG = S::TG, FW = S::FW, Q = S::Q, kD = S::kDepth;
-  if (a.run_if && *a.run_if == 0u) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kWhStages], s_empty[kWhStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

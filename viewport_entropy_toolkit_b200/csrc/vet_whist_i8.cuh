@@ -7,14 +7,14 @@
 //
 //   * a weight is quantised once, at table-build time, to 39 fractional bits,
 //     q = rint(w * 2^39) in [0, 2^39] (w = 1.0 occurs: a cell that coincides with a tile
-//     centre), and cut into five 8-bit slices q = sum_s q_s 2^(8s); a count is cut into two
-//     8-bit planes c = c_0 + 256 c_1 (frames with a count >= 65536 in one cell take the FP64
-//     kernel of vet_whist.cuh instead, decided on the device);
+//     centre), and cut into five 8-bit slices q = sum_s q_s 2^(8s); a count is cut into three
+//     8-bit planes c = c_0 + 2^8 c_1 + 2^16 c_2 (planes 1 and 2 are zero for almost every frame
+//     and are skipped per frame block through device-side flags; plane 2 -- 65536 users in one
+//     cell -- takes a second launch that adds to the result);
 //   * D_p,s[f, t] = sum_cell c_p[f, cell] * q_s[cell, t] is an unsigned 8-bit GEMM with int32
-//     accumulation -- exact: every partial sum is below 255 * 255 * U < 2^31 for U < 33k users
-//     per plane-sum, and in general sum_cell c_p <= U so D <= 255 * U (checked on the host);
-//   * HIST = 2^-39 * sum_s 2^(8s) (D_0,s + 256 D_1,s), evaluated in fp64 from the exact
-//     integers in a fixed order.  The only deviation from the FP64 kernel is the weight
+//     accumulation -- exact: sum_cell c_p <= U, so D <= 255 U < 2^31 (U < 8.4 M, checked on the host);
+//   * HIST = 2^-39 * sum_s 2^(8s) (D_0,s + 2^8 D_1,s + 2^16 D_2,s), evaluated in fp64 from the
+//     exact integers in a fixed order.  The only deviation from the FP64 kernel is the weight
 //     quantisation: |dw| <= 2^-40 = 9.1e-13 per (cell, tile), i.e. <= 1e-11 relative on a
 //     histogram entry whose mean weight is >= 0.1 (tolerance of the path: 1e-9, tests/).
 //
@@ -110,25 +110,28 @@ struct WhistI8Args {
   int64_t F;
   int T;
   int n_blocks;               // N blocks of 48 tiles
-  int rows_pad;               // rows per count plane (multiple of 128); plane 1 starts at row rows_pad
+  int row_a;                  // first row, in the plane tensor, of the plane accumulated in TMEM columns [0,240)
+  int row_b;                  // same for the plane accumulated in columns [256,496), used where flag_b is set
+  const uint32_t* flag_b;     // [frame blocks] or null: the frame block needs the second plane
+  const uint32_t* run_if;     // [frame blocks] or null: CTAs of a frame block whose flag is zero do nothing
+  int shift;                  // the planes hold count bits [shift, shift+16)
+  int accumulate;             // add to hist instead of storing (second pass, planes of higher bits)
   const int2* kb_range;       // [n_blocks] first / past-the-end 128-cell K block with a non-zero weight
-  const uint32_t* hi_flags;   // [rows_pad / 128] != 0: the frame block has counts >= 256 (plane 1 is needed)
-  const uint32_t* too_big;    // != 0: some count >= 65536 -> this kernel does nothing, k_whist runs instead
   double* hist;               // [F, T]
 };
 
 __global__ void __launch_bounds__(kI8Threads, 1)
 k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ CUtensorMap tm_w, WhistI8Args a) {
-  if (*a.too_big) return;
+  const int nb = blockIdx.x % a.n_blocks;
+  const int mb = blockIdx.x / a.n_blocks;
+  if (a.run_if && a.run_if[mb] == 0u) return;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) unsigned long long s_full[kI8Stages], s_empty[kI8Stages], s_accum;
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const int nb = blockIdx.x % a.n_blocks;
-  const int mb = blockIdx.x / a.n_blocks;
   const int2 kr = a.kb_range[nb];
-  const bool two = a.hi_flags[mb] != 0;
+  const bool two = a.flag_b && a.flag_b[mb] != 0u;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kI8Stages; ++i) {
@@ -155,8 +158,8 @@ k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ C
         const uint32_t bar = smem_u32(&s_full[stage]);
         const uint32_t base = ring + stage * kI8StageBytes;
         mbar_expect_tx(bar, bytes);
-        tma_load_2d(base, &tm_cnt, bar, kb * kI8BK, mb * kI8M);
-        if (two) tma_load_2d(base + kI8ABytes, &tm_cnt, bar, kb * kI8BK, a.rows_pad + mb * kI8M);
+        tma_load_2d(base, &tm_cnt, bar, kb * kI8BK, a.row_a + mb * kI8M);
+        if (two) tma_load_2d(base + kI8ABytes, &tm_cnt, bar, kb * kI8BK, a.row_b + mb * kI8M);
         tma_load_2d(base + 2 * kI8ABytes, &tm_w, bar, kb * kI8BK, nb * kI8N);
       }
     }
@@ -199,7 +202,7 @@ k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ C
         tc_ld16(lane_base + s * kI8TilesPerBlock + j0, r0);
         if (two) tc_ld16(lane_base + 256 + s * kI8TilesPerBlock + j0, r1);
         tc_wait_ld();
-        const double scale = __longlong_as_double((long long)(1023 + 8 * s - kI8FracBits) << 52);  // 2^(8s-39)
+        const double scale = __longlong_as_double((long long)(1023 + 8 * s - kI8FracBits + a.shift) << 52);  // 2^(8s-39+shift)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           long long x = (long long)(int)r0[j];
@@ -212,7 +215,7 @@ k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int tile = nb * kI8TilesPerBlock + j0 + j;
-          if (tile < a.T) row[tile] = v[j];
+          if (tile < a.T) row[tile] = a.accumulate ? row[tile] + v[j] : v[j];
         }
       }
     }
@@ -222,17 +225,19 @@ k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ C
   if (warp == 1) tc_dealloc(tmem, kI8TmemCols);
 }
 
-// Cell histogram rows (uint32) -> two byte planes [2][rows_pad][kp] for the int8 GEMM, zero
-// padded to kp cells; flags frame blocks that need plane 1 and counts that do not fit 16 bits.
+// Cell histogram rows (uint32) -> the byte planes of the tensor-core kernel, for frames that the
+// streaming kernel accumulated in several chunks (it then adds into `cnt` with RED and cannot emit the
+// planes itself).  All three planes of every row are written; the rows are marked dirty.
 struct CntPlanesArgs {
   const uint32_t* cnt;  // [F, cpad]
   int64_t F;
   int cpad;
   int kp;               // cells per plane row, multiple of 128
-  int64_t rows_pad;
+  int64_t plane_stride; // bytes between planes
   uint8_t* planes;
-  uint32_t* hi_flags;   // [rows_pad / 128], zeroed by the caller
-  uint32_t* too_big;    // zeroed by the caller
+  uint8_t* dirty;       // [rows]
+  uint32_t* hi1;        // [frame blocks], zeroed by the caller
+  uint32_t* hi2;
 };
 
 __global__ void __launch_bounds__(256) k_cnt_planes(CntPlanesArgs a) {
@@ -242,7 +247,8 @@ __global__ void __launch_bounds__(256) k_cnt_planes(CntPlanesArgs a) {
   const int upr = a.kp >> 7;  // 128-cell units per row
   const int64_t units = a.F * upr;
   uint32_t* __restrict__ p0 = reinterpret_cast<uint32_t*>(a.planes);
-  uint32_t* __restrict__ p1 = reinterpret_cast<uint32_t*>(a.planes + a.rows_pad * (int64_t)a.kp);
+  uint32_t* __restrict__ p1 = reinterpret_cast<uint32_t*>(a.planes + a.plane_stride);
+  uint32_t* __restrict__ p2 = reinterpret_cast<uint32_t*>(a.planes + 2 * a.plane_stride);
   constexpr int kUnroll = 4;
   for (int64_t u0 = warp * kUnroll; u0 < units; u0 += nwarps * kUnroll) {
     uint4 v[kUnroll];
@@ -262,14 +268,13 @@ __global__ void __launch_bounds__(256) k_cnt_planes(CntPlanesArgs a) {
       if (u < units) {
         const int64_t f = u / upr;
         const int64_t o = (f * (int64_t)a.kp + (u % upr) * 128) / 4 + lane;
-        const uint32_t all = v[i].x | v[i].y | v[i].z | v[i].w;
-        p0[o] = (v[i].x & 0xFFu) | ((v[i].y & 0xFFu) << 8) | ((v[i].z & 0xFFu) << 16) | ((v[i].w & 0xFFu) << 24);
-        p1[o] = ((v[i].x >> 8) & 0xFFu) | (((v[i].y >> 8) & 0xFFu) << 8) | (((v[i].z >> 8) & 0xFFu) << 16) |
-                (((v[i].w >> 8) & 0xFFu) << 24);
-        if (all >> 8) {
-          atomicOr(&a.hi_flags[f >> 7], 1u);
-          if (all >> 16) atomicOr(a.too_big, 1u);
-        }
+        const uint32_t w1 = pack_bytes(v[i], 8), w2 = pack_bytes(v[i], 16);
+        p0[o] = pack_bytes(v[i], 0);
+        p1[o] = w1;
+        p2[o] = w2;
+        if (w1) atomicOr(&a.hi1[f >> 7], 1u);
+        if (w2) atomicOr(&a.hi2[f >> 7], 1u);
+        if (u % upr == 0 && lane == 0) a.dirty[f] = 3;
       }
     }
   }
