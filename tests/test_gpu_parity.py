@@ -608,3 +608,74 @@ def test_full_size_properties_configs2(vet):
             dense += e.tile_weights(vec[0, u0:u0 + 25_000], 0).sum(0)
         np.testing.assert_allclose(a.hist0[f].cpu().numpy(), dense.cpu().numpy(), rtol=RTOL, atol=ATOL)
     e.close()
+
+
+# ---------------------------------------------------------------------------------
+# tensor-core weighted histogram (k_whist_i8): exact integer GEMM over count byte planes and
+# 39-bit fixed-point weight slices.  Stated tolerance of this path: entropies 1e-9 relative
+# (north_star); weighted histogram entries |d| <= users * 2^-40 absolute (weight quantisation)
+# on top of the 1e-9 relative bar.  VET_WHIST_IMPL forces the kernel for frame counts below
+# the heuristic threshold; it is read at every call.
+# ---------------------------------------------------------------------------------
+I8_QUANT = 2.0 ** -40
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(F=6, U=3000, tcs=[200], fov=90.0),
+    dict(F=4, U=2000, tcs=[20, 50], fov=120.0, iid=True, missing=0.2),
+    dict(F=3, U=1500, tcs=[250, 1000], fov=120.0),                      # 6 and 21 N blocks, u16 LUT
+    dict(F=5, U=701, tcs=[50], fov=360.0, pf=3.0, iid=True),            # every tile sees every cell
+    dict(F=5, U=700, tcs=[50], fov=10.0, pf=0.5, iid=True),             # most users outside every FOV
+    dict(F=131, U=257, tcs=[200, 50], fov=90.0, iid=True, missing=0.05),  # two frame blocks, partial second one
+    dict(F=3, U=70000, tcs=[200], fov=90.0, iid=True),                  # frames in several chunks: k_cnt_planes
+])
+def test_weighted_tensor_core_path_vs_oracle(vet, cfg, monkeypatch):
+    monkeypatch.setenv("VET_WHIST_IMPL", "i8")
+    p = synth(cfg["F"], cfg["U"], 4100 + cfg["U"], cfg.get("iid", False), cfg.get("missing", 0.0))
+    pf = cfg.get("pf", 2.0)
+    e = engine(vet, cfg["tcs"], cfg["fov"], True, pf)
+    sp = e.spatial(dev(p))
+    assert e.poll_flags() == 0
+    ref = orc.spatial_analyzer(p, W0, H0, cfg["tcs"], cfg["fov"], True, pf)
+    assert np.array_equal(sp.assign0.cpu().numpy(), ref["assign0"])
+    np.testing.assert_allclose(sp.hist0.cpu().numpy(), ref["hist0"], rtol=RTOL, atol=cfg["U"] * I8_QUANT)
+    np.testing.assert_allclose(sp.per_k.cpu().numpy(), ref["per_k"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    np.testing.assert_allclose(sp.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    monkeypatch.setenv("VET_WHIST_IMPL", "fp64")
+    sp64 = e.spatial(dev(p))
+    np.testing.assert_allclose(sp.hist0.cpu().numpy(), sp64.hist0.cpu().numpy(), rtol=RTOL, atol=cfg["U"] * I8_QUANT)
+    np.testing.assert_allclose(sp.entropy.cpu().numpy(), sp64.entropy.cpu().numpy(), rtol=RTOL, atol=ATOL, equal_nan=True)
+    e.close()
+
+
+def test_weighted_tensor_core_count_planes(vet, monkeypatch):
+    """Counts of 256 and more (second byte plane) and of 65536 and more (third plane, second GEMM
+    pass), rows of the higher planes left dirty by one call and cleaned by the next, analyze() ==
+    spatial(); all against the FP64 kernel on the same input."""
+    import bench
+    F, U = 260, 70_000
+    e = engine(vet, [200], fov=90.0)
+    hot = bench.synth_on_device(torch, F, U, 4242, torch.device("cuda"))
+    hot[:, :66_000, 1] = 0.25     # one cell holds 66k users of every frame
+    hot[:, :66_000, 2] = 0.75
+    hot[:, 66_000:67_000, 1] = 0.5  # another one 1000
+    hot[:, 66_000:67_000, 2] = 0.5
+    cold = bench.synth_on_device(torch, F - 60, U, 4243, torch.device("cuda"))
+    res = {}
+    for impl in ("fp64", "i8"):
+        monkeypatch.setenv("VET_WHIST_IMPL", impl)
+        a = e.spatial(hot)
+        b = e.spatial(cold)          # same plane rows as `hot`, now without large counts
+        c, _ = e.analyze(hot)
+        res[impl] = (a, b, c)
+    assert e.poll_flags() == 0
+    for x, y in zip(res["fp64"], res["i8"]):
+        assert torch.equal(x.assign0, y.assign0)
+        np.testing.assert_allclose(y.hist0.cpu().numpy(), x.hist0.cpu().numpy(), rtol=RTOL, atol=U * I8_QUANT)
+        np.testing.assert_allclose(y.entropy.cpu().numpy(), x.entropy.cpu().numpy(), rtol=RTOL, atol=0)
+    assert torch.equal(res["i8"][0].hist0, res["i8"][2].hist0) and torch.equal(res["i8"][0].entropy, res["i8"][2].entropy)
+    # exactness of the integer part: a frame whose users all sit on cell centres that coincide with
+    # nothing special still sums to the same total weight in both kernels up to the quantisation
+    tot64, tot8 = res["fp64"][0].hist0.sum(1), res["i8"][0].hist0.sum(1)
+    np.testing.assert_allclose(tot8.cpu().numpy(), tot64.cpu().numpy(), rtol=1e-11)
+    e.close()
