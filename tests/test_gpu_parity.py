@@ -679,3 +679,27 @@ def test_weighted_tensor_core_count_planes(vet, monkeypatch):
     tot64, tot8 = res["fp64"][0].hist0.sum(1), res["i8"][0].hist0.sum(1)
     np.testing.assert_allclose(tot8.cpu().numpy(), tot64.cpu().numpy(), rtol=1e-11)
     e.close()
+
+
+@pytest.mark.parametrize("U", [100_000, 20_001])
+def test_transition_two_pass_kernel_equals_three_pass_kernel(vet, U, monkeypatch):
+    """k_transition3 (two passes, one launch per tile count; dense table for 201 tiles, shared-memory
+    hash for 501/1001, rows that overflow it handed to k_transition2) against k_transition2 alone on
+    frames too large for the oracle: counts and pairs bit-exact, entropies to 1e-12."""
+    import bench
+    F = 40
+    p = bench.synth_on_device(torch, F, U, 515, torch.device("cuda"))
+    p[5, ::7, 1] = float("nan")                                   # missing users
+    g = torch.Generator(device="cuda").manual_seed(99)
+    p[20:23, :, 1:] = torch.rand((3, U, 2), generator=g, device="cuda")   # iid frames: ~U distinct pairs -> overflow rows
+    e = engine(vet, [200, 500, 1000], use_w=False)
+    res = {}
+    for impl in ("v2", "v3"):
+        monkeypatch.setenv("VET_TRANSITION_IMPL", impl)
+        res[impl] = e.transition(p)
+        assert e.poll_flags() == 0
+    a, b = res["v2"], res["v3"]
+    assert torch.equal(a.pairs0, b.pairs0) and torch.equal(a.prev_count0, b.prev_count0)
+    np.testing.assert_allclose(b.per_k.cpu().numpy(), a.per_k.cpu().numpy(), rtol=1e-12, atol=0)
+    np.testing.assert_allclose(b.entropy.cpu().numpy(), a.entropy.cpu().numpy(), rtol=1e-12, atol=0)
+    e.close()

@@ -50,4 +50,13 @@ if "tr" in which:
         out[f"transition_U{U}_F{F}_{tcs}"] = dict(ms=ms, gpairs=(F - 1) * U / ms / 1e6, prof=eng.profile_read())
         eng.profile(False)
         del p
-print(json.dumps(out, indent=1))
+if "c4" in which:  # BASELINE configs[3] at full size on one GPU, and its single-tile-count pieces
+    p = bench.synth_on_device(torch, 3600, 100_000, 4, dev)
+    for tcs in ([200, 500, 1000], [200], [500], [1000]):
+        eng = get_engine(100, 200, tcs, EntropyConfig(use_weight_distribution=False), dev)
+        eng.profile(True)
+        ms = timeit(lambda: eng.transition(p, want_pairs0=False, want_per_k=False), n=2, warm=1)
+        out[f"c4_transition_{tcs}"] = dict(ms=ms, gpairs=3599 * 100_000 / ms / 1e6, prof=eng.profile_read())
+        eng.profile(False)
+    del p
+print(json.dumps(out))

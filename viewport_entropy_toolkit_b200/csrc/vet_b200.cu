@@ -21,6 +21,7 @@
 #include "vet_tables.cuh"
 #include "vet_transition.cuh"
 #include "vet_transition2.cuh"
+#include "vet_transition3.cuh"
 #include "vet_vectors.cuh"
 #include "vet_whist.cuh"
 #include "vet_whist_i8.cuh"
@@ -126,6 +127,10 @@ struct vet_handle {
   uint32_t* d_i8flags = nullptr; // [2][plane_rows/128]
   CUtensorMap tm_cnt;
   bool planes_from_stream = false;  // the last launch_stream wrote the planes of its batch itself
+  uint32_t* d_redo = nullptr;   // [rows] frame pairs the two-pass transition kernel left to k_transition2
+  size_t redo_bytes = 0;
+  double* d_trk = nullptr;      // [K, rows] per-tile-count transition entropies when the caller wants none
+  size_t trk_bytes = 0;
   uint32_t tables_cap = 0;  // slot count the tables are currently laid out (and cleared) for
   int tables_blocks = 0;    // number of per-CTA tables cleared for that layout
   // host-buffer path
@@ -889,6 +894,8 @@ int ensure_planes(vet_handle* h, int64_t F, cudaStream_t st) {
   const int64_t rows = (F + vet::kI8M - 1) / vet::kI8M * vet::kI8M;
   if (rows <= h->plane_rows) return VET_OK;
   VET_CUDA(cudaStreamSynchronize(st));
+  cudaFree(h->d_redo);
+  cudaFree(h->d_trk);
   cudaFree(h->d_planes);
   cudaFree(h->d_dirty);
   cudaFree(h->d_i8flags);
@@ -1237,6 +1244,8 @@ extern "C" int vet_destroy(vet_handle* h) {
   for (void* p : h->d_vscratch) cudaFree(p);
   cudaFree(h->d_tables);
   cudaFree(h->d_pairs);
+  cudaFree(h->d_redo);
+  cudaFree(h->d_trk);
   cudaFree(h->d_planes);
   cudaFree(h->d_dirty);
   cudaFree(h->d_i8flags);
@@ -1647,51 +1656,15 @@ namespace {
 
 // Sizes the (prev,cur) pair tables, picks the shared- or global-memory variant and launches
 // k_transition for `rows` frame pairs.
-int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st) {
-  // capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
-  const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)Tmax * Tmax);
-  uint32_t cap = 1024;
-  while ((uint64_t)cap < 2 * max_pairs) cap <<= 1;
-  const size_t tile_bytes = (size_t)Tmax * (8 + 4 * 4);
-  const size_t smem_tab = tile_bytes + (size_t)cap * 16 + 64;
-  const bool in_smem = smem_tab + kStaticSmemSlack <= h->smem_optin;
-  const int blocks = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * (in_smem ? 1 : 2));
-  if (!in_smem) {
-    const size_t words = (size_t)blocks * 4 * cap;
-    if (h->tables_words < words || h->tables_cap != cap) {
-      if (h->tables_words < words) {
-        if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
-        h->d_tables = nullptr;
-        h->tables_words = 0;
-        VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
-        h->tables_words = words;
-      }
-      // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value).  Done once per layout:
-      // the kernels reset every slot they touch, so the tables stay clean between calls.
-      for (int b = 0; b < blocks; ++b) {
-        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
-        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
-      }
-      h->tables_cap = cap;
-      h->tables_blocks = blocks;
-    } else if (h->tables_blocks < blocks) {
-      for (int b = h->tables_blocks; b < blocks; ++b) {
-        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
-        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
-      }
-      h->tables_blocks = blocks;
-    }
-  }
-  a.cap = cap;
-  a.g_tables = h->d_tables;
-  static const bool force_v1 = [] {
-    const char* e = getenv("VET_TRANSITION_IMPL");
-    return e && std::string(e) == "v1";
-  }();
-  if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1) {
+// k_transition2 over all tile counts of `a` (dense table / shared-memory hash / global table per tile count);
+// only_rows != null restricts it to the flagged rows.
+int launch_transition2(vet_handle* h, const vet::TransitionArgs& a, int64_t U, int Tmax, int blocks, size_t tile_bytes,
+                       const uint32_t* only_rows, cudaStream_t st) {
+  {
     // fast paths: dense T*T table or shared-memory hash per tile count, global table as the in-kernel fallback
     vet::Transition2Args A2{};
     A2.t = a;
+    A2.only_rows = only_rows;
     const size_t budget = h->smem_optin - kStaticSmemSlack;
     size_t table_words = 0;
     for (int k = 0; k < a.K; ++k) {
@@ -1729,6 +1702,182 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
     VET_CUDA(cudaFuncSetAttribute(vet::k_transition2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
     vet::k_transition2<<<blocks, vet::kTrThreads, smem2, st>>>(A2, Tmax);
+  }
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st) {
+  // capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
+  const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)Tmax * Tmax);
+  uint32_t cap = 1024;
+  while ((uint64_t)cap < 2 * max_pairs) cap <<= 1;
+  const size_t tile_bytes = (size_t)Tmax * (8 + 4 * 4);
+  const size_t smem_tab = tile_bytes + (size_t)cap * 16 + 64;
+  const bool in_smem = smem_tab + kStaticSmemSlack <= h->smem_optin;
+  const int blocks = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * (in_smem ? 1 : 2));
+  if (!in_smem) {
+    const size_t words = (size_t)blocks * 4 * cap;
+    if (h->tables_words < words || h->tables_cap != cap) {
+      if (h->tables_words < words) {
+        if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
+        h->d_tables = nullptr;
+        h->tables_words = 0;
+        VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
+        h->tables_words = words;
+      }
+      // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value).  Done once per layout:
+      // the kernels reset every slot they touch, so the tables stay clean between calls.
+      for (int b = 0; b < blocks; ++b) {
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+      }
+      h->tables_cap = cap;
+      h->tables_blocks = blocks;
+    } else if (h->tables_blocks < blocks) {
+      for (int b = h->tables_blocks; b < blocks; ++b) {
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+      }
+      h->tables_blocks = blocks;
+    }
+  }
+  a.cap = cap;
+  a.g_tables = h->d_tables;
+  // VET_TRANSITION_IMPL = v1 | v2 pins an older kernel generation (A/B runs, tests); read at every call
+  const bool force_v1 = [] {
+    const char* e = getenv("VET_TRANSITION_IMPL");
+    return e && std::string(e) == "v1";
+  }();
+  const bool force_v2 = [] {
+    const char* e = getenv("VET_TRANSITION_IMPL");
+    return e && std::string(e) == "v2";
+  }();
+  // two-pass kernel, one launch per tile count; rows it cannot hold (hash overflow) are flagged in d_redo
+  // and recomputed by k_transition2 below
+  bool redo_only = false;
+  if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1 && !force_v2 && a.cell16 && U < ((int64_t)1 << 31)) {
+    const size_t budget = h->smem_optin - kStaticSmemSlack;
+    struct Plan {
+      int mode, lw;
+      size_t tab_off, lut_off, smem;
+      const void* lut;
+    } plan[vet::kMaxTileCounts];
+    bool ok = true;
+    for (int k = 0; k < a.K && ok; ++k) {
+      const size_t T = (size_t)a.T[k];
+      const uint8_t* l8 = nullptr;
+      bool is_cell_lut = false;
+      for (int j = 0; j < h->K; ++j)
+        if (h->ts[j].d_lut == a.lut[k]) {
+          l8 = h->ts[j].d_lut8;
+          is_cell_lut = true;
+        }
+      if (!is_cell_lut) {
+        ok = false;
+        break;
+      }
+      Plan& pl = plan[k];
+      pl.tab_off = (T * vet::kT3TileBytes + 15) & ~(size_t)15;
+      const size_t dense = T * T * 4, hash = (size_t)2 * vet::kT3Slots * 4;
+      size_t tab;
+      if (pl.tab_off + dense <= budget) {
+        pl.mode = vet::kT3Dense;
+        tab = dense;
+      } else if (pl.tab_off + hash <= budget) {
+        pl.mode = vet::kT3Hash;  // rows with more distinct pairs than the table holds are redone by k_transition2
+        tab = hash;
+      } else {
+        pl.mode = -1;  // this tile count goes to k_transition2 (global pair tables)
+        continue;
+      }
+      pl.lut_off = (pl.tab_off + tab + 15) & ~(size_t)15;
+      const size_t lut_bytes = (((size_t)h->C * (l8 ? 1 : 2)) + 15) & ~(size_t)15;
+      if (pl.lut_off + lut_bytes <= budget) {
+        pl.lw = l8 ? vet::kLutS8 : vet::kLutS16;
+        pl.lut = l8 ? (const void*)l8 : (const void*)a.lut[k];
+        pl.smem = pl.lut_off + lut_bytes;
+      } else {
+        pl.lw = vet::kLutG16;
+        pl.lut = a.lut[k];
+        pl.smem = pl.lut_off;
+      }
+    }
+    if (ok) {
+      const int blocks3 = (int)std::min<int64_t>(rows, h->sm_count);
+      if (int rc = grow((void**)&h->d_pairs, &h->pairs_bytes, (size_t)std::max(blocks, blocks3) * U * 4)) return rc;
+      if (int rc = grow((void**)&h->d_redo, &h->redo_bytes, (size_t)rows * 4)) return rc;
+      VET_CUDA(cudaMemsetAsync(h->d_redo, 0, (size_t)rows * 4, st));
+      double* per_k = a.per_k;
+      int64_t stride = a.per_k_stride;
+      if (a.K > 1 && !per_k) {
+        if (int rc = grow((void**)&h->d_trk, &h->trk_bytes, (size_t)a.K * rows * 8)) return rc;
+        per_k = h->d_trk;
+        stride = rows;
+      }
+      bool any_hash = false;
+      for (int k = 0; k < a.K; ++k) {
+        const Plan& pl = plan[k];
+        double* out_k = a.K == 1 ? a.entropy : per_k + k * stride;
+        if (pl.mode < 0) {
+          vet::TransitionArgs a1 = a;
+          a1.K = 1;
+          a1.T[0] = a.T[k];
+          a1.lut[0] = a.lut[k];
+          a1.entropy = out_k;
+          a1.per_k = nullptr;
+          a1.prev_count0 = k == 0 ? a.prev_count0 : nullptr;
+          a1.pairs0 = k == 0 ? a.pairs0 : nullptr;
+          if (int rc = launch_transition2(h, a1, U, Tmax, blocks, tile_bytes, nullptr, st)) return rc;
+          continue;
+        }
+        any_hash = any_hash || pl.mode == vet::kT3Hash;
+        vet::Transition3Args A3{};
+        A3.cell16 = a.cell16;
+        A3.F = a.F;
+        A3.U = (uint32_t)U;
+        A3.T = a.T[k];
+        A3.C = (int)h->C;
+        A3.lut_src = pl.lut;
+        A3.tab_off = (int)pl.tab_off;
+        A3.lut_off = (int)pl.lut_off;
+        A3.out = out_k;
+        A3.prev_count0 = k == 0 ? a.prev_count0 : nullptr;
+        A3.pairs0 = k == 0 ? a.pairs0 : nullptr;
+        A3.pair_scratch = h->d_pairs;
+        A3.redo = h->d_redo;
+        A3.flags = a.flags;
+        LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+#define VET_T3(MODE, LW)                                                                                              \
+  do {                                                                                                                \
+    VET_CUDA(cudaFuncSetAttribute(vet::k_transition3<MODE, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
+    vet::k_transition3<MODE, LW><<<blocks3, vet::kT3Threads, pl.smem, st>>>(A3);                                      \
+  } while (0)
+        if (pl.mode == vet::kT3Dense) {
+          if (pl.lw == vet::kLutS8) VET_T3(vet::kT3Dense, vet::kLutS8);
+          else if (pl.lw == vet::kLutS16) VET_T3(vet::kT3Dense, vet::kLutS16);
+          else VET_T3(vet::kT3Dense, vet::kLutG16);
+        } else {
+          if (pl.lw == vet::kLutS8) VET_T3(vet::kT3Hash, vet::kLutS8);
+          else if (pl.lw == vet::kLutS16) VET_T3(vet::kT3Hash, vet::kLutS16);
+          else VET_T3(vet::kT3Hash, vet::kLutG16);
+        }
+#undef VET_T3
+        VET_CUDA(cudaGetLastError());
+      }
+      if (a.K == 1 && a.per_k) {
+        VET_CUDA(cudaMemcpyAsync(a.per_k, a.entropy, (size_t)rows * 8, cudaMemcpyDeviceToDevice, st));
+      } else if (a.K > 1) {
+        LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+        vet::k_mean_rows<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(per_k, stride, a.K, rows, a.entropy);
+        VET_CUDA(cudaGetLastError());
+      }
+      if (!any_hash) return VET_OK;  // nothing can have been left over
+      redo_only = true;
+    }
+  }
+  if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1) {
+    if (int rc = launch_transition2(h, a, U, Tmax, blocks, tile_bytes, redo_only ? h->d_redo : nullptr, st)) return rc;
   } else if (in_smem) {
     VET_CUDA(cudaFuncSetAttribute(vet::k_transition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
     LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);

@@ -29,6 +29,7 @@ struct Transition2Args {
   const uint8_t* lut8[kMaxTileCounts];  // uint8 LUTs (null when T > 255)
   int lut_area_off;               // byte offset of the LUT staging area inside dynamic shared memory
   uint32_t* pair_scratch;         // [gridDim.x, U] (prev | cur << 16) of the current frame pair and tile count
+  const uint32_t* only_rows;      // optional [F-1]: process only the flagged rows (left over by k_transition3)
 };
 
 // per previous tile: users, first user, distinct keys, count of the latest key, latest key
@@ -93,7 +94,9 @@ __device__ __forceinline__ void pass_count(const TransitionArgs& a, const LutVie
       if (pc[j] != kNoPair) {
         const uint32_t p = pc[j] & 0xFFFFu;
         atomicAdd(&ta.m[p], 1u);
-        atomicMin(&ta.first[p], (uint32_t)u);
+        // minima only decrease: a plain (broadcast) load filters out almost every atomic, since user
+        // indices arrive in roughly increasing order
+        if ((uint32_t)u < *(volatile uint32_t*)&ta.first[p]) atomicMin(&ta.first[p], (uint32_t)u);
       }
       if (write_pairs0) *reinterpret_cast<uint32_t*>(a.pairs0 + 2 * (prow + u)) = pc[j];  // (prev, cur) or (0xFFFF, 0xFFFF)
     }
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(kTrThreads, 1) k_transition2(Transition2Args A
   unsigned char* s_lutarea = smem_raw + A.lut_area_off;
   int staged_k = -1;
   for (int64_t r = blockIdx.x; r < a.F - 1; r += gridDim.x) {
+    if (A.only_rows && A.only_rows[r] == 0u) continue;  // uniform over the CTA
     const int64_t prow = r * a.U, crow = (r + 1) * a.U;
     double esum = 0.0;
     for (int k = 0; k < a.K; ++k) {
@@ -224,7 +228,10 @@ __global__ void __launch_bounds__(kTrThreads, 1) k_transition2(Transition2Args A
       if (mode == kTrDense) {
         // pass 2: smallest non-first user index of every (prev,cur)
         for_pairs(a, pairs, [&](uint32_t u, uint32_t p, uint32_t c) {
-          if (ta.first[p] != u) atomicMin(&s_tab[p * (uint32_t)T + c], u);
+          if (ta.first[p] != u) {
+            uint32_t* s = &s_tab[p * (uint32_t)T + c];
+            if (u < *(volatile uint32_t*)s) atomicMin(s, u);
+          }
         });
         __syncthreads();
         // one warp per previous tile: distinct keys and the key seen first latest; rows reset on the way
@@ -255,14 +262,20 @@ __global__ void __launch_bounds__(kTrThreads, 1) k_transition2(Transition2Args A
             const uint32_t key = p * (uint32_t)T + c;
             uint32_t slot = (key * 2654435761u) & stb.mask;
             for (int probe = 0;; ++probe) {
-              const uint32_t old = atomicCAS(&stb.keys[slot], kEmpty, key);
+              // most users repeat a key that is already in the table: a plain load finds it without
+              // the serialised same-address CAS, and the first-user minimum rarely needs its atomic
+              uint32_t old = *(volatile uint32_t*)&stb.keys[slot];
               if (old == kEmpty) {
-                const uint32_t pos = atomicAdd(&s_used, 1u);
-                if (pos < kHashLimit) stb.list[pos] = slot;
-                else s_overflow = 1u;
+                old = atomicCAS(&stb.keys[slot], kEmpty, key);
+                if (old == kEmpty) {
+                  const uint32_t pos = atomicAdd(&s_used, 1u);
+                  if (pos < kHashLimit) stb.list[pos] = slot;
+                  else s_overflow = 1u;
+                  old = key;
+                }
               }
-              if (old == kEmpty || old == key) {
-                atomicMin(&stb.firsts[slot], u);
+              if (old == key) {
+                if (u < *(volatile uint32_t*)&stb.firsts[slot]) atomicMin(&stb.firsts[slot], u);
                 break;
               }
               if (probe >= kMaxProbes) {
