@@ -335,7 +335,7 @@ def main():
     # DRAM bytes of one launch from the committed ncu --set full capture (profiles/), configs[2] only
     traffic = None
     try:
-        tr_rec = json.loads((ROOT / "profiles" / "r01e_traffic.json").read_text())
+        tr_rec = json.loads((ROOT / "profiles" / "r01f_traffic.json").read_text())
         if args.workload == tr_rec["workload"]:
             traffic = tr_rec["dram_bytes_read"] + tr_rec["dram_bytes_write"]
     except Exception:
