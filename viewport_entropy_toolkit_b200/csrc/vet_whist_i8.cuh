@@ -25,7 +25,8 @@
 //
 // One CTA per (frame block, N block), 192 threads, warp-specialised:
 //   warp 0, one lane   TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the count planes
-//                      [128 x 128 B each] and the weight slices [240 x 128 B] into a 3-stage ring;
+//                      [128 x 128 B each] and the weight slices [240 x 128 B] into a ring of 4 stages
+//                      (3 when the frame block needs the second count plane);
 //   warp 1, one lane   tcgen05.mma.kind::i8 (M128 N240 K32, u8 x u8 -> s32) into TMEM: accumulator
 //                      of plane 0 in columns [0,240), of plane 1 in [256,496); tcgen05.commit
 //                      releases the stage / signals the epilogue;
@@ -45,14 +46,16 @@ constexpr int kI8TilesPerBlock = 48;
 constexpr int kI8N = kI8Slices * kI8TilesPerBlock;  // 240
 constexpr int kI8M = 128;
 constexpr int kI8BK = 128;  // cells (= bytes) per pipeline stage: one swizzle row
-constexpr int kI8Stages = 3;
+constexpr int kI8Stages = 3;      // with both count planes (62 KB per stage)
+constexpr int kI8StagesOne = 4;   // with plane 0 only (46 KB per stage): the usual case
 constexpr int kI8ABytes = kI8M * kI8BK;                    // 16 KB per count plane
 constexpr int kI8BBytes = kI8N * kI8BK;                    // 30 KB
 constexpr int kI8StageBytes = 2 * kI8ABytes + kI8BBytes;   // 62 KB, multiple of 1024
 constexpr int kI8Threads = 192;
 constexpr int kI8TmemCols = 512;
 constexpr int kI8SmemBytes = kI8Stages * kI8StageBytes + 1024;  // + slack to align the ring to 1024 B
-static_assert(kI8StageBytes % 1024 == 0, "stages must keep the 1024 B swizzle alignment");
+static_assert(kI8StageBytes % 1024 == 0 && (kI8ABytes + kI8BBytes) % 1024 == 0, "stages must keep the 1024 B swizzle alignment");
+static_assert(kI8StagesOne * (kI8ABytes + kI8BBytes) <= kI8Stages * kI8StageBytes, "both layouts share one ring");
 
 // ---- PTX wrappers (layouts: PTX ISA "tcgen05" / CUTLASS cute/arch/mma_sm100_desc.hpp) ----
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
@@ -126,15 +129,19 @@ k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ C
   const int mb = blockIdx.x / a.n_blocks;
   if (a.run_if && a.run_if[mb] == 0u) return;
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) unsigned long long s_full[kI8Stages], s_empty[kI8Stages], s_accum;
+  __shared__ __align__(8) unsigned long long s_full[kI8StagesOne], s_empty[kI8StagesOne], s_accum;
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int2 kr = a.kb_range[nb];
   const bool two = a.flag_b && a.flag_b[mb] != 0u;
 
+  // the ring holds 3 stages of {plane 0, plane 1, weights} or 4 stages of {plane 0, weights}
+  const uint32_t nstages = two ? kI8Stages : kI8StagesOne;
+  const uint32_t stage_bytes = two ? (uint32_t)kI8StageBytes : (uint32_t)(kI8ABytes + kI8BBytes);
+  const uint32_t w_off = two ? 2u * kI8ABytes : (uint32_t)kI8ABytes;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kI8Stages; ++i) {
+    for (int i = 0; i < kI8StagesOne; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
       mbar_init(smem_u32(&s_empty[i]), 1);
     }
@@ -150,36 +157,41 @@ k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ C
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      const uint32_t bytes = two ? (uint32_t)kI8StageBytes : (uint32_t)(kI8ABytes + kI8BBytes);
-      uint32_t n = 0;
-      for (int kb = kr.x; kb < kr.y; ++kb, ++n) {
-        const uint32_t stage = n % kI8Stages;
-        mbar_wait(smem_u32(&s_empty[stage]), ((n / kI8Stages) & 1u) ^ 1u);
+      uint32_t stage = 0, phase = 0;
+      for (int kb = kr.x; kb < kr.y; ++kb) {
+        mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
         const uint32_t bar = smem_u32(&s_full[stage]);
-        const uint32_t base = ring + stage * kI8StageBytes;
-        mbar_expect_tx(bar, bytes);
+        const uint32_t base = ring + stage * stage_bytes;
+        mbar_expect_tx(bar, stage_bytes);
         tma_load_2d(base, &tm_cnt, bar, kb * kI8BK, a.row_a + mb * kI8M);
         if (two) tma_load_2d(base + kI8ABytes, &tm_cnt, bar, kb * kI8BK, a.row_b + mb * kI8M);
-        tma_load_2d(base + 2 * kI8ABytes, &tm_w, bar, kb * kI8BK, nb * kI8N);
+        tma_load_2d(base + w_off, &tm_w, bar, kb * kI8BK, nb * kI8N);
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      uint32_t n = 0;
-      for (int kb = kr.x; kb < kr.y; ++kb, ++n) {
-        const uint32_t stage = n % kI8Stages;
-        mbar_wait(smem_u32(&s_full[stage]), (n / kI8Stages) & 1u);
+      uint32_t stage = 0, phase = 0;
+      for (int kb = kr.x; kb < kr.y; ++kb) {
+        mbar_wait(smem_u32(&s_full[stage]), phase);
         tc_fence_after();
-        const uint32_t base = ring + stage * kI8StageBytes;
+        const uint32_t base = ring + stage * stage_bytes;
 #pragma unroll
         for (int k = 0; k < kI8BK / 32; ++k) {  // one instruction covers 32 cells
           const uint32_t acc = (kb > kr.x || k > 0) ? 1u : 0u;
-          const uint64_t bdesc = i8_smem_desc(base + 2 * kI8ABytes + k * 32);
+          const uint64_t bdesc = i8_smem_desc(base + w_off + k * 32);
           tc_mma_i8(tmem, i8_smem_desc(base + k * 32), bdesc, kI8InstrDesc, acc);
           if (two) tc_mma_i8(tmem + 256, i8_smem_desc(base + kI8ABytes + k * 32), bdesc, kI8InstrDesc, acc);
         }
         tc_commit(smem_u32(&s_empty[stage]));  // stage is free once these MMAs have read it
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
       tc_commit(smem_u32(&s_accum));
     }
