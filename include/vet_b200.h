@@ -79,6 +79,17 @@ typedef struct {
    * (the reference's free functions accept any List[Vector], EU:70-151,213-219).  When
    * non-NULL, T_k = num_tiles[k] (tile_counts[k] is ignored) and `centres` is required. */
   const int32_t* num_tiles;
+  /* Optional: latitude/longitude grid tiling of NaiveSpatialEntropyAnalyzer (NA:39-241,
+   * compute_naive_spatial_entropy EU:362-453) instead of the lattice.  When naive_tile_width > 0 the
+   * handle has ONE tile set; the "tile" of a sample is the reference's string key
+   * "{int((lon+180)/tile_width)}_{int((lat+90)/tile_height)}" (EU:378-381) encoded as
+   *     lon_idx * (180/tile_height + 1) + lat_idx          (vet_num_tiles = number of such codes),
+   * every sample weighs 1.0 on its tile (EU:357), and use_weight_distribution only selects the
+   * normalisation (EU:443-448: by num_tiles = (180/h)*(360/w) when set or when there are more
+   * users than tiles, else by the user count).  tile_counts / centres / fov / power are ignored.
+   * 360 % tile_width == 0 and 180 % tile_height == 0 are required (EU:414-417). */
+  int32_t naive_tile_width;
+  int32_t naive_tile_height;
 } vet_config;
 
 const char* vet_last_error(void);
@@ -184,6 +195,15 @@ int vet_spatial_host(vet_handle* h, const void* packed_host, int dtype, int64_t 
 int vet_transition_host(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U,
                         double* entropy_host, double* per_k_host, int32_t* prev_count0_host,
                         uint16_t* pairs0_host, int mode);
+
+/* compute_naive_spatial_entropy (EU:362-453) for frames of ARBITRARY RadialPoints:
+ * lonlat_dev[F,U,2] float64 degrees (NaN = absent user, EU:426-427) ->
+ *   entropy_dev[F]     normalised entropy (NaN for a frame without users: the reference raises, flag word)
+ *   lon_idx_dev[F,U], lat_idx_dev[F,U]   (optional) the two halves of find_naive_tile_index (EU:360-381), -1 = absent
+ * Stateless apart from the handle's device and flag word; tile sizes in degrees as in NaiveAnalyzerConfig (CFG:104-105). */
+int vet_naive_points(vet_handle* h, const double* lonlat_dev, int64_t F, int64_t U, int32_t tile_width,
+                     int32_t tile_height, int32_t use_weight_distribution, double* entropy_dev,
+                     int32_t* lon_idx_dev, int32_t* lat_idx_dev, void* stream);
 
 /* Synchronises `stream`, returns the sticky VET_FLAG_* word in *flags and
  * clears it. */

@@ -524,3 +524,82 @@ def transition_analyzer(packed: np.ndarray, W: int, H: int, tile_counts: Sequenc
     for k in range(K):                       # TA:139-160
         ent = ent + per_k[k]
     return dict(entropy=ent / K, per_k=per_k, prev_count0=prev_count0, pairs0=pairs0)
+
+
+# ---------------------------------------------------------------------------
+# Latitude/longitude grid tiling (NaiveSpatialEntropyAnalyzer; EU:335-453, NA:102-152)
+# ---------------------------------------------------------------------------
+def naive_tile_index(lon, lat, tile_width: int, tile_height: int) -> Tuple[np.ndarray, np.ndarray]:
+    """find_naive_tile_index (EU:378-379), vectorised: int((lon+180)/tile_width), int((lat+90)/tile_height)
+    (true division, truncation; both operands non-negative for valid RadialPoints)."""
+    li = np.trunc((np.asarray(lon, dtype=np.float64) + 180) / tile_width).astype(np.int64)
+    la = np.trunc((np.asarray(lat, dtype=np.float64) + 90) / tile_height).astype(np.int64)
+    return li, la
+
+
+def compute_naive_spatial_entropy_literal(points: Dict[str, Optional[Tuple[float, float]]], tile_height: int,
+                                          tile_width: int, use_weight: bool):
+    """compute_naive_spatial_entropy (EU:404-453) with its dict bookkeeping; points maps an identifier
+    to (lon, lat) or None.  Returns (entropy, {key: weight}, {identifier: key})."""
+    if not points:
+        raise OracleValidationError("Empty radial points dictionary")
+    if not tile_height or not tile_width:
+        raise OracleValidationError("No tile dimensions provided")
+    if 180 % tile_height != 0:
+        raise OracleValidationError("Tile height must divide 180!")
+    if 360 % tile_width != 0:
+        raise OracleValidationError("Tile width must divide 360!")
+    num_tiles = int(180.0 / tile_height) * int(360.0 / tile_width)      # EU:409
+    weight_per_tile: Dict[str, float] = {}
+    total_weight = 0.0
+    assignments: Dict[str, str] = {}
+    for identifier, point in points.items():
+        if point is None:                                                # EU:426-427
+            continue
+        key = f"{int((point[0] + 180) / tile_width)}_{int((point[1] + 90) / tile_height)}"   # EU:378-381
+        assignments[identifier] = key
+        weight_per_tile[key] = weight_per_tile.get(key, 0.0) + 1.0      # EU:357, 433-435
+        total_weight += 1.0
+    spatial_entropy = 0.0
+    for weight in weight_per_tile.values():                              # EU:437-440
+        proportion = weight / total_weight
+        spatial_entropy -= proportion * np.log2(proportion)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if use_weight or total_weight > num_tiles:                       # EU:443-448
+            max_proportion = 1.0 / num_tiles
+            max_entropy = -num_tiles * max_proportion * np.log2(max_proportion)
+        else:
+            max_proportion = 1.0 / total_weight
+            max_entropy = -total_weight * max_proportion * np.log2(max_proportion)
+        return np.float64(spatial_entropy) / max_entropy, weight_per_tile, assignments
+
+
+def naive_analyzer(packed: np.ndarray, W: int, H: int, tile_width: int, tile_height: int, use_weight: bool):
+    """NA:125-150 on packed[F,U,3].  Returns dict(entropy[F], hist0[F,codes] (users per grid code
+    lon_idx*(180/tile_height+1)+lat_idx), assign0[F,U] uint16 codes, lon_idx/lat_idx[F,U] (-1 = absent))."""
+    packed = np.asarray(packed)
+    F, U, _ = packed.shape
+    px, py, valid = decode(packed[..., 1], packed[..., 2], W, H)
+    lon_t, lat_t = axis_tables(W, H)
+    li, la = naive_tile_index(lon_t[px], lat_t[py], tile_width, tile_height)
+    nlat1 = 180 // tile_height + 1
+    codes = (360 // tile_width + 1) * nlat1
+    num_tiles = int(180.0 / tile_height) * int(360.0 / tile_width)
+    ent = np.empty(F, dtype=np.float64)
+    hist0 = np.zeros((F, codes), dtype=np.float64)
+    assign0 = np.full((F, U), MISSING, dtype=np.uint16)
+    for f in range(F):
+        ok = valid[f]
+        if not ok.any():
+            raise OracleValidationError("Empty radial points dictionary")
+        code = li[f][ok] * nlat1 + la[f][ok]
+        hist = np.bincount(code, minlength=codes).astype(np.float64)
+        total = float(ok.sum())
+        p = hist[hist > 0] / total
+        Hs = -(p * np.log2(p)).sum()
+        n = float(num_tiles) if (use_weight or total > num_tiles) else total
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ent[f] = np.float64(Hs) / (-n * (1.0 / n) * np.log2(1.0 / n))
+        hist0[f] = hist
+        assign0[f, ok] = code
+    return dict(entropy=ent, hist0=hist0, assign0=assign0, lon_idx=np.where(valid, li, -1), lat_idx=np.where(valid, la, -1))

@@ -434,9 +434,102 @@ def gen_analyzers():
             out[f"dir10/{nme}"] = df[["time", "2dmu", "2dmv"]].to_numpy(dtype=np.float64)
     np.savez_compressed(OUT / "analyzers.npz", **out)
 
+NAIVE_TILES = [(30, 30), (45, 90), (10, 20), (360, 180), (3, 3), (120, 60)]   # (tile_width, tile_height) degrees
+
+
+def gen_naive():
+    """Latitude/longitude grid tiling (NaiveSpatialEntropyAnalyzer NA:39-241, EU:335-453): the reference's
+    tile key of EVERY reachable cell for several tile sizes, compute_naive_spatial_entropy on seeded frames
+    (both normalisations, missing users), and the analyzer end to end on a CSV directory."""
+    import pandas as pd
+    vet, U = _ref()
+    out = {}
+    # (1) every cell of the default grid through the reference decode chain and find_naive_tile_index
+    lon = np.zeros((H0 + 1, W0 + 1))
+    lat = np.zeros((H0 + 1, W0 + 1))
+    for py in range(H0 + 1):
+        for px in range(W0 + 1):
+            lon[py, px], lat[py, px], _ = ref_cell_vector(px, py, W0, H0)
+    for tw, th in NAIVE_TILES:
+        li = np.zeros((H0 + 1, W0 + 1), dtype=np.int32)
+        la = np.zeros((H0 + 1, W0 + 1), dtype=np.int32)
+        for py in range(H0 + 1):
+            for px in range(W0 + 1):
+                key = U.find_naive_tile_index(vet.RadialPoint(lon=lon[py, px], lat=lat[py, px]), th, tw)
+                a, b = key.split("_")
+                li[py, px], la[py, px] = int(a), int(b)
+        out[f"cells/{tw}x{th}/lon_idx"] = li
+        out[f"cells/{tw}x{th}/lat_idx"] = la
+    # (2) seeded frames
+    cases = [("n_30_w", 5, 400, (30, 30), True, 0.0, False), ("n_30_u", 5, 400, (30, 30), False, 0.1, False),
+             ("n_45x90_u", 4, 3, (45, 90), False, 0.0, True), ("n_10x20_w", 3, 1500, (10, 20), True, 0.05, True),
+             ("n_360_u", 3, 50, (360, 180), False, 0.0, True), ("n_3_u", 3, 6000, (3, 3), False, 0.0, True),
+             ("n_120x60_one", 2, 1, (120, 60), False, 0.0, False)]
+    for tag, F, Un, (tw, th), use_w, missing, iid in cases:
+        packed = synth_packed(F, Un, 9000 + Un, missing=missing, iid=iid)
+        ent = np.zeros(F)
+        keys = np.full((F, Un, 2), -1, dtype=np.int32)
+        nkeys = np.zeros(F, dtype=np.int64)
+        for f in range(F):
+            mu = packed[f, :, 1].astype(np.float64)
+            mv = packed[f, :, 2].astype(np.float64)
+            ok = ~(np.isnan(mu) | np.isnan(mv))
+            px = U.normalize_to_pixel(np.where(ok, mu, 0.0), W0)
+            py = U.normalize_to_pixel(np.where(ok, mv, 0.0), H0)
+            pts = {}
+            for u in range(Un):
+                if ok[u]:
+                    lo, la_, _ = ref_cell_vector(px[u], py[u], W0, H0)
+                    pts[f"u{u:05d}"] = vet.RadialPoint(lon=lo, lat=la_)
+                else:
+                    pts[f"u{u:05d}"] = None
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                e, wts, asg = U.compute_naive_spatial_entropy(pts, th, tw, U.EntropyConfig(use_weight_distribution=use_w))
+            ent[f] = e
+            nkeys[f] = len(wts)
+            assert sum(wts.values()) == ok.sum()
+            for u in range(Un):
+                if ok[u]:
+                    a, b = asg[f"u{u:05d}"].split("_")
+                    keys[f, u] = (int(a), int(b))
+        out[f"frames/{tag}/packed"] = packed
+        out[f"frames/{tag}/tile"] = np.array([tw, th])
+        out[f"frames/{tag}/use_w"] = np.array(use_w)
+        out[f"frames/{tag}/entropy"] = ent
+        out[f"frames/{tag}/keys"] = keys
+        out[f"frames/{tag}/nkeys"] = nkeys
+        print("naive", tag, ent, flush=True)
+    # (3) analyzer end to end on the dir10 directory of analyzers.npz
+    src = np.load(OUT / "analyzers.npz")
+    names = [f"user{u:02d}" for u in range(10)]
+    real_glob = Path.glob
+    with tempfile.TemporaryDirectory() as d, tempfile.TemporaryDirectory() as od:
+        for nme in names:
+            a = src[f"dir10/{nme}"]
+            pd.DataFrame({"time": a[:, 0], "2dmu": a[:, 1], "2dmv": a[:, 2]}).to_csv(f"{d}/{nme}.csv", index=False)
+        Path.glob = lambda self, pat: iter([Path(d) / f"{n}.csv" for n in names])
+        try:
+            for tw, th, use_w in ((30, 30, True), (45, 90, False)):
+                from viewport_entropy_toolkit.config import NaiveAnalyzerConfig
+                cfg = NaiveAnalyzerConfig(video_width=W0, video_height=H0, output_dir=Path(od), tile_width=tw, tile_height=th,
+                                              entropy_config=U.EntropyConfig(use_weight_distribution=use_w))
+                na = vet.NaiveSpatialEntropyAnalyzer(cfg)
+                na.process_directory(Path(d))
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    df = na.compute_entropy()
+                out[f"analyzer/{tw}x{th}_{int(use_w)}/time"] = df["time"].to_numpy(dtype=np.float64)
+                out[f"analyzer/{tw}x{th}_{int(use_w)}/entropy"] = df["entropy"].to_numpy(dtype=np.float64)
+                assert df["tile_weights"].isna().all() and df["tile_assignments"].isna().all()
+                print("naive analyzer", tw, th, use_w, df["entropy"].to_numpy()[:4], flush=True)
+        finally:
+            Path.glob = real_glob
+    np.savez_compressed(OUT / "naive.npz", **out)
+
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lattices", "decode", "nearest", "weights", "frames", "quirks", "analyzers"]
+    which = sys.argv[1:] or ["lattices", "decode", "nearest", "weights", "frames", "quirks", "analyzers", "naive"]
     for w in which:
         {"lattices": gen_lattices, "decode": gen_decode, "nearest": gen_nearest, "weights": gen_weights,
-         "frames": gen_frames, "quirks": gen_transition_quirks, "analyzers": gen_analyzers}[w]()
+         "frames": gen_frames, "quirks": gen_transition_quirks, "analyzers": gen_analyzers, "naive": gen_naive}[w]()

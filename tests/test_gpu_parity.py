@@ -703,3 +703,110 @@ def test_transition_two_pass_kernel_equals_three_pass_kernel(vet, U, monkeypatch
     np.testing.assert_allclose(b.per_k.cpu().numpy(), a.per_k.cpu().numpy(), rtol=1e-12, atol=0)
     np.testing.assert_allclose(b.entropy.cpu().numpy(), a.entropy.cpu().numpy(), rtol=1e-12, atol=0)
     e.close()
+
+
+# ---------------------------------------------------------------------------------
+# latitude/longitude grid tiling (NaiveSpatialEntropyAnalyzer, NA:39-241 / EU:335-453)
+# ---------------------------------------------------------------------------------
+def _naive_golden():
+    npz = load_golden("naive")
+    out = {}
+    for k in npz.files:
+        case, _, field = k.rpartition("/")
+        out.setdefault(case, {})[field] = npz[k]
+    return out
+
+
+def test_naive_cell_table_every_cell_vs_reference(vet):
+    """The grid code of every reachable cell (the cell -> tile table the streaming kernels use) against the
+    reference's find_naive_tile_index on its own decode chain, for six tile sizes."""
+    g = _naive_golden()
+    for name, c in g.items():
+        if not name.startswith("cells/"):
+            continue
+        tw, th = (int(x) for x in name.split("/")[1].split("x"))
+        e = vet.Engine(W0, H0, [1], vet.EntropyConfig(), naive_tiles=(tw, th))
+        nlat1 = 180 // th + 1
+        assert e.num_tiles[0] == (360 // tw + 1) * nlat1
+        lut = e.cell_lut(0).astype(np.int64)
+        assert np.array_equal(lut // nlat1, c["lon_idx"]) and np.array_equal(lut % nlat1, c["lat_idx"]), name
+        e.close()
+
+
+@pytest.mark.parametrize("case", ["n_30_w", "n_30_u", "n_45x90_u", "n_10x20_w", "n_360_u", "n_3_u", "n_120x60_one"])
+def test_naive_frames_vs_reference_fixtures(vet, case):
+    """Packed path (streaming kernels with the grid table) and the functional API on RadialPoint dicts
+    (k_naive_points) against compute_naive_spatial_entropy of the live reference; -inf / NaN quirks of
+    a single 360x180 tile included."""
+    c = _naive_golden()[f"frames/{case}"]
+    tw, th = (int(x) for x in c["tile"])
+    use_w = bool(c["use_w"])
+    cfg = vet.NaiveAnalyzerConfig(tile_width=tw, tile_height=th, output_dir=__import__("pathlib").Path("/tmp/vet_naive"),
+                                  entropy_config=vet.EntropyConfig(use_weight_distribution=use_w))
+    na = vet.NaiveSpatialEntropyAnalyzer(cfg)
+    packed = c["packed"]
+    for p in (packed.astype(np.float32), packed.astype(np.float64)):
+        res = na.compute_entropy_packed(dev(p))
+        np.testing.assert_allclose(res.entropy.cpu().numpy(), c["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+        nlat1 = 180 // th + 1
+        code = res.assign0.cpu().numpy().astype(np.int64)
+        ok = code != 0xFFFF
+        assert np.array_equal(np.where(ok, code // nlat1, -1), c["keys"][..., 0])
+        assert np.array_equal(np.where(ok, code % nlat1, -1), c["keys"][..., 1])
+        hist = res.hist0.cpu().numpy()
+        assert np.array_equal((hist > 0).sum(1), c["nkeys"]) and np.array_equal(hist.sum(1), ok.sum(1))
+    ref = orc.naive_analyzer(packed, W0, H0, tw, th, use_w)
+    assert np.array_equal(res.hist0.cpu().numpy(), ref["hist0"]) and np.array_equal(res.assign0.cpu().numpy(), ref["assign0"])
+    # functional API, frame 0
+    px, py, ok0 = orc.decode(packed[0, :, 1], packed[0, :, 2], W0, H0)
+    lon_t, lat_t = orc.axis_tables(W0, H0)
+    pts = {f"u{u:05d}": (vet.RadialPoint(float(lon_t[px[u]]), float(lat_t[py[u]])) if ok0[u] else None) for u in range(len(ok0))}
+    e, wts, asg = vet.compute_naive_spatial_entropy(pts, th, tw, vet.EntropyConfig(use_weight_distribution=use_w))
+    np.testing.assert_allclose(e, c["entropy"][0], rtol=RTOL, atol=ATOL, equal_nan=True)
+    assert len(wts) == c["nkeys"][0] and sum(wts.values()) == ok0.sum()
+    for u in np.flatnonzero(ok0):
+        assert asg[f"u{u:05d}"] == f"{c['keys'][0, u, 0]}_{c['keys'][0, u, 1]}"
+        assert asg[f"u{u:05d}"] == vet.find_naive_tile_index(pts[f"u{u:05d}"], th, tw)
+
+
+def test_naive_analyzer_end_to_end_and_errors(vet, tmp_path):
+    import pandas as pd
+    a = load_golden("analyzers")
+    g = _naive_golden()
+    d10 = tmp_path / "dir10"; d10.mkdir()
+    names = [f"user{u:02d}" for u in range(10)]
+    for n in names:
+        arr = a[f"dir10/{n}"]
+        pd.DataFrame({"time": arr[:, 0], "2dmu": arr[:, 1], "2dmv": arr[:, 2]}).to_csv(d10 / f"{n}.csv", index=False)
+    for tw, th, use_w in ((30, 30, True), (45, 90, False)):
+        cfg = vet.NaiveAnalyzerConfig(output_dir=tmp_path / "out", tile_width=tw, tile_height=th,
+                                      entropy_config=vet.EntropyConfig(use_weight_distribution=use_w))
+        na = vet.NaiveSpatialEntropyAnalyzer(cfg)
+        na.process_directory(d10, order=names)
+        df = na.compute_entropy()
+        ref = g[f"analyzer/{tw}x{th}_{int(use_w)}"]
+        assert np.array_equal(df["time"].to_numpy(), ref["time"])
+        np.testing.assert_allclose(df["entropy"].to_numpy(), ref["entropy"], rtol=RTOL, atol=ATOL)
+        assert df["tile_weights"].isna().all() and df["tile_assignments"].isna().all()   # NA:136-150
+    na.create_visualization("naive_e2e")
+    assert (tmp_path / "out" / "naive_e2e.csv").exists()
+    # error behaviour (CFG:112-115, EU:404-417)
+    with pytest.raises(ValueError):
+        vet.NaiveAnalyzerConfig(tile_width=0, tile_height=30, output_dir=tmp_path / "out")
+    pt = {"a": vet.RadialPoint(0.0, 0.0)}
+    with pytest.raises(vet.ValidationError):
+        vet.compute_naive_spatial_entropy({}, 30, 30, vet.EntropyConfig())
+    with pytest.raises(vet.ValidationError):
+        vet.compute_naive_spatial_entropy(pt, 7, 30, vet.EntropyConfig())
+    with pytest.raises(vet.ValidationError):
+        vet.compute_naive_spatial_entropy(pt, 30, 7, vet.EntropyConfig())
+    bad = vet.NaiveSpatialEntropyAnalyzer(vet.NaiveAnalyzerConfig(tile_width=7, tile_height=30, output_dir=tmp_path / "out"))
+    bad.load_packed(np.zeros((2, 3, 3)) + 0.5)
+    with pytest.raises(vet.ValidationError):
+        bad.compute_entropy()
+    empty = vet.NaiveSpatialEntropyAnalyzer(vet.NaiveAnalyzerConfig(tile_width=30, tile_height=30, output_dir=tmp_path / "out"))
+    p = np.zeros((2, 3, 3)) + 0.5
+    p[1, :, 1] = np.nan
+    empty.load_packed(p)
+    with pytest.raises(vet.ValidationError, match="Empty radial points"):
+        empty.compute_entropy()

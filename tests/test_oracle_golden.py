@@ -219,3 +219,62 @@ def test_edge_cases():
     packed = np.zeros((2, 3, 3)); packed[..., 1:] = 0.5; packed[1, :, 1] = np.nan
     with pytest.raises(orc.OracleValidationError):
         orc.spatial_analyzer(packed, 100, 200, [20])
+
+
+# ---------------------------------------------------------------------------
+# latitude/longitude grid tiling (NaiveSpatialEntropyAnalyzer) vs the live-reference fixtures
+# ---------------------------------------------------------------------------
+def _naive_groups():
+    """{'cells/30x30': {...}, 'frames/n_30_w': {...}, 'analyzer/30x30_1': {...}} from 'a/b/field' keys."""
+    npz = load_golden("naive")
+    out = {}
+    for k in npz.files:
+        case, _, field = k.rpartition("/")
+        out.setdefault(case, {})[field] = npz[k]
+    return out
+
+
+def test_naive_tile_index_every_cell():
+    g = _naive_groups()
+    lon_t, lat_t = orc.axis_tables(100, 200)
+    n = 0
+    for name, c in g.items():
+        if not name.startswith("cells/"):
+            continue
+        tw, th = (int(x) for x in name.split("/")[1].split("x"))
+        li, la = orc.naive_tile_index(lon_t[None, :], lat_t[:, None], tw, th)
+        assert np.array_equal(np.broadcast_to(li, c["lon_idx"].shape), c["lon_idx"]), name
+        assert np.array_equal(np.broadcast_to(la, c["lat_idx"].shape), c["lat_idx"]), name
+        n += 1
+    assert n == 6
+
+
+def _naive_frames():
+    return {k.split("/", 1)[1]: v for k, v in _naive_groups().items() if k.startswith("frames/")}
+
+
+@pytest.mark.parametrize("case", ["n_30_w", "n_30_u", "n_45x90_u", "n_10x20_w", "n_360_u", "n_3_u", "n_120x60_one"])
+def test_naive_frame_fixtures(case):
+    c = _naive_frames()[case]
+    tw, th = (int(x) for x in c["tile"])
+    use_w = bool(c["use_w"])
+    res = orc.naive_analyzer(c["packed"], 100, 200, tw, th, use_w)
+    np.testing.assert_allclose(res["entropy"], c["entropy"], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.array_equal(res["lon_idx"], c["keys"][..., 0]) and np.array_equal(res["lat_idx"], c["keys"][..., 1])
+    assert np.array_equal((res["hist0"] > 0).sum(1), c["nkeys"])
+    # literal layer on the first frame
+    px, py, ok = orc.decode(c["packed"][0, :, 1], c["packed"][0, :, 2], 100, 200)
+    lon_t, lat_t = orc.axis_tables(100, 200)
+    pts = {f"u{u:05d}": ((float(lon_t[px[u]]), float(lat_t[py[u]])) if ok[u] else None) for u in range(len(ok))}
+    e, wts, asg = orc.compute_naive_spatial_entropy_literal(pts, th, tw, use_w)
+    np.testing.assert_allclose(e, c["entropy"][0], rtol=1e-13, atol=0, equal_nan=True)
+    assert len(wts) == c["nkeys"][0] and sum(wts.values()) == ok.sum()
+
+
+def test_naive_validation():
+    with pytest.raises(orc.OracleValidationError):
+        orc.compute_naive_spatial_entropy_literal({}, 30, 30, True)
+    with pytest.raises(orc.OracleValidationError):
+        orc.compute_naive_spatial_entropy_literal({"a": (0.0, 0.0)}, 7, 30, True)
+    with pytest.raises(orc.OracleValidationError):
+        orc.compute_naive_spatial_entropy_literal({"a": (0.0, 0.0)}, 30, 7, True)

@@ -6,23 +6,25 @@ in hand-written sm_100a CUDA kernels behind a C ABI (include/vet_b200.h).  Impor
 the package does not need a GPU; computing anything does.
 """
 from .data_types import Point, RadialPoint, Vector, ValidationError, SpatialError
-from .config import (AnalyzerConfig, EntropyConfig, VisualizationConfig, DEFAULT_VIDEO_DIMENSIONS,
+from .config import (AnalyzerConfig, NaiveAnalyzerConfig, EntropyConfig, VisualizationConfig, DEFAULT_VIDEO_DIMENSIONS,
                      DEFAULT_TILE_COUNTS, DEFAULT_OUTPUT_FORMATS)
 from .engine import Engine, SpatialResult, TransitionResult, UnsupportedConfigurationError, get_engine
-from .analyzers import SpatialEntropyAnalyzer, TransitionEntropyAnalyzer
+from .analyzers import SpatialEntropyAnalyzer, TransitionEntropyAnalyzer, NaiveSpatialEntropyAnalyzer
 from . import utilities
 from .utilities import (generate_fibonacci_lattice, normalize_to_pixel, pixel_to_spherical, validate_video_dimensions,
                         vector_angle_distance, find_angular_distances, find_nearest_tile, calculate_tile_weights,
-                        compute_spatial_entropy, compute_transition_entropy)
+                        compute_spatial_entropy, compute_transition_entropy,
+                        find_naive_tile_index, calculate_naive_tile_weights, compute_naive_spatial_entropy)
 
 __version__ = "0.1.0"
 __all__ = [
     "Point", "RadialPoint", "Vector", "ValidationError", "SpatialError",
-    "AnalyzerConfig", "EntropyConfig", "VisualizationConfig",
+    "AnalyzerConfig", "NaiveAnalyzerConfig", "EntropyConfig", "VisualizationConfig",
     "DEFAULT_VIDEO_DIMENSIONS", "DEFAULT_TILE_COUNTS", "DEFAULT_OUTPUT_FORMATS",
     "Engine", "SpatialResult", "TransitionResult", "UnsupportedConfigurationError", "get_engine",
-    "SpatialEntropyAnalyzer", "TransitionEntropyAnalyzer",
+    "SpatialEntropyAnalyzer", "TransitionEntropyAnalyzer", "NaiveSpatialEntropyAnalyzer",
     "generate_fibonacci_lattice", "normalize_to_pixel", "pixel_to_spherical", "validate_video_dimensions",
     "vector_angle_distance", "find_angular_distances", "find_nearest_tile", "calculate_tile_weights",
     "compute_spatial_entropy", "compute_transition_entropy",
+    "find_naive_tile_index", "calculate_naive_tile_weights", "compute_naive_spatial_entropy",
 ]

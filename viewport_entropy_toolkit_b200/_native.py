@@ -39,6 +39,8 @@ class VetConfig(C.Structure):
         ("lon_by_px", C.POINTER(C.c_double)),
         ("lat_by_py", C.POINTER(C.c_double)),
         ("num_tiles", C.POINTER(C.c_int32)),
+        ("naive_tile_width", C.c_int32),
+        ("naive_tile_height", C.c_int32),
     ]
 
 
@@ -65,6 +67,7 @@ SYMBOLS = {
     "vet_analyze": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "vet_spatial_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P]),
     "vet_transition_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, C.c_int]),
+    "vet_naive_points": (C.c_int, [_P, _P, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "vet_poll_flags": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
     "vet_launch_count": (_I64, [_P]),
     "vet_profile_enable": (C.c_int, [_P, C.c_int]),

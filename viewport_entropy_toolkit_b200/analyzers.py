@@ -1,7 +1,8 @@
 """Analyzer facades with the reference's class API, backed by the device engine.
 
-SpatialEntropyAnalyzer   <-> analyzers/spatial_entropy.py    (SA:40-253)
-TransitionEntropyAnalyzer <-> analyzers/transition_entropy.py (TA:40-264)
+SpatialEntropyAnalyzer      <-> analyzers/spatial_entropy.py       (SA:40-253)
+TransitionEntropyAnalyzer   <-> analyzers/transition_entropy.py    (TA:40-264)
+NaiveSpatialEntropyAnalyzer <-> analyzers/naive_spatial_entropy.py (NA:39-241)
 
 `process_directory` / `compute_entropy` / `create_visualization` / `run_analysis`
 keep their names, arguments, return types and error behaviour; the frame loops of
@@ -21,7 +22,8 @@ import pandas as pd
 import torch
 
 from . import _tables
-from .config import AnalyzerConfig, DEFAULT_OUTPUT_FORMATS
+from . import _native as N
+from .config import AnalyzerConfig, NaiveAnalyzerConfig, DEFAULT_OUTPUT_FORMATS
 from .data_types import ValidationError, Vector
 from .engine import Engine, SpatialResult, TransitionResult, get_engine
 from .ingest import load_directory
@@ -39,7 +41,7 @@ class _AnalyzerBase:
         self._device = device
         self._data_cache: Dict = {}
         self._entropy_results: Optional[pd.DataFrame] = None
-        self._fibonacci_vectors = {count: _lattice_vectors(count) for count in self.config.tile_counts}
+        self._fibonacci_vectors = {count: _lattice_vectors(count) for count in getattr(self.config, "tile_counts", [])}
         self._engine: Optional[Engine] = None
 
     @property
@@ -187,4 +189,54 @@ class TransitionEntropyAnalyzer(_AnalyzerBase):
             rows["tile_assignments"].append(
                 {ids[u]: (int(p), int(c)) for u, (p, c) in enumerate(pairs[r]) if p != 0xFFFF})
         self._entropy_results = pd.DataFrame(rows)
+        return self._entropy_results
+
+
+class NaiveSpatialEntropyAnalyzer(_AnalyzerBase):
+    """Per-frame normalised Shannon entropy over a latitude/longitude grid of tile_width x
+    tile_height degree tiles (NA:39-241, compute_naive_spatial_entropy EU:362-453): a sample counts
+    1.0 on the tile "{int((lon+180)/tile_width)}_{int((lat+90)/tile_height)}" (EU:378-381) of its
+    rounded direction; entropy_config.use_weight_distribution only selects the normalisation
+    (EU:443-448).  The frame loop of NA:125-150 runs in the same streaming kernels as the lattice
+    analyzers, the grid being one more cell -> tile table."""
+
+    def __init__(self, config: Optional[NaiveAnalyzerConfig] = None, device: Optional[torch.device] = None):
+        super().__init__(config or NaiveAnalyzerConfig(), device)
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            c = self.config
+            if c.tile_width <= 0 or c.tile_height <= 0:
+                # the reference's -1 placeholders (CFG:104-105) would produce meaningless negative keys
+                raise ValidationError("No tile dimensions provided")
+            self._engine = get_engine(c.video_width, c.video_height, [1], c.entropy_config, self._device,
+                                      naive_tiles=(c.tile_width, c.tile_height))
+        return self._engine
+
+    def tile_key(self, code: int) -> str:
+        """The reference's string key of a grid code (EU:381)."""
+        nlat1 = 180 // self.config.tile_height + 1
+        return f"{code // nlat1}_{code % nlat1}"
+
+    def compute_entropy_packed(self, packed: torch.Tensor, **kw) -> SpatialResult:
+        """packed[F,U,3] on the device -> SpatialResult; hist0[F, codes] holds the users per grid code,
+        assign0[F,U] the grid code of every user (`tile_key` turns a code into the reference's key)."""
+        res = self.engine.spatial(packed, **kw)
+        flags = self.engine.poll_flags()
+        if flags & N.VET_FLAG_OUT_OF_RANGE:
+            raise ValidationError("Normalized coordinates must be between 0 and 1")  # DU:256-257
+        if flags & N.VET_FLAG_EMPTY_FRAME:
+            raise ValidationError("Empty radial points dictionary")  # EU:404-405
+        return res
+
+    def compute_entropy(self) -> pd.DataFrame:
+        if not self._data_cache:
+            raise ValidationError("No data available. Call process_directory first.")
+        res = self.compute_entropy_packed(self._device_packed(), want_hist0=False, want_assign0=False)
+        ent = res.entropy.cpu().numpy()
+        n = len(ent)
+        # NA:136-150 stores None for the weights and assignments of every frame
+        self._entropy_results = pd.DataFrame({"time": list(self._data_cache["times"]), "entropy": list(ent),
+                                              "tile_weights": [None] * n, "tile_assignments": [None] * n})
         return self._entropy_results

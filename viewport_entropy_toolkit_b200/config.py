@@ -1,6 +1,6 @@
 """Configuration dataclasses, field-for-field compatible with the reference
-(AnalyzerConfig CFG:39-82, EntropyConfig EU:20-38, VisualizationConfig VU:32-60,
-defaults CFG:23-36)."""
+(AnalyzerConfig CFG:39-82, NaiveAnalyzerConfig CFG:84-126, EntropyConfig EU:20-38,
+VisualizationConfig VU:32-60, defaults CFG:23-36)."""
 from __future__ import annotations
 
 from dataclasses import dataclass, field
@@ -67,6 +67,30 @@ class AnalyzerConfig:
             raise ValueError("Must specify at least one tile count")
         if any(c <= 0 for c in self.tile_counts):
             raise ValueError("Tile counts must be positive")
+        self.output_dir.mkdir(parents=True, exist_ok=True)
+
+    def get_output_path(self, base_name: str, extension: str) -> Path:
+        return self.output_dir / f"{base_name}{extension}"
+
+
+@dataclass
+class NaiveAnalyzerConfig:
+    """Latitude-longitude grid tiling (CFG:84-126): tile_width / tile_height in degrees.  Same
+    fields, defaults (the -1 placeholders) and checks as the reference; whether the sizes divide
+    360 / 180 is only checked when an entropy is computed (EU:414-417)."""
+    video_width: int = DEFAULT_VIDEO_DIMENSIONS["width"]
+    video_height: int = DEFAULT_VIDEO_DIMENSIONS["height"]
+    output_dir: Path = Path("output")
+    entropy_config: EntropyConfig = field(default_factory=EntropyConfig)
+    visualization_config: VisualizationConfig = field(default_factory=VisualizationConfig)
+    tile_width: int = -1
+    tile_height: int = -1
+
+    def __post_init__(self) -> None:
+        if self.video_width <= 0 or self.video_height <= 0:
+            raise ValueError("Video dimensions must be positive")
+        if not self.tile_height or not self.tile_width:
+            raise ValueError("Must specify both tile_height and tile_width")
         self.output_dir.mkdir(parents=True, exist_ok=True)
 
     def get_output_path(self, base_name: str, extension: str) -> Path:

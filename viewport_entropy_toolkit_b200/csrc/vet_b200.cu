@@ -25,6 +25,7 @@
 #include "vet_vectors.cuh"
 #include "vet_whist.cuh"
 #include "vet_whist_i8.cuh"
+#include "vet_naive.cuh"
 
 namespace {
 
@@ -92,6 +93,11 @@ struct vet_handle {
   int K = 0;
   double fov = 120.0, pf = 2.0, max_d = 0.0;
   int use_weight = 1;
+  // latitude/longitude grid tiling (NaiveSpatialEntropyAnalyzer): one tile set of grid codes
+  bool naive = false;
+  int naive_w = 0, naive_h = 0;
+  int norm_T0 = 0;      // (180/h)*(360/w): the tile count the entropy is normalised by (EU:409)
+  int norm_always = 0;  // config.use_weight_distribution (EU:443)
   int sm_count = 0;
   size_t smem_optin = 0;
   int maxT = 0;
@@ -486,6 +492,26 @@ int build_tile_set(vet_handle* h, TileSet& t) {
   return VET_OK;
 }
 
+// Grid tiling: cell -> code LUT from the per-axis degree tables (find_naive_tile_index, EU:378-381).
+int build_naive_tile_set(vet_handle* h, TileSet& t, const std::vector<double>& lon, const std::vector<double>& lat) {
+  const int nlat1 = 180 / h->naive_h + 1;
+  std::vector<int> li(h->W + 1), la(h->H + 1);
+  for (int px = 0; px <= h->W; ++px) li[px] = (int)((lon[px] + 180) / h->naive_w);
+  for (int py = 0; py <= h->H; ++py) la[py] = (int)((lat[py] + 90) / h->naive_h);
+  t.h_lut.resize(h->C);
+  for (int py = 0; py <= h->H; ++py)
+    for (int px = 0; px <= h->W; ++px) t.h_lut[(size_t)py * (h->W + 1) + px] = (uint16_t)(li[px] * nlat1 + la[py]);
+  std::vector<uint16_t> l16(h->C + 8, 0);
+  std::copy(t.h_lut.begin(), t.h_lut.end(), l16.begin());
+  if (int rc = upload(&t.d_lut, l16.data(), l16.size())) return rc;
+  if (t.T <= 255) {
+    std::vector<uint8_t> l8(h->C + 16, 0);
+    for (int64_t c = 0; c < h->C; ++c) l8[c] = (uint8_t)t.h_lut[c];
+    if (int rc = upload(&t.d_lut8, l8.data(), l8.size())) return rc;
+  }
+  return VET_OK;
+}
+
 void free_tile_set(TileSet& t) {
   cudaFree(t.d_unit);
   cudaFree(t.d_lut);
@@ -739,6 +765,8 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
   e.hist0_out = hist0;
   e.nvalid = h->d_nvalid;
   e.use_weight = 0;
+  e.norm_always = h->norm_always;
+  e.norm_T0 = h->norm_T0;
   e.entropy = entropy;
   e.per_k = per_k;
   e.per_k_stride = per_k_stride;
@@ -839,10 +867,10 @@ bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U) {
   if (U * 255 >= ((int64_t)1 << 31)) return false;  // int32 accumulators: D <= 255 * sum(count plane) <= 255 U
   if ((size_t)vet::kI8SmemBytes + kStaticSmemSlack > h->smem_optin) return false;
   if (impl == 2) return true;
-  // one CTA per (128 frames, 48 tiles): worth it once the grid fills a good part of the SMs
-  int64_t ctas = 0;
-  for (int k = 0; k < h->K; ++k) ctas += ((F + vet::kI8M - 1) / vet::kI8M) * ((h->ts[k].T + vet::kI8TilesPerBlock - 1) / vet::kI8TilesPerBlock);
-  return ctas >= h->sm_count / 2;
+  // A CTA of the tensor-core kernel takes ~70 us whatever the batch (it walks all cells of 128 frames x 48
+  // tiles); the FP64 kernel costs ~0.14 us per frame at 201 tiles.  From a few hundred frames on the
+  // tensor cores win (measured: equal at 450 frames, 0.07 vs 0.50 ms at 3600).
+  return F >= 512;
 }
 
 // Quantised weight slices of tile set t: row nb*240 + s*48 + j of [i8_blocks*240, kp] holds slice s of
@@ -894,8 +922,6 @@ int ensure_planes(vet_handle* h, int64_t F, cudaStream_t st) {
   const int64_t rows = (F + vet::kI8M - 1) / vet::kI8M * vet::kI8M;
   if (rows <= h->plane_rows) return VET_OK;
   VET_CUDA(cudaStreamSynchronize(st));
-  cudaFree(h->d_redo);
-  cudaFree(h->d_trk);
   cudaFree(h->d_planes);
   cudaFree(h->d_dirty);
   cudaFree(h->d_i8flags);
@@ -1026,6 +1052,8 @@ int launch_epilogue(vet_handle* h, int64_t F, int64_t U, double* entropy, double
   a.cpad = h->Cpad;
   a.K = h->K;
   a.use_weight = h->use_weight;
+  a.norm_always = h->norm_always;
+  a.norm_T0 = h->norm_T0;
   for (int k = 0; k < h->K; ++k) {
     a.ts[k].T = h->ts[k].T;
     a.ts[k].lut = h->ts[k].d_lut;
@@ -1059,15 +1087,23 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   *out = nullptr;
   // CFG:62-67
   if (cfg->video_width <= 0 || cfg->video_height <= 0) return fail(VET_ERR_INVALID_ARG, "Video dimensions must be positive");
-  if (cfg->num_tile_counts <= 0 || !cfg->tile_counts) return fail(VET_ERR_INVALID_ARG, "Must specify at least one tile count");
-  for (int k = 0; k < cfg->num_tile_counts; ++k)
-    if (cfg->tile_counts[k] <= 0) return fail(VET_ERR_INVALID_ARG, "Tile counts must be positive");
+  const bool naive = cfg->naive_tile_width != 0 || cfg->naive_tile_height != 0;
+  if (naive) {
+    // EU:410-417 (negative sizes -- the -1 placeholders of CFG:104-105 -- are rejected here)
+    if (cfg->naive_tile_width <= 0 || cfg->naive_tile_height <= 0) return fail(VET_ERR_INVALID_ARG, "No tile dimensions provided");
+    if (180 % cfg->naive_tile_height != 0) return fail(VET_ERR_INVALID_ARG, "Tile height must divide 180!");
+    if (360 % cfg->naive_tile_width != 0) return fail(VET_ERR_INVALID_ARG, "Tile width must divide 360!");
+  } else {
+    if (cfg->num_tile_counts <= 0 || !cfg->tile_counts) return fail(VET_ERR_INVALID_ARG, "Must specify at least one tile count");
+    for (int k = 0; k < cfg->num_tile_counts; ++k)
+      if (cfg->tile_counts[k] <= 0) return fail(VET_ERR_INVALID_ARG, "Tile counts must be positive");
+  }
   // DU:239
   if (cfg->video_width % 2 || cfg->video_height % 2) return fail(VET_ERR_INVALID_ARG, "Video dimensions must be even numbers");
   // EU:35-38
-  if (!(cfg->fov_angle > 0 && cfg->fov_angle <= 360)) return fail(VET_ERR_INVALID_ARG, "FOV angle must be between 0 and 360 degrees");
-  if (!(cfg->power_factor > 0)) return fail(VET_ERR_INVALID_ARG, "Power factor must be positive");
-  if (cfg->num_tile_counts > vet::kMaxTileCounts)
+  if (!naive && !(cfg->fov_angle > 0 && cfg->fov_angle <= 360)) return fail(VET_ERR_INVALID_ARG, "FOV angle must be between 0 and 360 degrees");
+  if (!naive && !(cfg->power_factor > 0)) return fail(VET_ERR_INVALID_ARG, "Power factor must be positive");
+  if (!naive && cfg->num_tile_counts > vet::kMaxTileCounts)
     return fail(VET_ERR_UNSUPPORTED, "at most %d tile counts per handle", vet::kMaxTileCounts);
 
   int ndev = 0;
@@ -1091,10 +1127,17 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   h->H = cfg->video_height;
   h->C = (int64_t)(h->W + 1) * (h->H + 1);
   h->Cpad = (int)((h->C + 3) & ~(int64_t)3);
-  h->K = cfg->num_tile_counts;
-  h->fov = cfg->fov_angle;
-  h->pf = cfg->power_factor;
-  h->use_weight = cfg->use_weight_distribution ? 1 : 0;
+  h->K = naive ? 1 : cfg->num_tile_counts;
+  h->fov = naive ? 120.0 : cfg->fov_angle;
+  h->pf = naive ? 2.0 : cfg->power_factor;
+  h->use_weight = (!naive && cfg->use_weight_distribution) ? 1 : 0;
+  h->naive = naive;
+  if (naive) {
+    h->naive_w = cfg->naive_tile_width;
+    h->naive_h = cfg->naive_tile_height;
+    h->norm_T0 = (180 / h->naive_h) * (360 / h->naive_w);
+    h->norm_always = cfg->use_weight_distribution ? 1 : 0;
+  }
   h->max_d = np_radians(h->fov / 2.0);  // EU:124
   cudaDeviceProp prop;
   VET_CUDA(cudaGetDeviceProperties(&prop, h->device));
@@ -1104,6 +1147,14 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   h->ts.resize(h->K);
   for (int k = 0; k < h->K; ++k) {
     TileSet& t = h->ts[k];
+    if (naive) {
+      t.n = 0;
+      t.T = (360 / h->naive_w + 1) * (180 / h->naive_h + 1);  // grid codes incl. the closed upper edges
+      if (t.T > kMaxT) return fail(VET_ERR_UNSUPPORTED, "%dx%d degree tiles give %d grid codes; at most %d supported", h->naive_w, h->naive_h, t.T, kMaxT);
+      h->maxT = t.T;
+      h->sumT = t.T;
+      continue;
+    }
     t.n = cfg->tile_counts[k];
     t.T = 2 * (t.n / 2) + 1;  // DU:43-45
     if (cfg->num_tiles) {
@@ -1124,6 +1175,7 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   h->direct_only = stream_smem_bytes(h) + kStaticSmemSlack > h->smem_optin ||
                    epilogue_smem_bytes(h) + kStaticSmemSlack > h->smem_optin;
   if (h->C >= ((int64_t)1 << 31)) return fail(VET_ERR_UNSUPPORTED, "video %dx%d has too many cells", h->W, h->H);
+  if (naive && h->direct_only) return fail(VET_ERR_UNSUPPORTED, "video %dx%d is too large for the grid-tiling tables", h->W, h->H);
 
   std::vector<double> lon, lat;
   if (cfg->lon_by_px && cfg->lat_by_py) {
@@ -1175,7 +1227,7 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
     h->launches++;
     VET_CUDA(cudaGetLastError());
     for (int k = 0; k < h->K; ++k)
-      if (int rc = build_tile_set(h, h->ts[k])) return rc;
+      if (int rc = naive ? build_naive_tile_set(h, h->ts[k], lon, lat) : build_tile_set(h, h->ts[k])) return rc;
     if (h->K <= 4 && h->maxT <= 255) {
       std::vector<uint32_t> packed_lut(h->C + 4, 0);
       for (int k = 0; k < h->K; ++k)
@@ -1267,6 +1319,7 @@ extern "C" int64_t vet_num_cells(const vet_handle* h) { return h ? h->C : fail(V
 extern "C" int64_t vet_launch_count(const vet_handle* h) { return h ? h->launches : 0; }
 
 extern "C" int vet_lattice(const vet_handle* h, int k, double* centres_host) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_lattice: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || !centres_host || k < 0 || k >= h->K) return fail(VET_ERR_INVALID_ARG, "bad argument");
   std::memcpy(centres_host, h->ts[k].h_centres.data(), h->ts[k].h_centres.size() * sizeof(double));
   return VET_OK;
@@ -1299,6 +1352,7 @@ extern "C" int vet_decode(vet_handle* h, const void* packed_dev, int dtype, int6
 }
 
 extern "C" int vet_nearest_tile(vet_handle* h, int k, const double* vec_dev, int64_t n, int32_t* idx_dev, void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_nearest_tile: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || k < 0 || k >= h->K || n < 0 || (n > 0 && (!vec_dev || !idx_dev))) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (n == 0) return VET_OK;
   DeviceGuard guard(h->device);
@@ -1315,6 +1369,7 @@ extern "C" int vet_nearest_tile(vet_handle* h, int k, const double* vec_dev, int
 }
 
 extern "C" int vet_tile_weights(vet_handle* h, int k, const double* vec_dev, int64_t n, double* w_dev, void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_tile_weights: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || k < 0 || k >= h->K || n < 0 || (n > 0 && (!vec_dev || !w_dev))) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (n == 0) return VET_OK;
   DeviceGuard guard(h->device);
@@ -1364,6 +1419,7 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
 
 extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
                               double* per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode, void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_transition: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
   if (F <= 1) return VET_OK;  // TA:143-146: the first frame yields no row
@@ -1412,6 +1468,7 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
 extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* sp_entropy_dev,
                            double* sp_per_k_dev, double* hist0_dev, uint16_t* assign0_dev, double* tr_entropy_dev,
                            double* tr_per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode, void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_analyze: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
   if (F == 0) return VET_OK;
@@ -1617,6 +1674,7 @@ int transition_direct(vet_handle* h, const void* packed, int dtype, int64_t F, i
 }  // namespace
 
 extern "C" int vet_angular_distances(vet_handle* h, int k, const double* vec_dev, int64_t n, double* d_dev, void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_angular_distances: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || k < 0 || k >= h->K || n < 0 || (n > 0 && (!vec_dev || !d_dev))) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (n == 0) return VET_OK;
   DeviceGuard guard(h->device);
@@ -1630,6 +1688,7 @@ extern "C" int vet_angular_distances(vet_handle* h, int k, const double* vec_dev
 
 extern "C" int vet_spatial_vectors(vet_handle* h, const double* vec_dev, int64_t F, int64_t U, double* entropy_dev,
                                    double* per_k_dev, double* hist0_dev, uint16_t* assign0_dev, void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_spatial_vectors: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || F < 0 || U < 0) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (F == 0) return VET_OK;
   if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:168-169
@@ -1641,6 +1700,7 @@ extern "C" int vet_spatial_vectors(vet_handle* h, const double* vec_dev, int64_t
 extern "C" int vet_transition_vectors(vet_handle* h, const double* vec_dev, int64_t F, int64_t U, double* entropy_dev,
                                       double* per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode,
                                       void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_transition_vectors: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || F < 0 || U < 0) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
   if (F <= 1) return VET_OK;
@@ -1894,6 +1954,42 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
 
 }  // namespace
 
+extern "C" int vet_naive_points(vet_handle* h, const double* lonlat_dev, int64_t F, int64_t U, int32_t tile_width,
+                                int32_t tile_height, int32_t use_weight_distribution, double* entropy_dev,
+                                int32_t* lon_idx_dev, int32_t* lat_idx_dev, void* stream) {
+  if (!h || F < 0 || U < 0) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  // EU:404-417
+  if (tile_width <= 0 || tile_height <= 0) return fail(VET_ERR_INVALID_ARG, "No tile dimensions provided");
+  if (180 % tile_height != 0) return fail(VET_ERR_INVALID_ARG, "Tile height must divide 180!");
+  if (360 % tile_width != 0) return fail(VET_ERR_INVALID_ARG, "Tile width must divide 360!");
+  if (F == 0) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty radial points dictionary");
+  if (!lonlat_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  DeviceGuard guard(h->device);
+  vet::NaivePointsArgs a{};
+  a.lonlat = lonlat_dev;
+  a.F = F;
+  a.U = U;
+  a.tile_width = tile_width;
+  a.tile_height = tile_height;
+  a.nlat1 = 180 / tile_height + 1;
+  a.ncodes = (360 / tile_width + 1) * a.nlat1;
+  a.num_tiles = (180 / tile_height) * (360 / tile_width);
+  a.norm_always = use_weight_distribution ? 1 : 0;
+  a.entropy = entropy_dev;
+  a.lon_idx = lon_idx_dev;
+  a.lat_idx = lat_idx_dev;
+  a.flags = h->d_flags;
+  const size_t smem = (size_t)a.ncodes * 4;
+  if (smem + kStaticSmemSlack > h->smem_optin)
+    return fail(VET_ERR_UNSUPPORTED, "%dx%d degree tiles give %d grid codes; too many for one frame's shared-memory histogram", tile_width, tile_height, a.ncodes);
+  VET_CUDA(cudaFuncSetAttribute(vet::k_naive_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - kStaticSmemSlack)));
+  h->launches++;
+  vet::k_naive_points<<<(int)std::min<int64_t>(F, (int64_t)h->sm_count * 8), 256, smem, (cudaStream_t)stream>>>(a);
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
 extern "C" int vet_poll_flags(vet_handle* h, void* stream, uint32_t* flags) {
   if (!h || !flags) return fail(VET_ERR_INVALID_ARG, "null argument");
   DeviceGuard guard(h->device);
@@ -2074,6 +2170,7 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
 extern "C" int vet_transition_host(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U,
                                    double* entropy_host, double* per_k_host, int32_t* prev_count0_host,
                                    uint16_t* pairs0_host, int mode) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_transition_host: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (F <= 1) return VET_OK;
   if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");

@@ -120,8 +120,10 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 //   H = -sum_{t: hist>0} p log2 p,  p = hist/total
 //   n = T if (weighted or total > T) else total;  Hn = H / (-n * (1/n) * log2(1/n))
 // Called by all threads of the block; hist in shared memory.
+// norm_T: the tile count of the normalisation when it differs from the histogram length (naive
+// lat/lon tiling: codes of the closed upper edges exist beyond num_tiles, EU:409,443-448); 0 = T.
 __device__ __forceinline__ double normalized_entropy(const double* hist, int T, double total, bool by_tiles_always,
-                                                     double* red) {
+                                                     double* red, int norm_T = 0) {
   double acc = 0.0;
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const double w = hist[t];
@@ -131,7 +133,8 @@ __device__ __forceinline__ double normalized_entropy(const double* hist, int T, 
     }
   }
   const double Hs = block_sum(acc, red);
-  const double n = (by_tiles_always || total > (double)T) ? (double)T : total;
+  const double nt = (double)(norm_T > 0 ? norm_T : T);
+  const double n = (by_tiles_always || total > nt) ? nt : total;
   const double mp = 1.0 / n;
   const double mx = -n * mp * log2(mp);
   return Hs / mx;

@@ -97,6 +97,8 @@ struct EpilogueArgs {
   int cpad;
   int K;
   int use_weight;
+  int norm_always;  // normalise by the tile count even for few users (naive tiling with use_weight_distribution)
+  int norm_T0;      // tile count of the normalisation for tile set 0 when it differs from its T (naive tiling), else 0
   TileSetDev ts[kMaxTileCounts];
   double* entropy;  // [F]
   double* per_k;    // [K, per_k_stride] or null
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(512, 1) k_epilogue(EpilogueArgs a, int maxT) {
         for (int t = threadIdx.x; t < T; t += blockDim.x) part += s_hist[t];
         total = block_sum(part, s_red);
       }
-      double e = normalized_entropy(s_hist, T, total, a.use_weight != 0, s_red);
+      double e = normalized_entropy(s_hist, T, total, a.use_weight != 0 || a.norm_always != 0, s_red, k == 0 ? a.norm_T0 : 0);
       if (n_valid == 0.0) e = __longlong_as_double(0x7ff8000000000000LL);
       if (threadIdx.x == 0 && a.per_k) a.per_k[k * a.per_k_stride + f] = e;
       if (k == 0 && a.hist0)

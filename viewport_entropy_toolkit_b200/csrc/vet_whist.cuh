@@ -269,6 +269,8 @@ struct EntropyRowsArgs {
   double* hist0_out;                   // [F,T_0] (ihist mode only): tile_counts[0] histogram as float64, or null
   const uint32_t* nvalid;              // [F] present users per frame
   int use_weight;
+  int norm_always;   // naive tiling with use_weight_distribution: always normalise by the tile count
+  int norm_T0;       // naive tiling: tile count of the normalisation for tile set 0 (0 = its T)
   double* entropy;   // [F]
   double* per_k;     // [K, stride] or null
   int64_t per_k_stride;
@@ -300,7 +302,8 @@ __global__ void k_entropy_rows(EntropyRowsArgs a) {
         }
       }
       const double Hs = warp_sum(acc);
-      const double nn = (a.use_weight || total > (double)T) ? (double)T : total;
+      const double nt = (double)((k == 0 && a.norm_T0 > 0) ? a.norm_T0 : T);
+      const double nn = (a.use_weight || a.norm_always || total > nt) ? nt : total;
       const double mp = 1.0 / nn;
       const double mx = -nn * mp * log2(mp);
       double e = Hs / mx;

@@ -66,11 +66,15 @@ class Engine:
 
     def __init__(self, video_width: int, video_height: int, tile_counts: Sequence[int],
                  entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None,
-                 native_tables: bool = False, centres: Optional[Sequence[np.ndarray]] = None):
+                 native_tables: bool = False, centres: Optional[Sequence[np.ndarray]] = None,
+                 naive_tiles: Optional[Tuple[int, int]] = None):
         """native_tables=True lets the library derive the lattice and axis tables itself
         (libm) instead of receiving the numpy-made ones; used by tests to show both agree.
         centres: optional list of [T_k,3] arrays of ARBITRARY tile centres (the reference's
-        free functions take any List[Vector]); tile_counts is then only a label."""
+        free functions take any List[Vector]); tile_counts is then only a label.
+        naive_tiles=(tile_width, tile_height) in degrees selects the latitude/longitude grid tiling
+        of NaiveSpatialEntropyAnalyzer (NA:39-241) instead of the lattice: one tile set whose tile
+        ids are grid codes lon_idx * (180/tile_height + 1) + lat_idx; tile_counts is ignored."""
         self._h = None
         lib = N.load_library()
         if not torch.cuda.is_available():
@@ -81,7 +85,8 @@ class Engine:
             raise RuntimeError("viewport_entropy_toolkit_b200 needs a CUDA device; there is no CPU path")
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.video_width, self.video_height = int(video_width), int(video_height)
-        self.tile_counts = [int(c) for c in tile_counts]
+        self.naive_tiles = None if naive_tiles is None else (int(naive_tiles[0]), int(naive_tiles[1]))
+        self.tile_counts = [int(c) for c in tile_counts] if naive_tiles is None else [1]
         self.entropy_config = ec
         # DU:236-240 (the reference validates dims when the first sample is converted)
         if self.video_width <= 0 or self.video_height <= 0:
@@ -108,7 +113,9 @@ class Engine:
             centres=None if native_tables else cptrs,
             lon_by_px=None if native_tables else lon.ctypes.data_as(C.POINTER(C.c_double)),
             lat_by_py=None if native_tables else lat.ctypes.data_as(C.POINTER(C.c_double)),
-            num_tiles=ntiles)
+            num_tiles=ntiles,
+            naive_tile_width=self.naive_tiles[0] if self.naive_tiles else 0,
+            naive_tile_height=self.naive_tiles[1] if self.naive_tiles else 0)
         h = C.c_void_p()
         _check(lib.vet_create(C.byref(h), C.byref(cfg)))
         self._h = h
@@ -261,6 +268,23 @@ class Engine:
                                                 _ptr(out.prev_count0), _ptr(out.pairs0), m, self._stream()))
         return out
 
+    def naive_points(self, lonlat: torch.Tensor, tile_width: int, tile_height: int, use_weight_distribution: bool,
+                     want_indices: bool = True):
+        """compute_naive_spatial_entropy (EU:362-453) on lonlat[F,U,2] float64 degrees (NaN = absent):
+        -> (entropy[F], lon_idx[F,U] int32, lat_idx[F,U] int32); the reference's tile key of a point is
+        f"{lon_idx}_{lat_idx}" (EU:381)."""
+        v = lonlat.to(device=self.device, dtype=torch.float64).contiguous()
+        if v.dim() != 3 or v.shape[-1] != 2:
+            raise ValueError("lonlat must be [F, U, 2]")
+        F, U = int(v.shape[0]), int(v.shape[1])
+        ent = torch.empty(F, dtype=torch.float64, device=self.device)
+        li = torch.empty((F, U), dtype=torch.int32, device=self.device) if want_indices else None
+        la = torch.empty((F, U), dtype=torch.int32, device=self.device) if want_indices else None
+        _check(self._lib.vet_naive_points(self._h, v.data_ptr(), F, U, int(tile_width), int(tile_height),
+                                          int(bool(use_weight_distribution)), ent.data_ptr(), _ptr(li), _ptr(la),
+                                          self._stream()))
+        return ent, li, la
+
     # -- stages 1-3 fused -----------------------------------------------------------
     def spatial(self, packed: torch.Tensor, want_per_k: bool = True, want_hist0: bool = True,
                 want_assign0: bool = True, out: Optional[SpatialResult] = None) -> SpatialResult:
@@ -410,7 +434,8 @@ _ENGINES: Dict[tuple, Engine] = {}
 
 def get_engine(video_width: int, video_height: int, tile_counts: Sequence[int],
                entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None,
-               centres: Optional[Sequence[np.ndarray]] = None) -> Engine:
+               centres: Optional[Sequence[np.ndarray]] = None,
+               naive_tiles: Optional[Tuple[int, int]] = None) -> Engine:
     """Engine cache keyed by (device, configuration): building the tables costs a
     few milliseconds, analyzers and the functional API share them."""
     ec = entropy_config or EntropyConfig()
@@ -420,12 +445,14 @@ def get_engine(video_width: int, video_height: int, tile_counts: Sequence[int],
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     ckey = None if centres is None else tuple(np.ascontiguousarray(c, dtype=np.float64).tobytes() for c in centres)
     key = (idx, int(video_width), int(video_height), tuple(int(c) for c in tile_counts), float(ec.fov_angle),
-           bool(ec.use_weight_distribution), float(ec.power_factor), ckey)
+           bool(ec.use_weight_distribution), float(ec.power_factor), ckey,
+           None if naive_tiles is None else (int(naive_tiles[0]), int(naive_tiles[1])))
     eng = _ENGINES.get(key)
     if eng is None:
         if len(_ENGINES) >= 32:  # bound the cache (functional calls with ad-hoc centre lists)
             _ENGINES.pop(next(iter(_ENGINES))).close()
-        eng = Engine(video_width, video_height, tile_counts, ec, torch.device("cuda", idx), centres=centres)
+        eng = Engine(video_width, video_height, tile_counts, ec, torch.device("cuda", idx), centres=centres,
+                     naive_tiles=naive_tiles)
         _ENGINES[key] = eng
     return eng
 

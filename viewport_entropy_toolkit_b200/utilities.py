@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _tables
-from .config import EntropyConfig
+from .config import EntropyConfig, DEFAULT_VIDEO_DIMENSIONS
 from .data_types import Point, RadialPoint, ValidationError, Vector
 from .engine import get_engine
 
@@ -141,3 +141,47 @@ def compute_transition_entropy(prior_vector_dict: dict, current_vector_dict: dic
     pairs = res.pairs0[0].cpu().numpy()
     weights = {tile_centers[i]: int(counts[i]) for i in np.flatnonzero(counts)}
     return np.float64(res.entropy[0].item()), weights, {k: (int(p), int(c)) for k, (p, c) in zip(ids, pairs)}
+
+
+# ---- latitude/longitude grid tiling (EU:335-453) ------------------------------------------------
+def find_naive_tile_index(point: RadialPoint, tile_height: float, tile_width: float) -> str:
+    """EU:360-381: "{lon index}_{lat index}" of the grid tile a point sits in (host arithmetic: one
+    division per axis, identical to the reference's)."""
+    return f"{int((point.lon + 180) / tile_width)}_{int((point.lat + 90) / tile_height)}"
+
+
+def calculate_naive_tile_weights(point: RadialPoint, tile_height: float, tile_width: float,
+                                 config: EntropyConfig) -> Dict[str, float]:
+    """EU:335-358: weight 1.0 on the point's own tile."""
+    return {find_naive_tile_index(point, tile_height, tile_width): 1.0}
+
+
+def compute_naive_spatial_entropy(points_dict: Dict[str, Optional[RadialPoint]], tile_height: int, tile_width: int,
+                                  config: EntropyConfig) -> Tuple[float, Dict[str, float], Dict[str, str]]:
+    """EU:362-453: (normalised entropy, {tile key: users}, {identifier: tile key}) on the device."""
+    if not points_dict:
+        raise ValidationError("Empty radial points dictionary")
+    if not tile_height or not tile_width:
+        raise ValidationError("No tile dimensions provided")
+    if 180 % tile_height != 0:
+        raise ValidationError("Tile height must divide 180!")
+    if 360 % tile_width != 0:
+        raise ValidationError("Tile width must divide 360!")
+    if tile_height < 0 or tile_width < 0:
+        raise ValidationError("No tile dimensions provided")  # the reference would index negative tiles
+    ids = [k for k, v in points_dict.items() if v is not None]
+    num_tiles = int(180.0 / tile_height) * int(360.0 / tile_width)
+    if not ids:  # EU:437-448 on an empty histogram
+        if config.use_weight_distribution:
+            return np.float64(0.0) / (-num_tiles * (1.0 / num_tiles) * np.log2(1.0 / num_tiles)), {}, {}
+        raise ZeroDivisionError("float division by zero")
+    eng = get_engine(DEFAULT_VIDEO_DIMENSIONS["width"], DEFAULT_VIDEO_DIMENSIONS["height"], [1], config,
+                     naive_tiles=(int(tile_width), int(tile_height)))
+    lonlat = torch.tensor([[[points_dict[k].lon, points_dict[k].lat] for k in ids]], dtype=torch.float64)
+    ent, li, la = eng.naive_points(lonlat, int(tile_width), int(tile_height), config.use_weight_distribution)
+    eng.poll_flags()
+    keys = [f"{int(a)}_{int(b)}" for a, b in zip(li[0].cpu().numpy(), la[0].cpu().numpy())]
+    weights: Dict[str, float] = {}
+    for key in keys:
+        weights[key] = weights.get(key, 0.0) + 1.0
+    return np.float64(ent[0].item()), weights, dict(zip(ids, keys))
