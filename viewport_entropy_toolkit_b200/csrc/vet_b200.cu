@@ -1441,16 +1441,19 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
   for (int64_t f0 = 0; f0 < F - 1; f0 += fb - 1) {
     const int64_t nf = std::min(fb, F - f0);
     const char* in = (const char*)packed_dev + (size_t)f0 * U * 3 * esz;
-    if (int rc = launch_stream(h, in, dtype, nf, U, nullptr, true, st)) return rc;
+    // one tile count: the streaming kernel writes the tile ids themselves (its own LUT lookup) into the
+    // scratch and the transition kernels take them through the identity table -- no lookups per pair
+    const bool tiles_direct = h->K == 1;
+    if (int rc = launch_stream(h, in, dtype, nf, U, tiles_direct ? (uint16_t*)h->d_cells : nullptr, !tiles_direct, st)) return rc;
     vet::TransitionArgs a{};
-    a.cell16 = csz == 2 ? (const uint16_t*)h->d_cells : nullptr;
-    a.cell32 = csz == 4 ? (const int32_t*)h->d_cells : nullptr;
+    a.cell16 = (csz == 2 || tiles_direct) ? (const uint16_t*)h->d_cells : nullptr;
+    a.cell32 = (csz == 4 && !tiles_direct) ? (const int32_t*)h->d_cells : nullptr;
     a.F = nf;
     a.U = U;
     a.K = h->K;
     for (int k = 0; k < h->K; ++k) {
       a.T[k] = h->ts[k].T;
-      a.lut[k] = h->ts[k].d_lut;
+      a.lut[k] = tiles_direct ? h->d_identity : h->ts[k].d_lut;
     }
     a.entropy = entropy_dev + f0;
     a.per_k = per_k_dev ? per_k_dev + f0 : nullptr;
@@ -1497,20 +1500,21 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
     const int64_t nf = std::min(fb, F - f0);
     const char* in = (const char*)packed_dev + (size_t)f0 * U * 3 * esz;
     uint16_t* asg = assign ? assign + f0 * U : (uint16_t*)h->d_vscratch[0];
-    if (int rc = launch_stream(h, in, dtype, nf, U, asg, true, st)) return rc;
+    const bool tiles_direct = h->K == 1;  // the assignments double as the transition stage's input (identity table)
+    if (int rc = launch_stream(h, in, dtype, nf, U, asg, !tiles_direct, st)) return rc;
     if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
                                  hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
       return rc;
     if (nf >= 2) {
       vet::TransitionArgs a{};
-      a.cell16 = csz == 2 ? (const uint16_t*)h->d_cells : nullptr;
-      a.cell32 = csz == 4 ? (const int32_t*)h->d_cells : nullptr;
+      a.cell16 = tiles_direct ? asg : (csz == 2 ? (const uint16_t*)h->d_cells : nullptr);
+      a.cell32 = (csz == 4 && !tiles_direct) ? (const int32_t*)h->d_cells : nullptr;
       a.F = nf;
       a.U = U;
       a.K = h->K;
       for (int k = 0; k < h->K; ++k) {
         a.T[k] = h->ts[k].T;
-        a.lut[k] = h->ts[k].d_lut;
+        a.lut[k] = tiles_direct ? h->d_identity : h->ts[k].d_lut;
       }
       a.entropy = tr_entropy_dev + f0;
       a.per_k = tr_per_k_dev ? tr_per_k_dev + f0 : nullptr;
@@ -1833,7 +1837,8 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
           l8 = h->ts[j].d_lut8;
           is_cell_lut = true;
         }
-      if (!is_cell_lut) {
+      const bool identity = a.lut[k] == h->d_identity;  // the input rows hold tile ids already
+      if (!is_cell_lut && !identity) {
         ok = false;
         break;
       }
@@ -1853,7 +1858,11 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
       }
       pl.lut_off = (pl.tab_off + tab + 15) & ~(size_t)15;
       const size_t lut_bytes = (((size_t)h->C * (l8 ? 1 : 2)) + 15) & ~(size_t)15;
-      if (pl.lut_off + lut_bytes <= budget) {
+      if (identity) {
+        pl.lw = vet::kLutIdentity;
+        pl.lut = nullptr;
+        pl.smem = pl.lut_off;
+      } else if (pl.lut_off + lut_bytes <= budget) {
         pl.lw = l8 ? vet::kLutS8 : vet::kLutS16;
         pl.lut = l8 ? (const void*)l8 : (const void*)a.lut[k];
         pl.smem = pl.lut_off + lut_bytes;
@@ -1916,10 +1925,12 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         if (pl.mode == vet::kT3Dense) {
           if (pl.lw == vet::kLutS8) VET_T3(vet::kT3Dense, vet::kLutS8);
           else if (pl.lw == vet::kLutS16) VET_T3(vet::kT3Dense, vet::kLutS16);
+          else if (pl.lw == vet::kLutIdentity) VET_T3(vet::kT3Dense, vet::kLutIdentity);
           else VET_T3(vet::kT3Dense, vet::kLutG16);
         } else {
           if (pl.lw == vet::kLutS8) VET_T3(vet::kT3Hash, vet::kLutS8);
           else if (pl.lw == vet::kLutS16) VET_T3(vet::kT3Hash, vet::kLutS16);
+          else if (pl.lw == vet::kLutIdentity) VET_T3(vet::kT3Hash, vet::kLutIdentity);
           else VET_T3(vet::kT3Hash, vet::kLutG16);
         }
 #undef VET_T3

@@ -35,10 +35,10 @@ constexpr int kT3Probes = 128;
 constexpr int kT3TileBytes = 2 * 8 + 6 * 4;  // per-tile arrays below
 
 enum : int { kT3Dense = 0, kT3Hash = 1 };
-enum : int { kLutS8 = 0, kLutS16 = 1, kLutG16 = 2 };
+enum : int { kLutS8 = 0, kLutS16 = 1, kLutG16 = 2, kLutIdentity = 3 };  // kLutIdentity: the input already holds tile ids
 
 struct Transition3Args {
-  const uint16_t* cell16;  // [F,U] cell ids, 0xFFFF = missing
+  const uint16_t* cell16;  // [F,U] cell ids (or tile ids with kLutIdentity), 0xFFFF = missing
   int64_t F;
   uint32_t U;
   int T;
@@ -58,6 +58,7 @@ template <int LW>
 struct Lut3 {
   const void* p;
   __device__ __forceinline__ uint32_t operator()(uint32_t cell) const {
+    if (LW == kLutIdentity) return cell;
     if (LW == kLutS8) return static_cast<const uint8_t*>(p)[cell];
     if (LW == kLutS16) return static_cast<const uint16_t*>(p)[cell];
     return __ldg(static_cast<const uint16_t*>(p) + cell);
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     for (uint32_t i = tid; i < words; i += kT3Threads) s_tab[i] = kEmpty;
   }
   Lut3<LW> lut{a.lut_src};
-  if (LW != kLutG16) {
+  if (LW == kLutS8 || LW == kLutS16) {
     const int bytes = a.C * (LW == kLutS8 ? 1 : 2);
     const uint4* __restrict__ src = static_cast<const uint4*>(a.lut_src);
     uint4* dst = reinterpret_cast<uint4*>(smem_raw + a.lut_off);
