@@ -226,8 +226,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout (one JSON line only)
+        # keep NCCL's version banner and warnings out of stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     peaks = {}
@@ -397,8 +397,41 @@ def main():
             rate = w2["F"] * w2["U"] / (ms2 * 1e-3)
             extra[name] = {"workload": w2["desc"], "ms_per_step": ms2, "value": rate, "unit": UNIT,
                            "whole_step_frac": ALG_BYTES_PER_SAMPLE * rate / 1e9 / peak_gbs}
+            if name == "c5shard":
+                # configs[4] asks for weighted spatial AND transition entropy: both analyzers in one pass (vet_analyze)
+                def both():
+                    return e2.analyze(p2, want_per_k=False, want_assign0=True, want_pairs0=False)
+                both()
+                torch.cuda.synchronize()
+                a0.record()
+                for _ in range(3):
+                    both()
+                a1.record()
+                torch.cuda.synchronize()
+                ms3 = a0.elapsed_time(a1) / 3
+                extra["c5shard_analyze"] = {"workload": w2["desc"] + " + transition entropy, one pass over the input",
+                                            "ms_per_step": ms3, "value": w2["F"] * w2["U"] / (ms3 * 1e-3), "unit": UNIT,
+                                            "whole_step_frac": ALG_BYTES_PER_SAMPLE * w2["F"] * w2["U"] / (ms3 * 1e-3) / 1e9 / peak_gbs}
             del p2, o2
             torch.cuda.empty_cache()
+        # configs[3]: transition-entropy matrices for tile_counts=[200,500,1000] on the headline tensor shape
+        p4 = synth_on_device(torch, 3600, 100_000, 20260000 + 4000, device)
+        e4 = get_engine(100, 200, [200, 500, 1000], EntropyConfig(use_weight_distribution=False), device)
+
+        def trans():
+            return e4.transition(p4, want_pairs0=False, want_per_k=False)
+        trans()
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(3):
+            trans()
+        a1.record()
+        torch.cuda.synchronize()
+        ms4 = a0.elapsed_time(a1) / 3
+        extra["c4"] = {"workload": "configs[3]: synthetic 100k users x 3600 frames, tile_counts=[200,500,1000], transition entropy",
+                       "ms_per_step": ms4, "value": 3599 * 100_000 / (ms4 * 1e-3), "unit": "user frame pairs/s (each under 3 tile counts)"}
+        del p4
+        torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
