@@ -1,5 +1,6 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
 every kernel family once, sizes of a few thousand samples."""
+import os
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -18,12 +19,25 @@ def packed(F, U, dtype=np.float32):
 
 e = Engine(100, 200, [200, 20], EntropyConfig(fov_angle=90.0))
 r = e.spatial(packed(70, 2501))                     # k_stream_tma (odd U: unaligned tile heads) + k_whist + k_entropy_rows
-t = e.transition(packed(4, 9000))                   # k_stream_tma<cells> + k_transition2 (dense)
+t = e.transition(packed(4, 9000))                   # k_stream_tma<cells> + k_transition3 (dense) per tile count + k_mean_rows
+os.environ["VET_WHIST_IMPL"] = "i8"
+hot = packed(140, 2504)
+hot[:, :600, 1:] = 0.5                              # 600 users in one cell: second count plane
+r5 = e.spatial(hot)                                 # k_stream_tma (byte planes) + k_whist_i8 (TMA, tcgen05, TMEM), both passes
+r6 = e.spatial(packed(3, 70001))                    # frames in chunks: k_cnt_planes + k_whist_i8
+del os.environ["VET_WHIST_IMPL"]
+os.environ["VET_TRANSITION_IMPL"] = "v2"
+t4 = e.transition(packed(4, 9000))                  # k_transition2 (dense)
+del os.environ["VET_TRANSITION_IMPL"]
+e.close()
+e = Engine(100, 200, [1], EntropyConfig(), naive_tiles=(30, 30))
+r7 = e.spatial(packed(5, 999))                      # grid tiling: k_stream_tiles with the grid-code table
+n1 = e.naive_points(torch.rand((3, 500, 2), dtype=torch.float64, device="cuda") * 90.0, 30, 30, True)   # k_naive_points
 e.close()
 e = Engine(100, 200, [20, 50, 1000], EntropyConfig(use_weight_distribution=False))
 r2 = e.spatial(packed(9, 3001, np.float64))         # k_stream_tiles (direct unweighted) + k_entropy_rows
 r3 = e.spatial(packed(3, 90001))                    # cells path: k_stream_tma + k_epilogue, several chunks per frame
-t2 = e.transition(packed(3, 20000))                 # k_transition2 hash + overflow -> global fallback
+t2 = e.transition(packed(3, 20000))                 # k_transition3 hash, overflow -> rows redone by k_transition2 (global tables)
 t3 = e.transition(packed(5, 700), mode="textbook")  # k_transition (shared-memory table)
 e.close()
 e = Engine(200, 400, [20], EntropyConfig())

@@ -133,6 +133,7 @@ struct vet_handle {
   uint32_t* d_i8flags = nullptr; // [2][plane_rows/128]
   CUtensorMap tm_cnt;
   bool planes_from_stream = false;  // the last launch_stream wrote the planes of its batch itself
+  bool i8_attr_set = false;
   uint32_t* d_redo = nullptr;   // [rows] frame pairs the two-pass transition kernel left to k_transition2
   size_t redo_bytes = 0;
   double* d_trk = nullptr;      // [K, rows] per-tile-count transition entropies when the caller wants none
@@ -968,10 +969,9 @@ int launch_cnt_planes(vet_handle* h, int64_t F, const uint32_t* cnt, cudaStream_
 int launch_whist_i8(vet_handle* h, int k, int64_t F, double* hist, cudaStream_t st) {
   TileSet& t = h->ts[k];
   if (int rc = build_i8_tables(h, t)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->i8_attr_set) {  // function attributes are per device: once per handle
     VET_CUDA(cudaFuncSetAttribute(vet::k_whist_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, vet::kI8SmemBytes));
-    attr_set = true;
+    h->i8_attr_set = true;
   }
   const int fblocks = (int)((F + vet::kI8M - 1) / vet::kI8M);
   vet::WhistI8Args a{};
