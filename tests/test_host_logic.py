@@ -101,6 +101,18 @@ def test_config_and_type_validation(pkg, tmp_path):
     assert pkg.Vector.from_spherical(-79.2, -11.7) == pkg.Vector(0.183488, -0.961878, -0.202787)
     assert pkg.RadialPoint(190 - 360, 0).normalize_coordinates().lon == -170
     assert issubclass(pkg.ValidationError, pkg.SpatialError)
+    # NaiveAnalyzerConfig (CFG:84-126): -1 placeholders accepted at construction, zero rejected
+    ncfg = pkg.NaiveAnalyzerConfig(output_dir=tmp_path / "naive")
+    assert (ncfg.tile_width, ncfg.tile_height) == (-1, -1) and (tmp_path / "naive").is_dir()
+    with pytest.raises(ValueError):
+        pkg.NaiveAnalyzerConfig(tile_width=30, tile_height=0, output_dir=tmp_path)
+    with pytest.raises(ValueError):
+        pkg.NaiveAnalyzerConfig(video_height=-2, tile_width=30, tile_height=30, output_dir=tmp_path)
+    # find_naive_tile_index / calculate_naive_tile_weights are host arithmetic (EU:335-381)
+    pt = pkg.RadialPoint(-79.2, -11.7)
+    assert pkg.find_naive_tile_index(pt, 30, 30) == "3_2"
+    assert pkg.find_naive_tile_index(pkg.RadialPoint(180.0, 90.0), 30, 45) == "8_6"   # (point, tile_height, tile_width)
+    assert pkg.calculate_naive_tile_weights(pt, 30, 30, pkg.EntropyConfig()) == {"3_2": 1.0}
 
 
 def test_host_tables_equal_oracle_and_reference(pkg):
