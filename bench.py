@@ -214,6 +214,13 @@ def main():
         run_reference_arm(args, wl, rank)
         return
 
+    # Contract: ONE JSON line on stdout.  Native libraries (NCCL's version banner, ...) write to file
+    # descriptor 1 behind Python's back, so stdout is pointed at stderr for the duration of the run and the
+    # JSON line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
@@ -226,7 +233,10 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep NCCL's version banner and warnings out of stdout (one JSON line only)
+        # keep NCCL's version banner and warnings out of stdout (one JSON line only): the banner is what
+        # NCCL_DEBUG=VERSION (set on some boxes) and WARN print; other levels are redirected to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
@@ -440,7 +450,8 @@ def main():
                "sample": f"24 frames x 128 users of the workload through the oracle's literal layer, one core ({dt1:.1f} s)"}
 
     if rank == 0:
-        print(json.dumps({
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -451,7 +462,7 @@ def main():
                        "transition": bool(args.transition), "sharding": "frames (one shard of the workload shape per rank); per-frame entropy all-gathered every step" + (" together with the hist0 rows" if args.gather_hist0 else " (hist0 and assign0 stay on the owning rank)") + ", asynchronously (overlapping the next step), all waited for inside the timed region"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "extra": extra,
-        }))
+        }) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
