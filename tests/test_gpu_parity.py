@@ -810,3 +810,75 @@ def test_naive_analyzer_end_to_end_and_errors(vet, tmp_path):
     empty.load_packed(p)
     with pytest.raises(vet.ValidationError, match="Empty radial points"):
         empty.compute_entropy()
+
+
+# ---------------------------------------------------------------------------------
+# full-size runs of the remaining BASELINE configs: size-independent properties + oracle on sampled rows
+# ---------------------------------------------------------------------------------
+def _cells_of(frame):
+    """DU:261 in fp64 (exact for float32 inputs) with plain torch ops: [U] packed rows -> cell ids"""
+    return (frame[:, 2].double() * H0).to(torch.int64) * (W0 + 1) + (frame[:, 1].double() * W0).to(torch.int64)
+
+
+def test_full_size_properties_configs3(vet):
+    """BASELINE configs[3] at FULL size (100k users x 3600 frames, tile_counts=[200,500,1000], transition entropy):
+    users per previous tile sum to U, pairs equal the exhaustive LUT of the two frames' cells, the entropy is the
+    mean over tile counts, reruns are bit-identical, and sampled rows match the oracle's closed form for every
+    tile count (dense table for 201 tiles, shared-memory hash + diagonal for 501 and 1001)."""
+    import bench
+    F, U, tcs = 3600, 100_000, [200, 500, 1000]
+    p = bench.synth_on_device(torch, F, U, 20260000 + 4000, torch.device("cuda"))
+    e = engine(vet, tcs, use_w=False)
+    a = e.transition(p)
+    assert e.poll_flags() == 0
+    b = e.transition(p, want_pairs0=False)
+    assert torch.equal(a.entropy, b.entropy) and torch.equal(a.per_k, b.per_k) and torch.equal(a.prev_count0, b.prev_count0)
+    del b
+    assert torch.equal(a.prev_count0.sum(1), torch.full((F - 1,), U, dtype=torch.int64, device="cuda"))
+    ent = a.entropy.cpu().numpy()
+    assert np.isfinite(ent).all() and (ent >= 0).all()
+    np.testing.assert_allclose(ent, a.per_k.cpu().numpy().sum(0) / len(tcs), rtol=1e-15)
+    luts = [torch.from_numpy(e.cell_lut(k).astype(np.int64)).cuda().ravel() for k in range(len(tcs))]
+    for r in (0, 1799, F - 2):
+        cp, cc = _cells_of(p[r]), _cells_of(p[r + 1])
+        assert torch.equal(a.pairs0[r, :, 0].long(), luts[0][cp]) and torch.equal(a.pairs0[r, :, 1].long(), luts[0][cc])
+        for k, n in enumerate(tcs):
+            T = e.num_tiles[k]
+            e_ref, m_ref = orc.transition_entropy(luts[k][cp].cpu().numpy(), luts[k][cc].cpu().numpy(), T)
+            np.testing.assert_allclose(float(a.per_k[k, r]), e_ref, rtol=RTOL, atol=ATOL)
+            if k == 0:
+                assert np.array_equal(a.prev_count0[r].cpu().numpy(), m_ref)
+    e.close()
+
+
+def test_full_size_properties_configs4_shard(vet):
+    """One rank's frames of BASELINE configs[4] at full WIDTH (1M users per frame, 201 tiles, fov=90, weighted
+    spatial + transition entropy in one pass): analyze() equals the separate stages bit for bit, the weighted
+    histogram of a whole frame matches the dense per-user weight kernel, transition rows match the oracle."""
+    import bench
+    F, U = 24, 1_000_000
+    p = bench.synth_on_device(torch, F, U, 20260000 + 5000, torch.device("cuda"), chunk=8)
+    p[3, ::1000, 1] = float("nan")                       # some users missing in one frame
+    e = engine(vet, [200], fov=90.0)
+    sp, tr = e.analyze(p)
+    assert e.poll_flags() == 0
+    sp2 = e.spatial(p)
+    tr2 = e.transition(p)
+    assert torch.equal(sp.entropy, sp2.entropy) and torch.equal(sp.hist0, sp2.hist0) and torch.equal(sp.assign0, sp2.assign0)
+    assert torch.equal(tr.entropy, tr2.entropy) and torch.equal(tr.prev_count0, tr2.prev_count0) and torch.equal(tr.pairs0, tr2.pairs0)
+    lut = torch.from_numpy(e.cell_lut(0).astype(np.int64)).cuda().ravel()
+    vec, _ = e.decode(p[:1])
+    dense = torch.zeros(201, dtype=torch.float64, device="cuda")
+    for u0 in range(0, U, 100_000):
+        dense += e.tile_weights(vec[0, u0:u0 + 100_000], 0).sum(0)
+    np.testing.assert_allclose(sp.hist0[0].cpu().numpy(), dense.cpu().numpy(), rtol=RTOL, atol=ATOL)
+    for r in (0, 3, F - 2):                               # row 3: current frame has missing users
+        okp = ~(torch.isnan(p[r, :, 1]) | torch.isnan(p[r, :, 2]))
+        okc = ~(torch.isnan(p[r + 1, :, 1]) | torch.isnan(p[r + 1, :, 2]))
+        both = okp & okc
+        cp, cc = _cells_of(torch.nan_to_num(p[r])), _cells_of(torch.nan_to_num(p[r + 1]))
+        tp, tc = lut[cp][both].cpu().numpy(), lut[cc][both].cpu().numpy()
+        e_ref, m_ref = orc.transition_entropy(tp, tc, 201)
+        np.testing.assert_allclose(float(tr.entropy[r]), e_ref, rtol=RTOL, atol=ATOL)
+        assert np.array_equal(tr.prev_count0[r].cpu().numpy(), m_ref)
+    e.close()
