@@ -773,8 +773,10 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
   LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-  const int blocks = (int)std::min<int64_t>((F + 7) / 8, (int64_t)h->sm_count * 8);
-  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e);
+  const int kw = h->K >= 8 ? 8 : (h->K >= 4 ? 4 : (h->K >= 2 ? 2 : 1));  // warps per frame
+  const int groups = 8 / kw;
+  const int blocks = (int)std::min<int64_t>((F + groups - 1) / groups, (int64_t)h->sm_count * 8);
+  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, kw);
   VET_CUDA(cudaGetLastError());
   return VET_OK;
 }
@@ -1023,8 +1025,10 @@ int launch_weighted_rows(vet_handle* h, int64_t F, double* const* hists, const u
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
   LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-  const int blocks = (int)std::min<int64_t>((F + 7) / 8, (int64_t)h->sm_count * 8);
-  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e);
+  const int kw = h->K >= 8 ? 8 : (h->K >= 4 ? 4 : (h->K >= 2 ? 2 : 1));  // warps per frame
+  const int groups = 8 / kw;
+  const int blocks = (int)std::min<int64_t>((F + groups - 1) / groups, (int64_t)h->sm_count * 8);
+  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, kw);
   VET_CUDA(cudaGetLastError());
   return VET_OK;
 }
@@ -1844,7 +1848,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
       }
       Plan& pl = plan[k];
       pl.tab_off = (T * vet::kT3TileBytes + 15) & ~(size_t)15;
-      const size_t dense = T * T * 4, hash = (size_t)2 * vet::kT3Slots * 4;
+      const size_t dense = T * vet::t3_row_stride((uint32_t)T) * 4, hash = (size_t)2 * vet::kT3Slots * 4;
       size_t tab;
       if (pl.tab_off + dense <= budget) {
         pl.mode = vet::kT3Dense;

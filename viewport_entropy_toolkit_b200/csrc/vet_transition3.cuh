@@ -65,6 +65,10 @@ struct Lut3 {
   }
 };
 
+// Row pitch of the dense table: even, so that the diagonal (p, p) -- the pair of most users -- walks all
+// 32 banks (index p * (pitch + 1), pitch + 1 odd) instead of 16.
+__host__ __device__ __forceinline__ uint32_t t3_row_stride(uint32_t T) { return T + (T & 1u); }
+
 __device__ __forceinline__ uint32_t lds_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 
 template <int MODE>
@@ -73,7 +77,7 @@ __device__ __forceinline__ void t3_update(uint32_t* tab, uint32_t* diag, uint32_
   // minima only decrease and users arrive in roughly increasing order: a plain (broadcast) load
   // filters out almost every atomic
   if (MODE == kT3Dense) {
-    uint32_t* s = tab + p * T + c;
+    uint32_t* s = tab + p * t3_row_stride(T) + c;
     if (u < lds_u32(s)) atomicMin(s, u);
   } else if (p == c) {
     // staying inside the tile is by far the most frequent pair: it has its own dense slot
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   {
-    const uint32_t words = MODE == kT3Dense ? T * T : 2u * kT3Slots;
+    const uint32_t words = MODE == kT3Dense ? T * t3_row_stride(T) : 2u * kT3Slots;
     for (uint32_t i = tid; i < words; i += kT3Threads) s_tab[i] = kEmpty;
   }
   Lut3<LW> lut{a.lut_src};
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     if (MODE == kT3Dense) {
       for (uint32_t p = wid; p < T; p += kT3Threads / 32) {
         if (s_m[p] == 0u) continue;
-        uint32_t* row = s_tab + p * T;
+        uint32_t* row = s_tab + p * t3_row_stride(T);
         uint32_t cnt = 0;
         unsigned long long best = ~0ull;
         for (uint32_t c = lane; c < T; c += 32) {
