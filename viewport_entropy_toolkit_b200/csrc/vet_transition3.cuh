@@ -9,10 +9,11 @@
 // Pass 1 builds A[p][c] = min{u in S_p : cur(u) = c} over ALL users (one pre-checked atomicMin per
 // user) and m_p.  From row p of A:  D_p = #entries, (f_p, c_f) = the minimum entry (the first user
 // and its cur tile), (x_p, l'_p) = the maximum entry among c != c_f.  Excluding f_p only changes
-// the column c_f, so pass 2 collects, per p:  cnt_cf = #{u : cur = c_f},  second = min{u != f_p :
-// cur = c_f},  cnt_l = #{u : cur = l'_p}.  Then
+// the column c_f, so pass 2 collects, per p:  cnt_cf = #{u : cur = c_f},  other = #{u : cur != c_f}
+// (m_p = cnt_cf + other),  cnt_l = #{u : cur = l'_p}  and  early = [some u != f_p with cur = c_f comes
+// before x_p].  Then
 //     distinct(N_p) = D_p - 1 + [cnt_cf >= 2]
-//     latest key    = c_f if cnt_cf >= 2 and (no l'_p or second > x_p) else l'_p
+//     latest key    = c_f if cnt_cf >= 2 and (no l'_p or not early) else l'_p
 //     w_p           = cnt_cf - 1 resp. cnt_l            (m_p == 1: w_p = 1)
 // Order enters only through minima of user indices -> deterministic, counts bit-exact.
 //
@@ -33,6 +34,8 @@ constexpr uint32_t kT3Slots = 16384;
 constexpr uint32_t kT3Limit = kT3Slots * 3 / 4;
 constexpr int kT3Probes = 128;
 constexpr int kT3TileBytes = 2 * 8 + 6 * 4;  // per-tile arrays below
+constexpr uint32_t kNoTile = 0x3FFFu;        // 14-bit tile fields of s_cfl
+constexpr uint32_t kEarlyBit = 0x80000000u;
 
 enum : int { kT3Dense = 0, kT3Hash = 1 };
 enum : int { kLutS8 = 0, kLutS16 = 1, kLutG16 = 2, kLutIdentity = 3 };  // kLutIdentity: the input already holds tile ids
@@ -117,12 +120,12 @@ template <int MODE, int LW>
 __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t T = (uint32_t)a.T;
-  unsigned long long* s_info = reinterpret_cast<unsigned long long*>(smem_raw);  // row minimum, later (f_p<<32)|(l'<<16)|c_f
-  unsigned long long* s_rmax = s_info + T;                                        // ((x_p+1)<<32)|l'_p, 0 = none
-  uint32_t* s_m = reinterpret_cast<uint32_t*>(s_rmax + T);
-  uint32_t* s_d = s_m + T;       // distinct cur tiles of the row
-  uint32_t* s_second = s_d + T;
-  uint32_t* s_cf = s_second + T;  // cnt_cf
+  unsigned long long* s_rmin = reinterpret_cast<unsigned long long*>(smem_raw);  // row minimum (f_p<<32)|c_f, ~0 = empty row
+  unsigned long long* s_rmax = s_rmin + T;                                        // ((x_p+1)<<32)|l'_p, 0 = none
+  uint32_t* s_other = reinterpret_cast<uint32_t*>(s_rmax + T);  // users with cur != c_f  (m_p = cnt_cf + other)
+  uint32_t* s_d = s_other + T;    // distinct cur tiles of the row
+  uint32_t* s_cfl = s_d + T;      // c_f | l'_p << 14 (kNoTile = none) | "early" << 31
+  uint32_t* s_cf = s_cfl + T;     // cnt_cf
   uint32_t* s_cl = s_cf + T;      // cnt_l
   uint32_t* s_diag = s_cl + T;    // HASH: A[p][p]
   uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem_raw + a.tab_off);
@@ -157,11 +160,11 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     const uint16_t* __restrict__ crow = prow + U;
     uint32_t* __restrict__ p0row = a.pairs0 ? reinterpret_cast<uint32_t*>(a.pairs0) + r * (int64_t)U : nullptr;
     for (uint32_t t = tid; t < T; t += kT3Threads) {
-      s_info[t] = ~0ull;
+      s_rmin[t] = ~0ull;
       s_rmax[t] = 0ull;
-      s_m[t] = 0u;
+      s_other[t] = 0u;
       s_d[t] = 0u;
-      s_second[t] = kEmpty;
+      s_cfl[t] = kNoTile | (kNoTile << 14);
       s_cf[t] = 0u;
       s_cl[t] = 0u;
       if (MODE == kT3Hash) s_diag[t] = kEmpty;
@@ -202,7 +205,6 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
             if (pc[j] != kNoPair) {
               const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
               ++nvalid;
-              atomicAdd(&s_m[p], 1u);
               t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
             }
         } else {
@@ -213,7 +215,6 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
             if (pc[j] != kNoPair) {
               const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
               ++nvalid;
-              atomicAdd(&s_m[p], 1u);
               if (p == c) t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
               else pending |= 1u << j;
             }
@@ -247,7 +248,6 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
         if (ok) {
           const uint32_t p = pc & 0xFFFFu, c = pc >> 16;
           ++nvalid;
-          atomicAdd(&s_m[p], 1u);
           t3_update<MODE>(s_tab, s_diag, T, p, c, u, &s_used, &s_overflow);
         }
         __syncwarp();
@@ -275,7 +275,6 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     // ---- rows of A: D_p, (f_p, c_f), (x_p, l'_p); the table is left empty ----
     if (MODE == kT3Dense) {
       for (uint32_t p = wid; p < T; p += kT3Threads / 32) {
-        if (s_m[p] == 0u) continue;
         uint32_t* row = s_tab + p * t3_row_stride(T);
         uint32_t cnt = 0;
         unsigned long long best = ~0ull;
@@ -289,6 +288,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
         cnt = __reduce_add_sync(kFull, cnt);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(kFull, best, o));
+        if (best == ~0ull) continue;  // no user came from tile p (warp-uniform)
         const uint32_t cf = (uint32_t)best;
         unsigned long long top = 0ull;
         for (uint32_t c = lane; c < T; c += 32) {
@@ -302,8 +302,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
         for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(kFull, top, o));
         if (lane == 0) {
           s_d[p] = cnt;
+          s_rmin[p] = best;
           s_rmax[p] = top;
-          s_info[p] = (best & 0xFFFFFFFF00000000ull) | ((top ? (uint32_t)top & 0xFFFFu : 0xFFFFu) << 16) | cf;
+          s_cfl[p] = cf | ((top ? (uint32_t)top & kNoTile : kNoTile) << 14);
         }
       }
       __syncthreads();
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
       for (uint32_t p = tid; p < T; p += kT3Threads) {
         const uint32_t dg = s_diag[p];
         if (dg != kEmpty) {
-          s_info[p] = ((unsigned long long)dg << 32) | p;
+          s_rmin[p] = ((unsigned long long)dg << 32) | p;
           s_d[p] = 1u;
         }
       }
@@ -322,44 +323,50 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
         const uint32_t key = keys[s];
         if (key != kEmpty) {
           const uint32_t p = key / T, c = key - p * T;
-          atomicMin(&s_info[p], ((unsigned long long)firsts[s] << 32) | c);
+          atomicMin(&s_rmin[p], ((unsigned long long)firsts[s] << 32) | c);
           atomicAdd(&s_d[p], 1u);
         }
       }
       __syncthreads();
       for (uint32_t p = tid; p < T; p += kT3Threads) {
         const uint32_t dg = s_diag[p];
-        if (dg != kEmpty && p != (uint32_t)s_info[p]) s_rmax[p] = ((unsigned long long)(dg + 1u) << 32) | p;
+        if (dg != kEmpty && p != (uint32_t)s_rmin[p]) s_rmax[p] = ((unsigned long long)(dg + 1u) << 32) | p;
       }
       __syncthreads();
       for (uint32_t s = tid; s < kT3Slots; s += kT3Threads) {
         const uint32_t key = keys[s];
         if (key != kEmpty) {
           const uint32_t p = key / T, c = key - p * T;
-          if (c != (uint32_t)s_info[p]) atomicMax(&s_rmax[p], ((unsigned long long)(firsts[s] + 1u) << 32) | c);
+          if (c != (uint32_t)s_rmin[p]) atomicMax(&s_rmax[p], ((unsigned long long)(firsts[s] + 1u) << 32) | c);
           keys[s] = kEmpty;
           firsts[s] = kEmpty;
         }
       }
       __syncthreads();
       for (uint32_t p = tid; p < T; p += kT3Threads) {
-        const unsigned long long best = s_info[p], top = s_rmax[p];
-        if (s_m[p]) s_info[p] = (best & 0xFFFFFFFF00000000ull) | ((top ? (uint32_t)top & 0xFFFFu : 0xFFFFu) << 16) | (uint32_t)(best & 0xFFFFu);
+        const unsigned long long best = s_rmin[p], top = s_rmax[p];
+        if (best != ~0ull) s_cfl[p] = ((uint32_t)best & kNoTile) | ((top ? (uint32_t)top & kNoTile : kNoTile) << 14);
       }
       __syncthreads();
     }
 
-    // ---- pass 2: occurrences of c_f and l'_p, second user of (p, c_f) ----
+    // ---- pass 2: users per previous tile split into cur == c_f / other, occurrences of l'_p, and whether a
+    // non-first user of (p, c_f) comes before the first user of l'_p ("early": then l'_p is the latest key).
+    // One 32-bit load and one increment per user; the early test stops once its bit is set.
     auto second_pass = [&](uint32_t u, uint32_t pc) {
       if (pc == kNoPair) return;
       const uint32_t p = pc & 0xFFFFu, c = pc >> 16;
-      const unsigned long long inf = s_info[p];
-      const uint32_t lo = (uint32_t)inf;
-      if (c == (lo & 0xFFFFu)) {
+      const uint32_t w = lds_u32(&s_cfl[p]);
+      if (c == (w & kNoTile)) {
         atomicAdd(&s_cf[p], 1u);
-        if (u != (uint32_t)(inf >> 32) && u < lds_u32(&s_second[p])) atomicMin(&s_second[p], u);
-      } else if (c == (lo >> 16)) {
-        atomicAdd(&s_cl[p], 1u);
+        if (!(w & kEarlyBit) && ((w >> 14) & kNoTile) != kNoTile) {
+          const uint32_t f = reinterpret_cast<const uint32_t*>(s_rmin + p)[1];
+          const uint32_t x = reinterpret_cast<const uint32_t*>(s_rmax + p)[1] - 1u;
+          if (u != f && u < x) atomicOr(&s_cfl[p], kEarlyBit);
+        }
+      } else {
+        atomicAdd(&s_other[p], 1u);
+        if (c == ((w >> 14) & kNoTile)) atomicAdd(&s_cl[p], 1u);
       }
     };
     if (vec) {
@@ -383,15 +390,15 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     // ---- EU:297-330 ----
     double acc = 0.0;
     for (uint32_t p = tid; p < T; p += kT3Threads) {
-      const uint32_t m = s_m[p];
-      if (m == 0u) continue;
       const uint32_t ncf = s_cf[p];
+      const uint32_t m = ncf + s_other[p];
+      if (m == 0u) continue;
       const bool has2 = ncf >= 2u;
       const double Kp = 1.0 + (double)(s_d[p] - 1u + (has2 ? 1u : 0u));
       double wp = 1.0;
       if (m > 1u) {
         const unsigned long long top = s_rmax[p];
-        const bool cf_latest = has2 && (top == 0ull || s_second[p] > (uint32_t)(top >> 32) - 1u);
+        const bool cf_latest = has2 && (top == 0ull || !(s_cfl[p] & kEarlyBit));
         wp = cf_latest ? (double)(ncf - 1u) : (double)s_cl[p];
       }
       const double tp = wp / (double)m;
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
       s_used = 0u;
     }
     if (a.prev_count0)
-      for (uint32_t t = tid; t < T; t += kT3Threads) a.prev_count0[r * (int64_t)T + t] = (int32_t)s_m[t];
+      for (uint32_t t = tid; t < T; t += kT3Threads) a.prev_count0[r * (int64_t)T + t] = (int32_t)(s_cf[t] + s_other[t]);
     __syncthreads();
   }
 }
