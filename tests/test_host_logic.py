@@ -201,3 +201,59 @@ def test_ingest_errors(pkg, tmp_path):
     empty.mkdir()
     with pytest.raises(pkg.ValidationError, match="No trajectory data"):
         a.process_directory(empty)
+
+
+def _dir10(tmp_path):
+    a = load_golden("analyzers")
+    names = [f"user{u:02d}" for u in range(10)]
+    for n in names:
+        arr = a[f"dir10/{n}"]
+        pd.DataFrame({"time": arr[:, 0], "2dmu": arr[:, 1], "2dmv": arr[:, 2]}).to_csv(tmp_path / f"{n}.csv", index=False)
+    pd.DataFrame({"time": [1.2, 1.0, 1.1, 1.14], "2dmu": [.9, .0, 1.0, .29], "2dmv": [.9, 1.0, 0.0, .57]}).to_csv(tmp_path / "zz.csv", index=False)
+    return names + ["zz"]
+
+
+def test_reference_named_ingest_functions(pkg, tmp_path):
+    """process_viewport_data / format_trajectory_data (DU:289-410) under the reference's own names: consistent with
+    the packed ingest + oracle decode everywhere, and identical to the LIVE reference when it is present."""
+    from viewport_entropy_toolkit_b200 import ingest
+    names = _dir10(tmp_path)
+    ours = [pkg.process_viewport_data(tmp_path / f"{n}.csv", 100, 200)[::-1] for n in names]
+    assert [i for i, _ in ours] == names
+    assert list(ours[0][1].columns) == ["time", "2dmu", "2dmv", "pixel_x", "pixel_y", "lon", "lat"]
+    points_df, vectors_df = pkg.format_trajectory_data(ours)
+    packed, times, ids = ingest.load_directory(tmp_path, order=names)
+    assert np.array_equal(points_df["time"].to_numpy(), times) and list(points_df.columns) == ["time"] + names
+    vec, valid = orc.decode_vectors(packed[..., 1], packed[..., 2], 100, 200)
+    for u, n in enumerate(names):
+        for f in range(len(times)):
+            v, p = vectors_df[n][f], points_df[n][f]
+            if not valid[f, u]:
+                assert v is None and p is None
+            else:
+                assert (v.x, v.y, v.z) == tuple(vec[f, u]) and isinstance(p, pkg.RadialPoint)
+    with pytest.raises(pkg.ValidationError, match="Error processing viewport data"):
+        pkg.process_viewport_data(tmp_path / "missing.csv", 100, 200)
+    with pytest.raises(pkg.ValidationError, match="even numbers"):
+        pkg.process_viewport_data(tmp_path / "zz.csv", 101, 200)
+    with pytest.raises(pkg.ValidationError, match="No trajectory data"):
+        pkg.format_trajectory_data([])
+    from oracle import _refshim
+    if not _refshim.reference_available():
+        return
+    _refshim.load_reference()
+    from viewport_entropy_toolkit import utilities as RU
+    ref = []
+    for (ident, do), n in zip([pkg.process_viewport_data(tmp_path / f"{n}.csv", 100, 200)[::-1] for n in names], names):
+        dr, ir = RU.process_viewport_data(tmp_path / f"{n}.csv", 100, 200)
+        assert ir == ident and list(dr.columns) == list(do.columns) and (dr.dtypes == do.dtypes).all()
+        for c in dr.columns:
+            assert np.array_equal(dr[c].to_numpy(), do[c].to_numpy())
+        ref.append((ir, dr))
+    pr, vr = RU.format_trajectory_data(ref)
+    assert np.array_equal(pr["time"].to_numpy(), points_df["time"].to_numpy())
+    for n in names:
+        for x, y in zip(pr[n], points_df[n]):
+            assert (x is None and y is None) or (x.lon, x.lat) == (y.lon, y.lat)
+        for x, y in zip(vr[n], vectors_df[n]):
+            assert (x is None and y is None) or (x.x, x.y, x.z) == (y.x, y.y, y.z)

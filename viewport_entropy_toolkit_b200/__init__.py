@@ -14,7 +14,8 @@ from . import utilities
 from .utilities import (generate_fibonacci_lattice, normalize_to_pixel, pixel_to_spherical, validate_video_dimensions,
                         vector_angle_distance, find_angular_distances, find_nearest_tile, calculate_tile_weights,
                         compute_spatial_entropy, compute_transition_entropy,
-                        find_naive_tile_index, calculate_naive_tile_weights, compute_naive_spatial_entropy)
+                        find_naive_tile_index, calculate_naive_tile_weights, compute_naive_spatial_entropy,
+                        process_viewport_data, format_trajectory_data)
 
 __version__ = "0.1.0"
 __all__ = [
@@ -27,4 +28,5 @@ __all__ = [
     "vector_angle_distance", "find_angular_distances", "find_nearest_tile", "calculate_tile_weights",
     "compute_spatial_entropy", "compute_transition_entropy",
     "find_naive_tile_index", "calculate_naive_tile_weights", "compute_naive_spatial_entropy",
+    "process_viewport_data", "format_trajectory_data",
 ]

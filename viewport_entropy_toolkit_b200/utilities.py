@@ -17,6 +17,7 @@ from . import _tables
 from .config import EntropyConfig, DEFAULT_VIDEO_DIMENSIONS
 from .data_types import Point, RadialPoint, ValidationError, Vector
 from .engine import get_engine
+from .ingest import format_trajectory_data, process_viewport_data  # noqa: F401  (reference names, DU:289-410)
 
 _TINY_VIDEO = (2, 2)  # the vector entry points do not use the video grid
 
