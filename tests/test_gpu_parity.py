@@ -267,10 +267,14 @@ def test_spatial_vs_oracle(vet, cfg):
     dict(F=5, U=900, tcs=[50, 20], iid=True, missing=0.3),
     dict(F=3, U=9000, tcs=[200, 500, 1000], iid=False),     # fast paths: dense table (201) + shared-memory hash (501, 1001)
     dict(F=3, U=20000, tcs=[1000, 200], iid=True, missing=0.1),  # hash overflow -> in-kernel fallback to the global table
+    dict(F=4, U=5000, tcs=[1000], iid=False),               # one tile count: tile ids straight from the streaming kernel, hash table
+    dict(F=3, U=20001, tcs=[500], iid=True, missing=0.1),   # the same with overflow rows (redone through the identity table), odd U
+    dict(F=4, U=2500, tcs=[20], iid=False, dtype=np.float64),  # one tile count, dense table, float64 input
 ])
 @pytest.mark.parametrize("mode", ["literal", "textbook"])
 def test_transition_vs_oracle(vet, cfg, mode):
-    p = synth(cfg["F"], cfg["U"], 700 + cfg["U"], cfg.get("iid", False), cfg.get("missing", 0.0))
+    p = synth(cfg["F"], cfg["U"], 700 + cfg["U"], cfg.get("iid", False), cfg.get("missing", 0.0),
+              dtype=cfg.get("dtype", np.float32))
     e = engine(vet, cfg["tcs"], use_w=False)
     tr = e.transition(dev(p), mode=mode)
     assert e.poll_flags() == 0
