@@ -257,3 +257,22 @@ def test_reference_named_ingest_functions(pkg, tmp_path):
             assert (x is None and y is None) or (x.lon, x.lat) == (y.lon, y.lat)
         for x, y in zip(vr[n], vectors_df[n]):
             assert (x is None and y is None) or (x.x, x.y, x.z) == (y.x, y.y, y.z)
+
+
+def test_integration_stub_matches_the_abi(pkg):
+    """The ctypes stub shown in INTEGRATION.md declares struct vet_config exactly like the product's binding
+    (a shorter struct would make vet_create read past it)."""
+    import ctypes as C
+    from pathlib import Path
+    from viewport_entropy_toolkit_b200 import _native
+    src = (Path(__file__).resolve().parents[1] / "INTEGRATION.md").read_text()
+    code = src[src.index("class VetConfig(C.Structure):"):src.index("_lib.vet_last_error.restype")]
+    ns = {"C": C}
+    exec(code, ns)
+    stub = ns["VetConfig"]
+    assert [f[0] for f in stub._fields_] == [f[0] for f in _native.VetConfig._fields_]
+    assert C.sizeof(stub) == C.sizeof(_native.VetConfig)
+    header = (Path(__file__).resolve().parents[1] / "include" / "vet_b200.h").read_text()
+    body = header[header.index("typedef struct {"):header.index("} vet_config;")]
+    for name, _ in _native.VetConfig._fields_:
+        assert name in body, name
