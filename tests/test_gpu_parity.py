@@ -453,11 +453,15 @@ def test_functional_api_arbitrary_centres(vet):
         vet.compute_transition_entropy({"a": v}, {"b": v}, centres)
 
 
-@pytest.mark.parametrize("dims", [(200, 400), (1920, 1080)])
-def test_large_video_direct_mode(vet, dims):
-    """Videos whose cell grid does not fit the shared-memory tables run the direct per-sample
-    path (decode -> vectors -> brute force); results must match the oracle all the same."""
+@pytest.mark.parametrize("dims,regime", [((200, 400), "global"), ((200, 400), "direct"), ((1920, 1080), "direct")])
+def test_large_video_direct_mode(vet, dims, regime, monkeypatch):
+    """Videos whose cell grid does not fit the shared-memory tables: up to 262,144 cells (the 200x400 of the
+    reference's README) the per-cell tables stay in global memory (k_stream_global + the usual epilogues),
+    beyond that -- or with VET_REGIME=direct -- the direct per-sample path (decode -> vectors -> brute force)
+    runs; results must match the oracle all the same."""
     W, H = dims
+    if regime == "direct":
+        monkeypatch.setenv("VET_REGIME", "direct")   # read when the handle is created
     p = synth(4, 300, 4242, iid=True, missing=0.1, dtype=np.float64)
     for use_w, tcs in ((True, [20, 50]), (False, [200])):
         e = engine(vet, tcs, fov=100.0, use_w=use_w, W=W, H=H)
@@ -886,3 +890,40 @@ def test_full_size_properties_configs4_shard(vet):
         np.testing.assert_allclose(float(tr.entropy[r]), e_ref, rtol=RTOL, atol=ATOL)
         assert np.array_equal(tr.prev_count0[r].cpu().numpy(), m_ref)
     e.close()
+
+
+def test_global_table_regime_at_scale(vet, monkeypatch):
+    """200x400 video (80,601 cells: global-table regime) with enough frames for the tensor-core weighted
+    histogram (K = 80,640 cells) and the FP64 one: against the oracle, against each other, and the float32 /
+    several-tile-count / analyze() variants against the per-sample direct regime."""
+    W, H = 200, 400
+    p = synth(520, 700, 5151, iid=False, missing=0.05)
+    e = engine(vet, [200], fov=90.0, use_w=True, W=W, H=H)
+    a = e.spatial(dev(p))                                   # 520 frames: k_cnt_planes + k_whist_i8
+    assert e.poll_flags() == 0
+    sel = np.r_[0:3, 255:258, 517:520]
+    ref = orc.spatial_analyzer(p[sel], W, H, [200], 90.0, True, 2.0)
+    assert np.array_equal(a.assign0.cpu().numpy()[sel], ref["assign0"])
+    np.testing.assert_allclose(a.hist0.cpu().numpy()[sel], ref["hist0"], rtol=RTOL, atol=700 * I8_QUANT)
+    np.testing.assert_allclose(a.entropy.cpu().numpy()[sel], ref["entropy"], rtol=RTOL, atol=ATOL)
+    monkeypatch.setenv("VET_WHIST_IMPL", "fp64")
+    b = e.spatial(dev(p))
+    monkeypatch.delenv("VET_WHIST_IMPL")
+    np.testing.assert_allclose(a.hist0.cpu().numpy(), b.hist0.cpu().numpy(), rtol=RTOL, atol=700 * I8_QUANT)
+    np.testing.assert_allclose(a.entropy.cpu().numpy(), b.entropy.cpu().numpy(), rtol=RTOL, atol=0)
+    e.close()
+    q = synth(6, 2000, 5152, iid=True, missing=0.1)
+    for use_w, tcs in ((False, [50, 100, 200]), (True, [50, 200])):
+        g = engine(vet, tcs, fov=120.0, use_w=use_w, W=W, H=H)
+        sp, tr = g.analyze(dev(q))
+        assert g.poll_flags() == 0
+        monkeypatch.setenv("VET_REGIME", "direct")
+        d = engine(vet, tcs, fov=120.0, use_w=use_w, W=W, H=H)
+        monkeypatch.delenv("VET_REGIME")
+        sp2, tr2 = d.spatial(dev(q)), d.transition(dev(q))
+        assert torch.equal(sp.assign0, sp2.assign0) and torch.equal(tr.pairs0, tr2.pairs0) and torch.equal(tr.prev_count0, tr2.prev_count0)
+        np.testing.assert_allclose(sp.per_k.cpu().numpy(), sp2.per_k.cpu().numpy(), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(sp.hist0.cpu().numpy(), sp2.hist0.cpu().numpy(), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(tr.entropy.cpu().numpy(), tr2.entropy.cpu().numpy(), rtol=RTOL, atol=ATOL, equal_nan=True)
+        g.close()
+        d.close()

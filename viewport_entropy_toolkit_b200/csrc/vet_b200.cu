@@ -116,6 +116,8 @@ struct vet_handle {
   size_t ihist_bytes = 0;
   int sumT = 0;
   bool direct_only = false;      // video too large for the cell tables: packed input goes decode -> vectors path
+  bool global_tables = false;    // cell grid too large for shared memory but small enough for per-cell tables in
+                                 // global memory: k_stream_global + the usual table-regime epilogues
   uint16_t* d_identity = nullptr;  // [maxT] identity LUT (vectors path feeds tile indices to k_transition)
   void* d_vscratch[3] = {nullptr, nullptr, nullptr};  // idx[F,U] i32, per_k[K,F] f64, vec[F,U,3] f64
   size_t vscratch_bytes[3] = {0, 0, 0};
@@ -274,6 +276,7 @@ int transition_direct(vet_handle* h, const void* packed, int dtype, int64_t F, i
 
 constexpr size_t kStaticSmemSlack = 1024;
 constexpr int kMaxT = 16384;
+constexpr int64_t kGlobalTableCells = 262144;  // largest cell grid of the global-table regime (tables scale with C*T)
 
 // tensor-core weighted histogram (defined with launch_whist_i8 below)
 bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U);
@@ -581,13 +584,41 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
   a.chunks_per_frame = (int)((U + a.chunk_users - 1) / std::max<int64_t>(a.chunk_users, 1));
   if (a.chunks_per_frame < 1) a.chunks_per_frame = 1;
   a.cpad = h->Cpad;
-  if (a.chunks_per_frame > 1) {
+  if (a.chunks_per_frame > 1 && !h->global_tables) {
     VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->Cpad * 4, st));
     VET_CUDA(cudaMemsetAsync(h->d_nvalid, 0, (size_t)F * 4, st));
   }
+  h->planes_from_stream = false;
+  if (h->global_tables) {
+    vet::StreamGlobalArgs G{};
+    G.s = a;
+    G.s.chunks_per_frame = 1;
+    G.K = h->K;
+    G.sumT = h->sumT;
+    int off = 0;
+    for (int k = 0; k < h->K; ++k) {
+      G.hist_off[k] = off;
+      off += h->ts[k].T;
+      G.lut[k] = h->ts[k].d_lut;
+    }
+    VET_CUDA(cudaMemsetAsync(h->d_nvalid, 0, (size_t)F * 4, st));
+    if (h->use_weight) {
+      VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->Cpad * 4, st));
+    } else {  // unweighted: tile histograms directly, no cell histogram
+      G.s.cnt = nullptr;
+      if (int rc = grow((void**)&h->d_ihist, &h->ihist_bytes, (size_t)F * h->sumT * 4)) return rc;
+      VET_CUDA(cudaMemsetAsync(h->d_ihist, 0, (size_t)F * h->sumT * 4, st));
+      G.ihist = h->d_ihist;
+    }
+    const int gblocks = (int)std::min<int64_t>((F * U + 255) / 256, (int64_t)h->sm_count * 16);
+    LaunchTimer lt(h, VET_KERNEL_STREAM, st);
+    if (dtype == VET_F32) vet::k_stream_global<float><<<gblocks, 256, 0, st>>>(G);
+    else vet::k_stream_global<double><<<gblocks, 256, 0, st>>>(G);
+    VET_CUDA(cudaGetLastError());
+    return VET_OK;
+  }
   const int64_t items = F * a.chunks_per_frame;
   const int blocks = (int)std::min<int64_t>(items, h->sm_count);
-  h->planes_from_stream = false;
   if (use_tma_stream(h, packed)) {
     const bool lut8 = h->ts[0].d_lut8 != nullptr;
     vet::StreamTmaArgs A{};
@@ -659,7 +690,7 @@ struct TilesPlan {
 
 TilesPlan plan_tiles(const vet_handle* h, const void* packed, int64_t U) {
   TilesPlan p;
-  if (h->use_weight || h->direct_only) return p;
+  if (h->use_weight || h->direct_only || h->global_tables) return p;
   if (((uintptr_t)packed & 15) != 0) return p;
   static const bool disabled = [] {
     const char* e = getenv("VET_STREAM_IMPL");
@@ -1049,6 +1080,16 @@ int launch_weighted_epilogue(vet_handle* h, int64_t F, int64_t U, double* entrop
 int launch_epilogue(vet_handle* h, int64_t F, int64_t U, double* entropy, double* per_k, int64_t per_k_stride, double* hist0,
                     cudaStream_t st) {
   if (h->use_weight) return launch_weighted_epilogue(h, F, U, entropy, per_k, per_k_stride, hist0, st);
+  if (h->global_tables) {  // k_stream_global already made the tile histograms
+    TilesPlan tp;
+    int off = 0;
+    for (int k = 0; k < h->K; ++k) {
+      tp.A.hist_off[k] = off;
+      off += h->ts[k].T;
+    }
+    tp.A.sumT = off;
+    return launch_tiles_epilogue(h, tp, F, entropy, per_k, per_k_stride, hist0, st);
+  }
   vet::EpilogueArgs a{};
   a.cnt = h->d_cnt;
   a.F = F;
@@ -1178,6 +1219,13 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   // larger videos use the direct per-sample path (decode -> vectors)
   h->direct_only = stream_smem_bytes(h) + kStaticSmemSlack > h->smem_optin ||
                    epilogue_smem_bytes(h) + kStaticSmemSlack > h->smem_optin;
+  if (h->direct_only && h->C <= kGlobalTableCells) {
+    const char* e = getenv("VET_REGIME");  // "direct" pins the per-sample path for A/B runs and tests
+    if (!(e && std::string(e) == "direct")) {
+      h->direct_only = false;
+      h->global_tables = true;
+    }
+  }
   if (h->C >= ((int64_t)1 << 31)) return fail(VET_ERR_UNSUPPORTED, "video %dx%d has too many cells", h->W, h->H);
   if (naive && h->direct_only) return fail(VET_ERR_UNSUPPORTED, "video %dx%d is too large for the grid-tiling tables", h->W, h->H);
 

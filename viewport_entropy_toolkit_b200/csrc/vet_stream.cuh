@@ -80,6 +80,65 @@ __global__ void __launch_bounds__(1024, 1) k_stream_simple(StreamArgs a) {
   if (bad) atomicOr(a.flags, (uint32_t)VET_FLAG_OUT_OF_RANGE);
 }
 
+// Streaming kernel of the GLOBAL-TABLE regime: videos whose cell grid does not fit the shared-memory
+// histogram + LUT of the kernels above (e.g. the 200x400 of the reference's README: 80,601 cells) but
+// whose per-cell tables are still small.  Same per-cell formulation, the tables just stay in global
+// memory / L2: one RED into the frame's cell histogram (weighted handles; the tensor-core / FP64
+// weighted histogram then runs on it unchanged) or one RED per tile count into the frame's tile
+// histograms (unweighted handles), one LUT gather for the assignment.  Bound by L2 atomics, not by HBM.
+struct StreamGlobalArgs {
+  StreamArgs s;                       // cnt may be null (unweighted handles)
+  int K;
+  int sumT;
+  int hist_off[16];                   // offset of tile count k inside an ihist row
+  const uint16_t* lut[16];            // [C] per tile count
+  uint32_t* ihist;                    // [F, sumT] (pre-zeroed) or null
+};
+
+template <typename TIN>
+__global__ void __launch_bounds__(256) k_stream_global(StreamGlobalArgs A) {
+  const StreamArgs& a = A.s;
+  const TIN* __restrict__ packed = static_cast<const TIN*>(a.packed);
+  const float Wf = (float)a.W, Hf = (float)a.H;
+  const int64_t n = a.F * a.U;
+  const int lane = threadIdx.x & 31;
+  uint32_t bad = 0;
+  // whole warps walk consecutive samples, so a warp usually sits inside one frame
+  const int64_t nround = (n + 31) & ~(int64_t)31;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool in = i < n;
+    const int64_t f = in ? i / a.U : -1;
+    int cell = -1;
+    int st = kMissing;
+    if (in) st = decode_cell(packed[3 * i + 1], packed[3 * i + 2], Wf, Hf, a.W, a.H, cell);
+    const bool ok = st == kOk;
+    if (st == kOutOfRange) bad = 1;
+    if (ok) {
+      if (a.cnt) atomicAdd(&a.cnt[f * (int64_t)a.cpad + cell], 1u);
+      const uint32_t t0 = __ldg(A.lut[0] + cell);
+      if (a.assign0) a.assign0[i] = (uint16_t)t0;
+      if (A.ihist) {
+        uint32_t* __restrict__ row = A.ihist + f * (int64_t)A.sumT;
+        atomicAdd(&row[A.hist_off[0] + t0], 1u);
+        for (int k = 1; k < A.K; ++k) atomicAdd(&row[A.hist_off[k] + __ldg(A.lut[k] + cell)], 1u);
+      }
+    } else if (in && a.assign0) {
+      a.assign0[i] = (uint16_t)VET_MISSING;
+    }
+    if (in && a.cell16) a.cell16[i] = ok ? (uint16_t)cell : (uint16_t)0xFFFF;
+    if (in && a.cell32) a.cell32[i] = ok ? cell : -1;
+    // present users per frame: one atomic per warp when the warp is inside one frame
+    const int64_t f0 = __shfl_sync(kFull, f, 0);
+    if (__all_sync(kFull, f == f0 || !in)) {
+      const uint32_t c = __popc(__ballot_sync(kFull, ok));
+      if (lane == 0 && c) atomicAdd(&a.nvalid[f0], c);
+    } else if (ok) {
+      atomicAdd(&a.nvalid[f], 1u);
+    }
+  }
+  if (bad) atomicOr(a.flags, (uint32_t)VET_FLAG_OUT_OF_RANGE);
+}
+
 struct TileSetDev {
   int T;
   const uint16_t* lut;       // [C]
