@@ -453,7 +453,8 @@ def test_functional_api_arbitrary_centres(vet):
         vet.compute_transition_entropy({"a": v}, {"b": v}, centres)
 
 
-@pytest.mark.parametrize("dims,regime", [((200, 400), "global"), ((200, 400), "direct"), ((1920, 1080), "direct")])
+@pytest.mark.parametrize("dims,regime", [((200, 400), "global"), ((200, 400), "direct"), ((1920, 1080), "direct"),
+                                         ((1920, 1080), "global")])   # 2M cells: global LUTs when unweighted, else direct
 def test_large_video_direct_mode(vet, dims, regime, monkeypatch):
     """Videos whose cell grid does not fit the shared-memory tables: up to 262,144 cells (the 200x400 of the
     reference's README) the per-cell tables stay in global memory (k_stream_global + the usual epilogues),

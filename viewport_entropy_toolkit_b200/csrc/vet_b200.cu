@@ -277,6 +277,7 @@ int transition_direct(vet_handle* h, const void* packed, int dtype, int64_t F, i
 constexpr size_t kStaticSmemSlack = 1024;
 constexpr int kMaxT = 16384;
 constexpr int64_t kGlobalTableCells = 262144;  // largest cell grid of the global-table regime (tables scale with C*T)
+constexpr int64_t kGlobalLutCells = (int64_t)1 << 24;  // the same for unweighted handles (only LUTs: 2 B x C per tile count)
 
 // tensor-core weighted histogram (defined with launch_whist_i8 below)
 bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U);
@@ -1219,7 +1220,8 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   // larger videos use the direct per-sample path (decode -> vectors)
   h->direct_only = stream_smem_bytes(h) + kStaticSmemSlack > h->smem_optin ||
                    epilogue_smem_bytes(h) + kStaticSmemSlack > h->smem_optin;
-  if (h->direct_only && h->C <= kGlobalTableCells) {
+  // weighted handles need per-cell weight tables (C x T): bounded; unweighted ones only the cell -> tile LUTs
+  if (h->direct_only && (h->C <= kGlobalTableCells || (!h->use_weight && h->C <= kGlobalLutCells))) {
     const char* e = getenv("VET_REGIME");  // "direct" pins the per-sample path for A/B runs and tests
     if (!(e && std::string(e) == "direct")) {
       h->direct_only = false;
