@@ -76,4 +76,15 @@ if "mid" in which:  # the reference README's custom configuration: 200x400 video
                                             prof=eng.profile_read())
         eng.close()
     del p
+if "midu" in which:  # the same video, unweighted
+    from viewport_entropy_toolkit_b200.engine import Engine
+    F, U = 900, 100_000
+    p = bench.synth_on_device(torch, F, U, 6, dev)
+    for dims in ((200, 400), (1920, 1080)):
+        eng = Engine(dims[0], dims[1], [50, 100, 200], EntropyConfig(use_weight_distribution=False), dev)
+        eng.profile(True)
+        ms = timeit(lambda: eng.spatial(p, want_per_k=False), n=2, warm=1)
+        out[f"mid_{dims[0]}x{dims[1]}_unweighted"] = dict(frames=F, users=U, ms=ms, gsamples=F * U / ms / 1e6, prof=eng.profile_read())
+        eng.close()
+    del p
 print(json.dumps(out))

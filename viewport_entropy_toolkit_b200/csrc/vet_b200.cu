@@ -552,10 +552,17 @@ bool use_tma_stream(const vet_handle* h, const void* packed) {
   return stream_tma_smem_bytes(h, lut8) + kStaticSmemSlack <= h->smem_optin;
 }
 
+// bytes of the cell-histogram scratch for batches of fb frames (none where no kernel of the handle uses it)
+size_t cnt_scratch_bytes(const vet_handle* h, int64_t fb) {
+  if (h->global_tables && !h->use_weight) return 16;
+  return (size_t)(fb + vet::kWhRowPad) * h->Cpad * 4;
+}
+
 // frames per batch so that the per-frame cell histogram scratch stays bounded
 int64_t frames_per_batch(const vet_handle* h, int64_t F, int64_t U, bool need_cells) {
   const size_t budget = (size_t)1 << 30;  // 1 GiB of scratch
   size_t per_frame = (size_t)h->Cpad * 4;
+  if (h->global_tables && !h->use_weight) per_frame = (size_t)h->sumT * 4;  // tile histograms only, no cell histogram
   if (need_cells) per_frame += (size_t)U * (h->C <= 65535 ? 2 : 4);
   int64_t fb = (int64_t)std::max<size_t>(2, budget / std::max<size_t>(per_frame, 1));
   return std::min<int64_t>(F, fb);
@@ -1448,7 +1455,7 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
   cudaStream_t st = (cudaStream_t)stream;
   if (h->direct_only) return spatial_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, hist0_dev, assign0_dev, st);
   const int64_t fb = frames_per_batch(h, F, U, false);
-  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)(fb + vet::kWhRowPad) * h->Cpad * 4)) return rc;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, cnt_scratch_bytes(h, fb))) return rc;
   if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
   const size_t esz = dtype == VET_F32 ? 4 : 8;
   const int T0 = h->ts[0].T;
@@ -1486,7 +1493,7 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
     return transition_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, prev_count0_dev, pairs0_dev, mode, st);
   const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
   const size_t csz = h->C <= 65535 ? 2 : 4;
-  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)(fb + vet::kWhRowPad) * h->Cpad * 4)) return rc;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, cnt_scratch_bytes(h, fb))) return rc;
   if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
   if (int rc = grow(&h->d_cells, &h->cells_bytes, (size_t)fb * U * csz)) return rc;
   const size_t esz = dtype == VET_F32 ? 4 : 8;
@@ -1540,7 +1547,7 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
   }
   const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
   const size_t csz = h->C <= 65535 ? 2 : 4;
-  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)(fb + vet::kWhRowPad) * h->Cpad * 4)) return rc;
+  if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, cnt_scratch_bytes(h, fb))) return rc;
   if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
   if (int rc = grow(&h->d_cells, &h->cells_bytes, (size_t)fb * U * csz)) return rc;
   // the streaming kernel always writes assignments here (its LUT copy is what selects the fused variant)
@@ -2189,7 +2196,7 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
     cudaStreamWaitEvent(h->s_exec, in_done[b], 0);
     cudaStreamWaitEvent(h->s_exec, out_done[b], 0);  // assignment buffer b must have been downloaded
     const int64_t fbs = frames_per_batch(h, nf, U, false);
-    rc = grow((void**)&h->d_cnt, &h->cnt_bytes, (size_t)(fbs + vet::kWhRowPad) * h->Cpad * 4);
+    rc = grow((void**)&h->d_cnt, &h->cnt_bytes, cnt_scratch_bytes(h, fbs));
     if (rc == VET_OK) rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fbs * 4);
     for (int64_t g0 = 0; g0 < nf && rc == VET_OK; g0 += fbs) {
       const int64_t ng = std::min(fbs, nf - g0);
