@@ -58,8 +58,9 @@ def test_product_does_not_import_oracle():
     for f in (ROOT / "viewport_entropy_toolkit_b200").rglob("*.py"):
         src = f.read_text()
         assert "oracle" not in src.replace("# oracle", ""), f
-    for f in (ROOT / "viewport_entropy_toolkit_b200" / "csrc").glob("*"):
-        assert "oracle" not in f.read_text(), f
+    for f in (ROOT / "viewport_entropy_toolkit_b200" / "csrc").rglob("*"):
+        if f.is_file():
+            assert "oracle" not in f.read_text(), f
 
 
 def test_reference_smoke_tests(pkg, tmp_path):

@@ -1,0 +1,250 @@
+// Launchers of the transition stage: k_transition3 per tile count, k_transition2 / k_transition behind it.
+// Textual fragment of vet_b200.cu.
+namespace {
+
+// Sizes the (prev,cur) pair tables, picks the shared- or global-memory variant and launches
+// k_transition for `rows` frame pairs.
+// k_transition2 over all tile counts of `a` (dense table / shared-memory hash / global table per tile count);
+// only_rows != null restricts it to the flagged rows.
+int launch_transition2(vet_handle* h, const vet::TransitionArgs& a, int64_t U, int Tmax, int blocks, size_t tile_bytes,
+                       const uint32_t* only_rows, cudaStream_t st) {
+  {
+    // fast paths: dense T*T table or shared-memory hash per tile count, global table as the in-kernel fallback
+    vet::Transition2Args A2{};
+    A2.t = a;
+    A2.only_rows = only_rows;
+    const size_t budget = h->smem_optin - kStaticSmemSlack;
+    size_t table_words = 0;
+    for (int k = 0; k < a.K; ++k) {
+      const size_t dense_words = (size_t)a.T[k] * a.T[k];
+      if (tile_bytes + dense_words * 4 + 64 <= budget) {
+        A2.mode[k] = vet::kTrDense;
+        table_words = std::max(table_words, dense_words);
+      } else if (tile_bytes + (size_t)3 * vet::kHashSlots * 4 + 64 <= budget) {
+        A2.mode[k] = vet::kTrHash;
+        table_words = std::max(table_words, (size_t)3 * vet::kHashSlots);
+      } else {
+        A2.mode[k] = vet::kTrGlobal;
+      }
+    }
+    // LUT staging area after the table area, for the tile counts whose LUT still fits
+    const size_t lut_off = (tile_bytes + table_words * 4 + 64 + 15) & ~(size_t)15;
+    size_t lut_area = 0;
+    for (int k = 0; k < a.K; ++k) {
+      // a.lut[k] is one of the handle's uint16 LUTs (or the identity table of the vectors path)
+      const uint8_t* l8 = nullptr;
+      for (int j = 0; j < h->K; ++j)
+        if (h->ts[j].d_lut == a.lut[k]) l8 = h->ts[j].d_lut8;
+      const bool is_cell_lut = a.lut[k] != h->d_identity;
+      const size_t bytes = (((size_t)h->C * (l8 ? 1 : 2)) + 15) & ~(size_t)15;
+      A2.lut8[k] = l8;
+      A2.lut_smem[k] = (is_cell_lut && lut_off + bytes <= budget) ? 1 : 0;
+      if (A2.lut_smem[k]) lut_area = std::max(lut_area, bytes);
+    }
+    A2.lut_area_off = (int)lut_off;
+    const size_t smem2 = lut_off + lut_area;
+    // packed (prev | cur << 16) per user, one row per CTA
+    if (int rc = grow((void**)&h->d_pairs, &h->pairs_bytes, (size_t)blocks * U * 4)) return rc;
+    A2.pair_scratch = h->d_pairs;
+    A2.t.C = (int)h->C;
+    VET_CUDA(cudaFuncSetAttribute(vet::k_transition2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+    vet::k_transition2<<<blocks, vet::kTrThreads, smem2, st>>>(A2, Tmax);
+  }
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st) {
+  // capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
+  const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)Tmax * Tmax);
+  uint32_t cap = 1024;
+  while ((uint64_t)cap < 2 * max_pairs) cap <<= 1;
+  const size_t tile_bytes = (size_t)Tmax * (8 + 4 * 4);
+  const size_t smem_tab = tile_bytes + (size_t)cap * 16 + 64;
+  const bool in_smem = smem_tab + kStaticSmemSlack <= h->smem_optin;
+  const int blocks = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * (in_smem ? 1 : 2));
+  if (!in_smem) {
+    const size_t words = (size_t)blocks * 4 * cap;
+    if (h->tables_words < words || h->tables_cap != cap) {
+      if (h->tables_words < words) {
+        if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
+        h->d_tables = nullptr;
+        h->tables_words = 0;
+        VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
+        h->tables_words = words;
+      }
+      // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value).  Done once per layout:
+      // the kernels reset every slot they touch, so the tables stay clean between calls.
+      for (int b = 0; b < blocks; ++b) {
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+      }
+      h->tables_cap = cap;
+      h->tables_blocks = blocks;
+    } else if (h->tables_blocks < blocks) {
+      for (int b = h->tables_blocks; b < blocks; ++b) {
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+      }
+      h->tables_blocks = blocks;
+    }
+  }
+  a.cap = cap;
+  a.g_tables = h->d_tables;
+  // VET_TRANSITION_IMPL = v1 | v2 pins an older kernel generation (A/B runs, tests); read at every call
+  const bool force_v1 = [] {
+    const char* e = getenv("VET_TRANSITION_IMPL");
+    return e && std::string(e) == "v1";
+  }();
+  const bool force_v2 = [] {
+    const char* e = getenv("VET_TRANSITION_IMPL");
+    return e && std::string(e) == "v2";
+  }();
+  // two-pass kernel, one launch per tile count; rows it cannot hold (hash overflow) are flagged in d_redo
+  // and recomputed by k_transition2 below
+  bool redo_only = false;
+  if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1 && !force_v2 && a.cell16 && U < ((int64_t)1 << 31)) {
+    const size_t budget = h->smem_optin - kStaticSmemSlack;
+    struct Plan {
+      int mode, lw;
+      size_t tab_off, lut_off, smem;
+      const void* lut;
+    } plan[vet::kMaxTileCounts];
+    bool ok = true;
+    for (int k = 0; k < a.K && ok; ++k) {
+      const size_t T = (size_t)a.T[k];
+      const uint8_t* l8 = nullptr;
+      bool is_cell_lut = false;
+      for (int j = 0; j < h->K; ++j)
+        if (h->ts[j].d_lut == a.lut[k]) {
+          l8 = h->ts[j].d_lut8;
+          is_cell_lut = true;
+        }
+      const bool identity = a.lut[k] == h->d_identity;  // the input rows hold tile ids already
+      if (!is_cell_lut && !identity) {
+        ok = false;
+        break;
+      }
+      Plan& pl = plan[k];
+      pl.tab_off = (T * vet::kT3TileBytes + 15) & ~(size_t)15;
+      const size_t dense = T * vet::t3_row_stride((uint32_t)T) * 4, hash = (size_t)2 * vet::kT3Slots * 4;
+      size_t tab;
+      if (pl.tab_off + dense <= budget) {
+        pl.mode = vet::kT3Dense;
+        tab = dense;
+      } else if (pl.tab_off + hash <= budget) {
+        pl.mode = vet::kT3Hash;  // rows with more distinct pairs than the table holds are redone by k_transition2
+        tab = hash;
+      } else {
+        pl.mode = -1;  // this tile count goes to k_transition2 (global pair tables)
+        continue;
+      }
+      pl.lut_off = (pl.tab_off + tab + 15) & ~(size_t)15;
+      const size_t lut_bytes = (((size_t)h->C * (l8 ? 1 : 2)) + 15) & ~(size_t)15;
+      if (identity) {
+        pl.lw = vet::kLutIdentity;
+        pl.lut = nullptr;
+        pl.smem = pl.lut_off;
+      } else if (pl.lut_off + lut_bytes <= budget) {
+        pl.lw = l8 ? vet::kLutS8 : vet::kLutS16;
+        pl.lut = l8 ? (const void*)l8 : (const void*)a.lut[k];
+        pl.smem = pl.lut_off + lut_bytes;
+      } else {
+        pl.lw = vet::kLutG16;
+        pl.lut = a.lut[k];
+        pl.smem = pl.lut_off;
+      }
+    }
+    if (ok) {
+      const int blocks3 = (int)std::min<int64_t>(rows, h->sm_count);
+      if (int rc = grow((void**)&h->d_pairs, &h->pairs_bytes, (size_t)std::max(blocks, blocks3) * U * 4)) return rc;
+      if (int rc = grow((void**)&h->d_redo, &h->redo_bytes, (size_t)rows * 4)) return rc;
+      VET_CUDA(cudaMemsetAsync(h->d_redo, 0, (size_t)rows * 4, st));
+      double* per_k = a.per_k;
+      int64_t stride = a.per_k_stride;
+      if (a.K > 1 && !per_k) {
+        if (int rc = grow((void**)&h->d_trk, &h->trk_bytes, (size_t)a.K * rows * 8)) return rc;
+        per_k = h->d_trk;
+        stride = rows;
+      }
+      bool any_hash = false;
+      for (int k = 0; k < a.K; ++k) {
+        const Plan& pl = plan[k];
+        double* out_k = a.K == 1 ? a.entropy : per_k + k * stride;
+        if (pl.mode < 0) {
+          vet::TransitionArgs a1 = a;
+          a1.K = 1;
+          a1.T[0] = a.T[k];
+          a1.lut[0] = a.lut[k];
+          a1.entropy = out_k;
+          a1.per_k = nullptr;
+          a1.prev_count0 = k == 0 ? a.prev_count0 : nullptr;
+          a1.pairs0 = k == 0 ? a.pairs0 : nullptr;
+          if (int rc = launch_transition2(h, a1, U, Tmax, blocks, tile_bytes, nullptr, st)) return rc;
+          continue;
+        }
+        any_hash = any_hash || pl.mode == vet::kT3Hash;
+        vet::Transition3Args A3{};
+        A3.cell16 = a.cell16;
+        A3.F = a.F;
+        A3.U = (uint32_t)U;
+        A3.T = a.T[k];
+        A3.C = (int)h->C;
+        A3.lut_src = pl.lut;
+        A3.tab_off = (int)pl.tab_off;
+        A3.lut_off = (int)pl.lut_off;
+        A3.out = out_k;
+        A3.prev_count0 = k == 0 ? a.prev_count0 : nullptr;
+        A3.pairs0 = k == 0 ? a.pairs0 : nullptr;
+        A3.pair_scratch = h->d_pairs;
+        A3.redo = h->d_redo;
+        A3.flags = a.flags;
+        LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+#define VET_T3(MODE, LW)                                                                                              \
+  do {                                                                                                                \
+    VET_CUDA(cudaFuncSetAttribute(vet::k_transition3<MODE, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
+    vet::k_transition3<MODE, LW><<<blocks3, vet::kT3Threads, pl.smem, st>>>(A3);                                      \
+  } while (0)
+        if (pl.mode == vet::kT3Dense) {
+          if (pl.lw == vet::kLutS8) VET_T3(vet::kT3Dense, vet::kLutS8);
+          else if (pl.lw == vet::kLutS16) VET_T3(vet::kT3Dense, vet::kLutS16);
+          else if (pl.lw == vet::kLutIdentity) VET_T3(vet::kT3Dense, vet::kLutIdentity);
+          else VET_T3(vet::kT3Dense, vet::kLutG16);
+        } else {
+          if (pl.lw == vet::kLutS8) VET_T3(vet::kT3Hash, vet::kLutS8);
+          else if (pl.lw == vet::kLutS16) VET_T3(vet::kT3Hash, vet::kLutS16);
+          else if (pl.lw == vet::kLutIdentity) VET_T3(vet::kT3Hash, vet::kLutIdentity);
+          else VET_T3(vet::kT3Hash, vet::kLutG16);
+        }
+#undef VET_T3
+        VET_CUDA(cudaGetLastError());
+      }
+      if (a.K == 1 && a.per_k) {
+        VET_CUDA(cudaMemcpyAsync(a.per_k, a.entropy, (size_t)rows * 8, cudaMemcpyDeviceToDevice, st));
+      } else if (a.K > 1) {
+        LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+        vet::k_mean_rows<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(per_k, stride, a.K, rows, a.entropy);
+        VET_CUDA(cudaGetLastError());
+      }
+      if (!any_hash) return VET_OK;  // nothing can have been left over
+      redo_only = true;
+    }
+  }
+  if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1) {
+    if (int rc = launch_transition2(h, a, U, Tmax, blocks, tile_bytes, redo_only ? h->d_redo : nullptr, st)) return rc;
+  } else if (in_smem) {
+    VET_CUDA(cudaFuncSetAttribute(vet::k_transition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
+    LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+    vet::k_transition<true><<<blocks, 512, smem_tab, st>>>(a, Tmax);
+  } else {
+    VET_CUDA(cudaFuncSetAttribute(vet::k_transition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(tile_bytes + 64)));
+    LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+    vet::k_transition<false><<<blocks, 512, tile_bytes + 64, st>>>(a, Tmax);
+  }
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
+}  // namespace
