@@ -76,9 +76,7 @@ struct WhistArgs {
 // the FP64 pipe plus two register moves; otherwise I2F.F64.U32 on the conversion unit,
 // which runs beside the FP64 pipe.
 __device__ __forceinline__ double u32_to_f64(uint32_t v) {
-#ifdef VET_DBG_NO_CVT
-  return __hiloint2double(0x3ff00000, (int)v);  // timing experiment only: wrong values, no conversion
-#elif defined(VET_CVT_MAGIC)
+#if defined(VET_CVT_MAGIC)
   return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
 #else
   return (double)v;
@@ -216,10 +214,8 @@ __global__ void __launch_bounds__(kWhThreads, 1) k_whist(WhistArgs a) {
       for (int s = 0; s < S::kDepth; ++s) {
         // issue the count loads of step S+S::kDepth-1 and the unit load of step S+2(S::kDepth-1)
         const uint32_t* p = row0 + uring[(s + S::kDepth - 1) % S::kDepth];
-#ifndef VET_DBG_NO_CNT_LOADS
 #pragma unroll
         for (int r = 0; r < FW; ++r, p += a.cpad) ring[(s + S::kDepth - 1) % S::kDepth][r].load(p);
-#endif
         uring[(s + S::kDepth - 2) % S::kDepth] = __ldg(up);
         up += 32;
         whist_step<S, 0, TG>(sW, s, lane, ring[s], acc);  // step S out of ring[s]
