@@ -38,6 +38,19 @@ int64_t frames_per_batch(const vet_handle* h, int64_t F, int64_t U, bool need_ce
   return std::min<int64_t>(F, fb);
 }
 
+// Grid of a persistent kernel whose equal-cost items are dealt round-robin: the fewest CTAs that need the same
+// number of rounds as one CTA per SM would.
+int balanced_grid(int64_t items, int sm_count) {
+  static const bool per_sm = [] {
+    const char* e = getenv("VET_STREAM_GRID");
+    return e && std::string(e) == "sm";
+  }();
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(items, sm_count));
+  if (per_sm) return blocks;
+  const int64_t rounds = (items + blocks - 1) / blocks;
+  return (int)((items + rounds - 1) / rounds);
+}
+
 int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64_t U, uint16_t* assign0, bool cells,
                   cudaStream_t st) {
   vet::StreamArgs a{};
@@ -96,7 +109,10 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
     return VET_OK;
   }
   const int64_t items = F * a.chunks_per_frame;
-  const int blocks = (int)std::min<int64_t>(items, h->sm_count);
+  // Items are dealt round-robin and cost the same, so the kernel takes ceil(items / CTAs) rounds: use the fewest
+  // CTAs that still need that many rounds (3600 frames: 144 CTAs x 25 instead of 148 CTAs of which 100 do only 24).
+  // Measured on configs[2]: 0.790 -> 0.782 ms (97.6 -> 98.6 % of the HBM peak).  VET_STREAM_GRID=sm pins one CTA per SM.
+  const int blocks = balanced_grid(items, h->sm_count);
   if (use_tma_stream(h, packed)) {
     const bool lut8 = h->ts[0].d_lut8 != nullptr;
     vet::StreamTmaArgs A{};
@@ -230,7 +246,7 @@ int launch_stream_tiles(vet_handle* h, TilesPlan& p, const void* packed, int dty
   p.A.s = a;
   p.A.total_bytes = F * U * 3 * (int64_t)(dtype == VET_F32 ? 4 : 8);
   p.A.ihist = h->d_ihist;
-  const int blocks = (int)std::min<int64_t>(F * a.chunks_per_frame, h->sm_count);
+  const int blocks = balanced_grid(F * a.chunks_per_frame, h->sm_count);
   const int sm = (int)(h->smem_optin - kStaticSmemSlack);
   LaunchTimer lt(h, VET_KERNEL_STREAM, st);
 #define VET_LAUNCH_TILES(TIN, ASSIGN, KP)                                                                              \
