@@ -167,7 +167,7 @@ def run_reference_arm(args, wl, rank):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    users, frames = 32, 2 * cores
+    users, frames = 128, 4 * cores   # ~1.5 s of work per step on every core (the port does ~300 samples/s/core)
     pool = mp.get_context("fork").Pool(cores)
     for _ in range(args.warmup):
         cpu_rate(wl, frames, users, cores, pool=pool)
