@@ -928,3 +928,20 @@ def test_global_table_regime_at_scale(vet, monkeypatch):
         np.testing.assert_allclose(tr.entropy.cpu().numpy(), tr2.entropy.cpu().numpy(), rtol=RTOL, atol=ATOL, equal_nan=True)
         g.close()
         d.close()
+
+
+def test_host_path_equals_device_path_at_scale(vet):
+    """More frames than one host batch (512 for weighted handles) with a short last batch: the host-buffer path
+    and the device path take the same weighted kernel for every batch of a call and return the same bits."""
+    p = synth(1100, 1500, 6161, iid=False, missing=0.02)
+    e = engine(vet, [200, 50], fov=90.0)
+    d = e.spatial(dev(p))
+    h = e.spatial_host(p)
+    assert e.poll_flags() == 0
+    assert np.array_equal(h["entropy"], d.entropy.cpu().numpy())
+    assert np.array_equal(h["hist0"], d.hist0.cpu().numpy())
+    assert np.array_equal(h["assign0"], d.assign0.cpu().numpy())
+    ref = orc.spatial_analyzer(p[1090:], W0, H0, [200, 50], 90.0, True, 2.0)   # frames of the short last host batch
+    np.testing.assert_allclose(h["entropy"][1090:], ref["entropy"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(h["hist0"][1090:], ref["hist0"], rtol=RTOL, atol=1500 * I8_QUANT)
+    e.close()

@@ -323,6 +323,7 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
   if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:168-169
   if (!packed_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
   DeviceGuard guard(h->device);
+  h->call_frames = F;
   cudaStream_t st = (cudaStream_t)stream;
   if (h->direct_only) return spatial_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, hist0_dev, assign0_dev, st);
   const int64_t fb = frames_per_batch(h, F, U, false);
@@ -411,6 +412,7 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
   if (!packed_dev || !sp_entropy_dev || (F > 1 && !tr_entropy_dev)) return fail(VET_ERR_INVALID_ARG, "null buffer");
   if (U >= 0xFFFFFFFFll) return fail(VET_ERR_UNSUPPORTED, "too many users");
   DeviceGuard guard(h->device);
+  h->call_frames = F;
   cudaStream_t st = (cudaStream_t)stream;
   if (h->direct_only || F == 1) {  // no shared pass to gain: run the two stages one after the other
     if (int rc = vet_spatial(h, packed_dev, dtype, F, U, sp_entropy_dev, sp_per_k_dev, hist0_dev, assign0_dev, stream)) return rc;

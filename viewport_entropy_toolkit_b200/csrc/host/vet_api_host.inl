@@ -4,10 +4,14 @@
 
 namespace {
 
-// frames per host batch: about 256 MiB of packed input per copy
-int64_t host_batch_frames(int64_t F, int64_t U, size_t esz) {
-  const size_t per_frame = (size_t)U * 3 * esz;
-  return std::min<int64_t>(F, std::max<int64_t>(2, (int64_t)(((size_t)256 << 20) / std::max<size_t>(per_frame, 1))));
+// frames per host batch: about 256 MiB of packed input per copy; weighted handles take 512 frames when that
+// stays under 1 GiB, so that the host path runs the same tensor-core weighted histogram as the device path
+// (use_whist_i8: from 512 frames per batch) and returns the same bits
+int64_t host_batch_frames(const vet_handle* h, int64_t F, int64_t U, size_t esz) {
+  const size_t per_frame = std::max<size_t>((size_t)U * 3 * esz, 1);
+  int64_t fb = std::max<int64_t>(2, (int64_t)(((size_t)256 << 20) / per_frame));
+  if (h->use_weight && fb < 512 && (size_t)512 * per_frame <= ((size_t)1 << 30)) fb = 512;
+  return std::min<int64_t>(F, fb);
 }
 
 }  // namespace
@@ -19,6 +23,7 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
   if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");
   if (!packed_host || !entropy_host) return fail(VET_ERR_INVALID_ARG, "null buffer");
   DeviceGuard guard(h->device);
+  h->call_frames = F;
   const size_t esz = dtype == VET_F32 ? 4 : 8;
   if (h->direct_only) {  // large-video mode: plain upload, direct kernels, download
     const int T0d = h->ts[0].T;
@@ -48,7 +53,7 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
     if (e != cudaSuccess) return fail(VET_ERR_CUDA, "host-buffer pipeline failed: %s", cudaGetErrorString(e));
     return VET_OK;
   }
-  const int64_t fb = host_batch_frames(F, U, esz);
+  const int64_t fb = host_batch_frames(h, F, U, esz);
   const size_t in_bytes = (size_t)fb * U * 3 * esz;
   if (h->in_bytes < in_bytes) {
     for (int i = 0; i < 2; ++i) {

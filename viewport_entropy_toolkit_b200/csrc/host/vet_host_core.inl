@@ -110,6 +110,7 @@ struct vet_handle {
   CUtensorMap tm_cnt;
   bool planes_from_stream = false;  // the last launch_stream wrote the planes of its batch itself
   bool i8_attr_set = false;
+  int64_t call_frames = 0;       // frames of the API call in progress: its batches all take the same weighted kernel
   uint32_t* d_redo = nullptr;   // [rows] frame pairs the two-pass transition kernel left to k_transition2
   size_t redo_bytes = 0;
   double* d_trk = nullptr;      // [K, rows] per-tile-count transition entropies when the caller wants none

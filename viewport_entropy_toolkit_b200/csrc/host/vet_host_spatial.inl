@@ -398,7 +398,8 @@ bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U) {
   // A CTA of the tensor-core kernel takes ~70 us whatever the batch (it walks all cells of 128 frames x 48
   // tiles); the FP64 kernel costs ~0.14 us per frame at 201 tiles.  From a few hundred frames on the
   // tensor cores win (measured: equal at 450 frames, 0.07 vs 0.50 ms at 3600).
-  return F >= 512;
+  // decided per API call, not per internal batch, so that a short last batch does not switch kernels
+  return std::max(F, h->call_frames) >= 512;
 }
 
 // Quantised weight slices of tile set t: row nb*240 + s*48 + j of [i8_blocks*240, kp] holds slice s of
