@@ -528,8 +528,35 @@ def gen_naive():
     np.savez_compressed(OUT / "naive.npz", **out)
 
 
+def gen_geometry():
+    """Tile geometry for renders (DU:58-225, 412-743): boundary segments of the Fibonacci tiles, latitude /
+    longitude tile boxes and the tile areas, from the reference's own functions."""
+    load_reference()
+    from viewport_entropy_toolkit.utilities import data_utils as DU
+    out = {}
+    for n in (3, 20, 50, 200):
+        b = DU.get_fb_tile_boundaries(n)
+        rows = [(i, e, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z) for i, edges in b.items() for e, (p1, p2) in enumerate(edges)]
+        out[f"fb{n}/edges"] = np.array(rows, dtype=np.float64).reshape(-1, 8)
+        out[f"fb{n}/tiles"] = np.array([len(b)])
+        if n in (20, 50):
+            area, frac = DU.compute_fb_tile_areas(n)
+            out[f"fb{n}/area"] = np.array([area[i] for i in range(len(b))])
+            out[f"fb{n}/fraction"] = np.array([frac[i] for i in range(len(b))])
+        print("geometry fb", n, len(rows), flush=True)
+    for nh, nv in ((4, 2), (12, 6)):
+        t = DU.get_lat_lon_tiles(nh, nv)
+        keys = sorted(t)
+        rows = [(ki, e, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z) for ki, k in enumerate(keys) for e, (p1, p2) in enumerate(t[k])]
+        out[f"ll{nh}x{nv}/keys"] = np.array(keys)
+        out[f"ll{nh}x{nv}/edges"] = np.array(rows, dtype=np.float64)
+        area, frac = DU.compute_lat_lon_tile_areas(nh, nv)
+        out[f"ll{nh}x{nv}/area"] = np.array([area[k] for k in keys])
+    np.savez_compressed(OUT / "geometry.npz", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lattices", "decode", "nearest", "weights", "frames", "quirks", "analyzers", "naive"]
+    which = sys.argv[1:] or ["lattices", "decode", "nearest", "weights", "frames", "quirks", "analyzers", "naive", "geometry"]
     for w in which:
         {"lattices": gen_lattices, "decode": gen_decode, "nearest": gen_nearest, "weights": gen_weights,
-         "frames": gen_frames, "quirks": gen_transition_quirks, "analyzers": gen_analyzers, "naive": gen_naive}[w]()
+         "frames": gen_frames, "quirks": gen_transition_quirks, "analyzers": gen_analyzers, "naive": gen_naive, "geometry": gen_geometry}[w]()

@@ -277,3 +277,38 @@ def test_integration_stub_matches_the_abi(pkg):
     body = header[header.index("typedef struct {"):header.index("} vet_config;")]
     for name, _ in _native.VetConfig._fields_:
         assert name in body, name
+
+
+def test_tile_geometry_vs_reference_fixtures(pkg):
+    """Tile geometry for renders (DU:58-225, 412-743): boundary segments of the Fibonacci tiles, latitude/longitude
+    tile boxes and tile areas, bit for bit against the live-reference fixtures."""
+    from viewport_entropy_toolkit_b200 import geometry as G
+    g = group_keys(load_golden("geometry"))
+    for n in (3, 20, 50, 200):
+        b = G.get_fb_tile_boundaries(n)
+        assert len(b) == int(g[f"fb{n}"]["tiles"][0])
+        rows = [(i, e, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z) for i, edges in b.items() for e, (p1, p2) in enumerate(edges)]
+        assert np.array_equal(np.array(rows, dtype=np.float64).reshape(-1, 8), g[f"fb{n}"]["edges"]), n
+    for n in (20, 50):
+        area, frac = G.compute_fb_tile_areas(n)
+        assert np.array_equal(np.array([area[i] for i in range(len(area))]), g[f"fb{n}"]["area"])
+        assert np.array_equal(np.array([frac[i] for i in range(len(frac))]), g[f"fb{n}"]["fraction"])
+        assert abs(sum(frac.values()) - 1.0) < 1e-12           # the tiles cover the sphere
+    for nh, nv in ((4, 2), (12, 6)):
+        t = G.get_lat_lon_tiles(nh, nv)
+        keys = sorted(t)
+        assert keys == [str(k) for k in g[f"ll{nh}x{nv}"]["keys"]]
+        rows = [(ki, e, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z) for ki, k in enumerate(keys) for e, (p1, p2) in enumerate(t[k])]
+        assert np.array_equal(np.array(rows, dtype=np.float64), g[f"ll{nh}x{nv}"]["edges"])
+        area, frac = G.compute_lat_lon_tile_areas(nh, nv)
+        assert np.array_equal(np.array([area[k] for k in keys]), g[f"ll{nh}x{nv}"]["area"])
+    with pytest.raises(pkg.ValidationError):
+        G.get_fb_tile_boundaries(0)
+    with pytest.raises(pkg.ValidationError):
+        G.compute_lat_lon_tile_areas(0, 4)
+    with pytest.raises(ValueError):
+        G.triangulate_spherical_polygon([pkg.Vector(1, 0, 0), pkg.Vector(0, 1, 0)])
+    # exported under the reference's names
+    for name in ("get_fb_tile_boundaries", "get_lat_lon_tiles", "normalize", "great_circle_intersection", "get_tile_corners",
+                 "compute_spherical_polygon_area", "spherical_interpolation", "find_nearest_point", "angle_at_vertex"):
+        assert getattr(pkg.utilities, name) is getattr(G, name)

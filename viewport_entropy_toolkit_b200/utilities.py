@@ -18,6 +18,11 @@ from .config import EntropyConfig, DEFAULT_VIDEO_DIMENSIONS
 from .data_types import Point, RadialPoint, ValidationError, Vector
 from .engine import get_engine
 from .ingest import format_trajectory_data, process_viewport_data  # noqa: F401  (reference names, DU:289-410)
+from .geometry import (  # noqa: F401  (render support, DU:58-225, 412-743)
+    angle_at_vertex, calculate_spherical_triangle_area, compute_fb_tile_areas, compute_lat_lon_tile_areas,
+    compute_spherical_polygon_area, find_nearest_point, find_perpendicular_on_tangent_plane, get_fb_tile_boundaries,
+    get_lat_lon_tiles, get_line_segment, get_tile_corners, great_circle_intersection, normalize,
+    spherical_interpolation, triangulate_spherical_polygon)
 
 _TINY_VIDEO = (2, 2)  # the vector entry points do not use the video grid
 
