@@ -308,6 +308,11 @@ def test_tile_geometry_vs_reference_fixtures(pkg):
         G.compute_lat_lon_tile_areas(0, 4)
     with pytest.raises(ValueError):
         G.triangulate_spherical_polygon([pkg.Vector(1, 0, 0), pkg.Vector(0, 1, 0)])
+    # convert_vectors_to_coordinates (DT:219-276)
+    lons, lats = pkg.convert_vectors_to_coordinates([pkg.Vector(1, 0, 0), pkg.Vector(0, 1, 0), pkg.Vector(-1, 0, 0), pkg.Vector(0, 0, 2)])
+    assert np.array_equal(lons, [0.0, 90.0, 180.0, 0.0]) and np.array_equal(lats, [0.0, 0.0, 0.0, 90.0])
+    with pytest.raises(pkg.ValidationError):
+        pkg.convert_vectors_to_coordinates([])
     # exported under the reference's names
     for name in ("get_fb_tile_boundaries", "get_lat_lon_tiles", "normalize", "great_circle_intersection", "get_tile_corners",
                  "compute_spherical_polygon_area", "spherical_interpolation", "find_nearest_point", "angle_at_vertex"):

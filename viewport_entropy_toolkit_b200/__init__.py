@@ -5,7 +5,7 @@ Same public names as the reference package for the accelerated path; compute run
 in hand-written sm_100a CUDA kernels behind a C ABI (include/vet_b200.h).  Importing
 the package does not need a GPU; computing anything does.
 """
-from .data_types import Point, RadialPoint, Vector, ValidationError, SpatialError
+from .data_types import Point, RadialPoint, Vector, ValidationError, SpatialError, convert_vectors_to_coordinates
 from .config import (AnalyzerConfig, NaiveAnalyzerConfig, EntropyConfig, VisualizationConfig, DEFAULT_VIDEO_DIMENSIONS,
                      DEFAULT_TILE_COUNTS, DEFAULT_OUTPUT_FORMATS)
 from .engine import Engine, SpatialResult, TransitionResult, UnsupportedConfigurationError, get_engine
@@ -19,7 +19,7 @@ from .utilities import (generate_fibonacci_lattice, normalize_to_pixel, pixel_to
 
 __version__ = "0.1.0"
 __all__ = [
-    "Point", "RadialPoint", "Vector", "ValidationError", "SpatialError",
+    "Point", "RadialPoint", "Vector", "ValidationError", "SpatialError", "convert_vectors_to_coordinates",
     "AnalyzerConfig", "NaiveAnalyzerConfig", "EntropyConfig", "VisualizationConfig",
     "DEFAULT_VIDEO_DIMENSIONS", "DEFAULT_TILE_COUNTS", "DEFAULT_OUTPUT_FORMATS",
     "Engine", "SpatialResult", "TransitionResult", "UnsupportedConfigurationError", "get_engine",

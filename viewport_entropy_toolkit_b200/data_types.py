@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Tuple
+from typing import List, Union, Tuple
 
 import numpy as np
 
@@ -97,3 +97,23 @@ class Vector:
         from ._tables import spherical_to_vector
         x, y, z = spherical_to_vector(lon, lat)
         return cls(x=float(x), y=float(y), z=float(z))
+
+
+def convert_vectors_to_coordinates(vectors) -> Tuple[np.ndarray, np.ndarray]:
+    """[Vector] -> (longitudes, latitudes) in degrees for plotting (DT:219-276): lon = atan2(y, x),
+    lat = asin(z / |v|), longitudes folded into (-180, 180]."""
+    if vectors is None or len(vectors) == 0:
+        raise ValidationError("Empty vector collection provided")
+    try:
+        items = vectors.tolist() if isinstance(vectors, np.ndarray) else vectors
+        if not all(isinstance(v, Vector) for v in items):
+            raise ValidationError("All elements must be Vector instances")
+        pts = [RadialPoint(lon=np.degrees(np.arctan2(v.y, v.x)),
+                           lat=np.degrees(np.arcsin(v.z / np.sqrt(v.x ** 2 + v.y ** 2 + v.z ** 2)))) for v in items]
+        lons = np.array([p.lon for p in pts])
+        lats = np.array([p.lat for p in pts])
+        lons = np.where(lons > 180, lons - 360, lons)
+        lons = np.where(lons <= -180, lons + 360, lons)
+        return lons, lats
+    except Exception as e:
+        raise ValidationError(f"Failed to convert vectors to coordinates: {str(e)}")
