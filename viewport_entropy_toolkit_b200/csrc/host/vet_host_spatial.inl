@@ -92,6 +92,33 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
       off += h->ts[k].T;
       G.lut[k] = h->ts[k].d_lut;
     }
+    // weighted, and the grid fits shared memory as 16-bit counters: privatised histogram per (frame, chunk)
+    const size_t smem16 = (size_t)((h->Cpad + 1) / 2) * 4;
+    static const bool no16 = [] {
+      const char* e = getenv("VET_STREAM_IMPL");
+      return e && std::string(e) == "global";
+    }();
+    if (h->use_weight && !no16 && smem16 + kStaticSmemSlack <= h->smem_optin) {
+      vet::StreamArgs b = a;
+      const int64_t cpf = std::max<int64_t>((U + 65534) / 65535, std::min<int64_t>((U + 16383) / 16384, ((int64_t)h->sm_count * 8 + F - 1) / F));
+      b.chunk_users = (U + cpf - 1) / cpf;
+      b.chunks_per_frame = (int)((U + b.chunk_users - 1) / std::max<int64_t>(b.chunk_users, 1));
+      if (b.chunks_per_frame > 1) {
+        VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->Cpad * 4, st));
+        VET_CUDA(cudaMemsetAsync(h->d_nvalid, 0, (size_t)F * 4, st));
+      }
+      const int fblocks = balanced_grid(F * b.chunks_per_frame, h->sm_count);
+      LaunchTimer lt(h, VET_KERNEL_STREAM, st);
+      if (dtype == VET_F32) {
+        VET_CUDA(cudaFuncSetAttribute(vet::k_stream_frame16<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+        vet::k_stream_frame16<float><<<fblocks, 1024, smem16, st>>>(b);
+      } else {
+        VET_CUDA(cudaFuncSetAttribute(vet::k_stream_frame16<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+        vet::k_stream_frame16<double><<<fblocks, 1024, smem16, st>>>(b);
+      }
+      VET_CUDA(cudaGetLastError());
+      return VET_OK;
+    }
     VET_CUDA(cudaMemsetAsync(h->d_nvalid, 0, (size_t)F * 4, st));
     if (h->use_weight) {
       VET_CUDA(cudaMemsetAsync(h->d_cnt, 0, (size_t)F * h->Cpad * 4, st));

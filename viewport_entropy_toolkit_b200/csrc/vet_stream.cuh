@@ -139,6 +139,74 @@ __global__ void __launch_bounds__(256) k_stream_global(StreamGlobalArgs A) {
   if (bad) atomicOr(a.flags, (uint32_t)VET_FLAG_OUT_OF_RANGE);
 }
 
+// Weighted handles of the global-table regime whose cell grid fits shared memory as 16-BIT counters
+// (up to ~110k cells: the README's 200x400 video): one CTA per (frame, chunk of <= 65535 users) keeps a
+// privatised histogram of packed uint16 pairs -- a sample adds 1 or 65536 to its pair's word, and a chunk
+// cannot overflow a half -- instead of one L2 RED per sample.  The flush writes the uint32 row of `cnt`
+// (plain stores when the frame is one chunk, RED into the pre-zeroed row otherwise).
+template <typename TIN>
+__global__ void __launch_bounds__(1024, 1) k_stream_frame16(StreamArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* s_h = reinterpret_cast<uint32_t*>(smem_raw);
+  __shared__ uint32_t s_nvalid;
+  const TIN* __restrict__ packed = static_cast<const TIN*>(a.packed);
+  const float Wf = (float)a.W, Hf = (float)a.H;
+  const int words = (a.cpad + 1) >> 1;
+  const int64_t items = a.F * a.chunks_per_frame;
+  uint32_t bad = 0;
+  for (int c = threadIdx.x; c < words; c += blockDim.x) s_h[c] = 0u;
+  if (threadIdx.x == 0) s_nvalid = 0u;
+  __syncthreads();
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t f = item / a.chunks_per_frame;
+    const int64_t u0 = (item % a.chunks_per_frame) * a.chunk_users;
+    const int64_t u1 = min(a.U, u0 + a.chunk_users);
+    const int64_t base = f * a.U;
+    uint32_t nv = 0;
+    for (int64_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) {
+      const TIN mu = packed[3 * (base + u) + 1];
+      const TIN mv = packed[3 * (base + u) + 2];
+      int cell;
+      const int st = decode_cell(mu, mv, Wf, Hf, a.W, a.H, cell);
+      const bool ok = st == kOk;
+      if (st == kOutOfRange) bad = 1;
+      if (ok) {
+        atomicAdd(&s_h[cell >> 1], (cell & 1) ? 0x10000u : 1u);
+        ++nv;
+      }
+      if (a.assign0) a.assign0[base + u] = ok ? __ldg(a.lut0 + cell) : (uint16_t)VET_MISSING;
+      if (a.cell16) a.cell16[base + u] = ok ? (uint16_t)cell : (uint16_t)0xFFFF;
+      if (a.cell32) a.cell32[base + u] = ok ? cell : -1;
+    }
+    nv = __reduce_add_sync(kFull, nv);
+    if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&s_nvalid, nv);
+    __syncthreads();
+    uint32_t* __restrict__ row = a.cnt + f * (int64_t)a.cpad;  // cpad is a multiple of 4: pairs never straddle rows
+    if (a.chunks_per_frame == 1) {
+      for (int c = threadIdx.x; c < words; c += blockDim.x) {
+        const uint32_t v = s_h[c];
+        s_h[c] = 0u;
+        *reinterpret_cast<uint2*>(row + 2 * c) = make_uint2(v & 0xFFFFu, v >> 16);
+      }
+      if (threadIdx.x == 0) a.nvalid[f] = s_nvalid;
+    } else {
+      for (int c = threadIdx.x; c < words; c += blockDim.x) {
+        const uint32_t v = s_h[c];
+        if (v) {
+          s_h[c] = 0u;
+          if (v & 0xFFFFu) atomicAdd(&row[2 * c], v & 0xFFFFu);
+          if (v >> 16) atomicAdd(&row[2 * c + 1], v >> 16);
+        }
+      }
+      if (threadIdx.x == 0 && s_nvalid) atomicAdd(&a.nvalid[f], s_nvalid);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_nvalid = 0u;
+    __syncthreads();
+  }
+  if (bad) atomicOr(a.flags, (uint32_t)VET_FLAG_OUT_OF_RANGE);
+}
+
 struct TileSetDev {
   int T;
   const uint16_t* lut;       // [C]
