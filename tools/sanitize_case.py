@@ -41,7 +41,15 @@ t2 = e.transition(packed(3, 20000))                 # k_transition3 hash, overfl
 t3 = e.transition(packed(5, 700), mode="textbook")  # k_transition (shared-memory table)
 e.close()
 e = Engine(200, 400, [20], EntropyConfig())
-r4 = e.spatial(packed(2, 300))                      # direct regime: k_decode + k_nearest + k_spatial_vectors
+r4 = e.spatial(packed(2, 300))                      # global-table regime, weighted: k_stream_frame16 + k_whist
+e.close()
+e = Engine(200, 400, [20, 50], EntropyConfig(use_weight_distribution=False))
+r8 = e.spatial(packed(2, 300))                      # global-table regime, unweighted: k_stream_global + k_entropy_rows
+e.close()
+os.environ["VET_REGIME"] = "direct"
+e = Engine(200, 400, [20], EntropyConfig())
+del os.environ["VET_REGIME"]
+r9 = e.spatial(packed(2, 300))                      # direct regime: k_decode + k_nearest + k_spatial_vectors
 e.close()
 torch.cuda.synchronize()
 print("sanitize case ok", float(r.entropy[0]), float(t.entropy[0]), float(r2.entropy[0]), float(r3.entropy[0]),
