@@ -214,11 +214,17 @@ int vet_poll_flags(vet_handle* h, void* stream, uint32_t* flags);
 int64_t vet_launch_count(const vet_handle* h);
 
 /* Per-kernel device timing for the benchmark's roofline line.  When enabled, every
- * launch of the streaming / epilogue / transition kernels is bracketed by a CUDA
+ * launch of the streaming / epilogue / transition / transition-tail kernels is bracketed by a CUDA
  * event pair on its own stream (no synchronisation is added).  vet_profile_read
  * waits for the recorded events, returns the summed milliseconds and launch counts
  * per kernel (arrays of VET_KERNEL_COUNT) and clears the record. */
-enum { VET_KERNEL_STREAM = 0, VET_KERNEL_EPILOGUE = 1, VET_KERNEL_TRANSITION = 2, VET_KERNEL_COUNT = 3 };
+enum {
+  VET_KERNEL_STREAM = 0,
+  VET_KERNEL_EPILOGUE = 1,
+  VET_KERNEL_TRANSITION = 2,
+  VET_KERNEL_TRANSITION_TAIL = 3, /* k_transition3c: the pairs left after the full rounds, one per CTA cluster */
+  VET_KERNEL_COUNT = 4
+};
 int vet_profile_enable(vet_handle* h, int on);
 int vet_profile_read(vet_handle* h, double* ms_by_kernel, int64_t* launches_by_kernel);
 

@@ -714,6 +714,45 @@ def test_transition_two_pass_kernel_equals_three_pass_kernel(vet, U, monkeypatch
     e.close()
 
 
+@pytest.mark.parametrize("F,U,tcs", [
+    (3, 66_000, [200]),          # 2 pairs, clusters of 8, tile ids straight from the streaming kernel
+    (3, 40_001, [200, 20]),      # clusters of 4, odd U (scalar loads), LUTs staged in shared memory
+    (152, 16_384, [200]),        # 151 pairs: one full round of k_transition3 + 3 pairs on clusters of 2
+    (21, 131_072, [100, 200]),   # 20 pairs: more than the co-resident clusters of 8
+])
+def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs, monkeypatch):
+    """k_transition3c (the users of one frame pair split over a thread-block cluster, for the pairs left after
+    the full rounds) against k_transition3 alone: every output bit for bit, transition() and analyze();
+    the small cases also against the oracle."""
+    import bench
+    p = bench.synth_on_device(torch, F, U, 616 + U, torch.device("cuda"))
+    p[1, ::5, 1] = float("nan")                                   # missing users
+    g = torch.Generator(device="cuda").manual_seed(7)
+    p[F - 2:, :, 1:] = torch.rand((2, U, 2), generator=g, device="cuda")   # iid frames: every row of the table in use
+    e = engine(vet, tcs, use_w=False)
+    res = {}
+    e.profile(True)
+    for cl in ("0", "1"):
+        monkeypatch.setenv("VET_T3_CLUSTER", cl)
+        tr = e.transition(p)
+        _, tr2 = e.analyze(p)
+        assert e.poll_flags() == 0
+        res[cl] = (tr, tr2, e.profile_read()["transition_tail"][1])
+    e.profile(False)
+    assert res["0"][2] == 0 and res["1"][2] == 2 * len(tcs), "one cluster launch per tile count and call"
+    for a, b in ((res["0"][0], res["1"][0]), (res["0"][0], res["1"][1])):
+        assert torch.equal(a.pairs0, b.pairs0) and torch.equal(a.prev_count0, b.prev_count0)
+        assert np.array_equal(a.per_k.cpu().numpy(), b.per_k.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(a.entropy.cpu().numpy(), b.entropy.cpu().numpy(), equal_nan=True)
+    if F <= 3:
+        ref = orc.transition_analyzer(p.cpu().numpy(), W0, H0, tcs, mode="literal")
+        b = res["1"][0]
+        assert np.array_equal(b.pairs0.cpu().numpy(), ref["pairs0"])
+        assert np.array_equal(b.prev_count0.cpu().numpy(), ref["prev_count0"])
+        np.testing.assert_allclose(b.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    e.close()
+
+
 # ---------------------------------------------------------------------------------
 # latitude/longitude grid tiling (NaiveSpatialEntropyAnalyzer, NA:39-241 / EU:335-453)
 # ---------------------------------------------------------------------------------

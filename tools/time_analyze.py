@@ -1,0 +1,37 @@
+"""A/B timing of vet_analyze / vet_transition on the configs[4] shard (1M users x 450 frames, 200 tiles, weighted):
+python tools/time_analyze.py [frames] [users].  VET_T3_CLUSTER is read at every call; VET_ANALYZE_OVERLAP once
+per process (run the script twice for that one)."""
+import os
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+import bench
+from viewport_entropy_toolkit_b200 import EntropyConfig, get_engine
+
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 450
+U = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+dev = torch.device("cuda")
+p = bench.synth_on_device(torch, F, U, 20265000, dev, chunk=32 if U > 200_000 else 256)
+eng = get_engine(100, 200, [200], EntropyConfig(fov_angle=90.0, power_factor=2.0), dev)
+
+
+def timed(fn, n=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+for cl in ("0", "1"):
+    os.environ["VET_T3_CLUSTER"] = cl
+    t_an = timed(lambda: eng.analyze(p, want_per_k=False, want_assign0=True, want_pairs0=False))
+    t_tr = timed(lambda: eng.transition(p, want_pairs0=False, want_per_k=False))
+    print(f"F={F} U={U} overlap={os.environ.get('VET_ANALYZE_OVERLAP', '1')} cluster={cl}: "
+          f"analyze {t_an:.4f} ms, transition {t_tr:.4f} ms", flush=True)

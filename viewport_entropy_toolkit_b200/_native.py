@@ -73,7 +73,7 @@ SYMBOLS = {
     "vet_profile_enable": (C.c_int, [_P, C.c_int]),
     "vet_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
-KERNEL_NAMES = ("stream", "epilogue", "transition")
+KERNEL_NAMES = ("stream", "epilogue", "transition", "transition_tail")  # VET_KERNEL_* of vet_b200.h
 
 _lib: Optional[C.CDLL] = None
 

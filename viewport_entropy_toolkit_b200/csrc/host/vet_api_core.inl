@@ -236,6 +236,8 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);
   for (void* p : h->d_hout) cudaFree(p);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_exec) cudaStreamDestroy(h->s_exec);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -436,9 +438,27 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
     uint16_t* asg = assign ? assign + f0 * U : (uint16_t*)h->d_vscratch[0];
     const bool tiles_direct = h->K == 1;  // the assignments double as the transition stage's input (identity table)
     if (int rc = launch_stream(h, in, dtype, nf, U, asg, !tiles_direct, st)) return rc;
-    if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
-                                 hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
-      return rc;
+    // The two consumers of the streaming kernel's outputs are independent: the transition kernel goes first on
+    // the caller's stream (its persistent CTAs take every SM), the spatial epilogue on a side stream fills the SMs
+    // that fall idle in the transition kernel's last, partial round.  VET_ANALYZE_OVERLAP=0 runs them in sequence.
+    static const bool overlap = [] {
+      const char* e = getenv("VET_ANALYZE_OVERLAP");
+      return !(e && std::string(e) == "0");
+    }();
+    const bool side = overlap && nf >= 2;
+    cudaStream_t se = side ? h->s_exec : st;
+    if (side) {
+      if (!h->ev_fork) {
+        VET_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        VET_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+      }
+      VET_CUDA(cudaEventRecord(h->ev_fork, st));
+      VET_CUDA(cudaStreamWaitEvent(h->s_exec, h->ev_fork, 0));
+    } else {
+      if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
+                                   hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
+        return rc;
+    }
     if (nf >= 2) {
       vet::TransitionArgs a{};
       a.cell16 = tiles_direct ? asg : (csz == 2 ? (const uint16_t*)h->d_cells : nullptr);
@@ -458,6 +478,13 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
       a.mode = mode;
       a.flags = h->d_flags;
       if (int rc = launch_transition(h, a, nf - 1, U, h->maxT, st)) return rc;
+    }
+    if (side) {
+      if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
+                                   hist0_dev ? hist0_dev + f0 * T0 : nullptr, se))
+        return rc;
+      VET_CUDA(cudaEventRecord(h->ev_join, se));
+      VET_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     }
     if (nf == F - f0) break;
   }

@@ -123,6 +123,13 @@ struct vet_handle {
   void* d_hout[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // entropy, per_k, hist0, assign x2
   size_t hout_bytes[5] = {0, 0, 0, 0, 0};
   cudaStream_t s_copy = nullptr, s_exec = nullptr, s_out = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // vet_analyze: spatial epilogue beside the transition kernel
+  struct T3cOcc {
+    int lw, S;
+    size_t smem;
+    int n;
+  };
+  std::vector<T3cOcc> t3c_occ;  // co-resident clusters of k_transition3c per (LUT variant, cluster size, shared memory)
   int64_t launches = 0;
   // optional per-kernel timing (vet_profile_*): CUDA events recorded around each launch
   bool profiling = false;

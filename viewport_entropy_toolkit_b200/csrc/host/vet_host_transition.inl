@@ -55,6 +55,56 @@ int launch_transition2(vet_handle* h, const vet::TransitionArgs& a, int64_t U, i
   return VET_OK;
 }
 
+// k_transition3c: `rows` clusters of S CTAs, one frame pair each.
+template <int LW>
+int launch_t3c(const vet::Transition3Args& A, int rows, int S, size_t smem, cudaStream_t st, int* max_clusters) {
+  auto* kern = vet::k_transition3c<LW>;
+  VET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(rows * S));
+  cfg.blockDim = dim3(vet::kT3Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)S;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (max_clusters) {  // query only: how many clusters of this shape are co-resident
+    cfg.gridDim = dim3((unsigned)S);
+    if (cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      *max_clusters = 0;
+    }
+    return VET_OK;
+  }
+  VET_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
+  return VET_OK;
+}
+
+int launch_transition3c(int lw, const vet::Transition3Args& A, int rows, int S, size_t smem, cudaStream_t st,
+                        int* max_clusters = nullptr) {
+  switch (lw) {
+    case vet::kLutS8: return launch_t3c<vet::kLutS8>(A, rows, S, smem, st, max_clusters);
+    case vet::kLutS16: return launch_t3c<vet::kLutS16>(A, rows, S, smem, st, max_clusters);
+    case vet::kLutIdentity: return launch_t3c<vet::kLutIdentity>(A, rows, S, smem, st, max_clusters);
+    default: return launch_t3c<vet::kLutG16>(A, rows, S, smem, st, max_clusters);
+  }
+}
+
+// Co-resident clusters of k_transition3c<lw> with S CTAs and `smem` bytes each (cached per handle).
+int t3c_max_clusters(vet_handle* h, int lw, int S, size_t smem) {
+  for (const auto& c : h->t3c_occ)
+    if (c.lw == lw && c.S == S && c.smem == smem) return c.n;
+  int n = 0;
+  vet::Transition3Args none{};
+  if (launch_transition3c(lw, none, 1, S, smem, nullptr, &n) != VET_OK) n = 0;
+  h->t3c_occ.push_back({lw, S, smem, n});
+  return n;
+}
+
 int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st) {
   // capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
   const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)Tmax * Tmax);
@@ -103,6 +153,11 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
   }();
   // two-pass kernel, one launch per tile count; rows it cannot hold (hash overflow) are flagged in d_redo
   // and recomputed by k_transition2 below
+  // VET_T3_CLUSTER=0 keeps every frame pair on k_transition3 (A/B runs, tests)
+  const bool cluster_tail = [] {
+    const char* e = getenv("VET_T3_CLUSTER");
+    return !(e && std::string(e) == "0");
+  }();
   bool redo_only = false;
   if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1 && !force_v2 && a.cell16 && U < ((int64_t)1 << 31)) {
     const size_t budget = h->smem_optin - kStaticSmemSlack;
@@ -200,11 +255,35 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         A3.pair_scratch = h->d_pairs;
         A3.redo = h->d_redo;
         A3.flags = a.flags;
+        // dense tables: the rows % SMs pairs left after the full rounds go to k_transition3c, one pair per
+        // cluster of S CTAs (users split across the cluster) instead of one more, mostly idle, round
+        int64_t tail_rows = 0;
+        int tail_S = 0;
+        if (pl.mode == vet::kT3Dense && cluster_tail) {
+          const int64_t rem = rows % h->sm_count;
+          for (int S = 8; S >= 2 && rem > 0 && !tail_S; S >>= 1)
+            if (U >= (int64_t)S * vet::kT3Threads * 8 && rem <= t3c_max_clusters(h, pl.lw, S, pl.smem)) tail_S = S;
+          if (tail_S) tail_rows = rem;
+        }
+        if (tail_rows) {
+          vet::Transition3Args AT = A3;
+          const int64_t r0 = rows - tail_rows;
+          AT.cell16 = A3.cell16 + r0 * U;
+          AT.F = tail_rows + 1;
+          AT.out = A3.out + r0;
+          AT.prev_count0 = A3.prev_count0 ? A3.prev_count0 + r0 * A3.T : nullptr;
+          AT.pairs0 = A3.pairs0 ? A3.pairs0 + r0 * U * 2 : nullptr;
+          A3.F = r0 + 1;
+          LaunchTimer lt(h, VET_KERNEL_TRANSITION_TAIL, st);
+          if (int rc = launch_transition3c(pl.lw, AT, (int)tail_rows, tail_S, pl.smem, st)) return rc;
+          if (r0 == 0) continue;
+        }
+        const int blocks3k = (int)std::min<int64_t>(A3.F - 1, h->sm_count);
         LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
 #define VET_T3(MODE, LW)                                                                                              \
   do {                                                                                                                \
     VET_CUDA(cudaFuncSetAttribute(vet::k_transition3<MODE, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
-    vet::k_transition3<MODE, LW><<<blocks3, vet::kT3Threads, pl.smem, st>>>(A3);                                      \
+    vet::k_transition3<MODE, LW><<<blocks3k, vet::kT3Threads, pl.smem, st>>>(A3);                                     \
   } while (0)
         if (pl.mode == vet::kT3Dense) {
           if (pl.lw == vet::kLutS8) VET_T3(vet::kT3Dense, vet::kLutS8);
