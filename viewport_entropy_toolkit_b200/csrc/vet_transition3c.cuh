@@ -78,12 +78,20 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3c(Transition3Args 
 
     // ---- pass 1 over this CTA's chunks ----
     uint32_t nvalid = 0;
+    uint4 nvp = make_uint4(0u, 0u, 0u, 0u), nvc = nvp;  // loads of the next step, issued before the updates of this one
+    if (vec && (uint64_t)rank * chunk + tid * 8u < U) {
+      nvp = __ldg(reinterpret_cast<const uint4*>(prow + rank * chunk + tid * 8u));
+      nvc = __ldg(reinterpret_cast<const uint4*>(crow + rank * chunk + tid * 8u));
+    }
     for (uint64_t base = (uint64_t)rank * chunk; base < U; base += (uint64_t)S * chunk) {
       if (vec) {
         const uint32_t u0 = (uint32_t)base + tid * 8u;
+        const uint4 vp = nvp, vc = nvc;
+        if ((uint64_t)u0 + (uint64_t)S * chunk < U) {
+          nvp = __ldg(reinterpret_cast<const uint4*>(prow + u0 + S * chunk));
+          nvc = __ldg(reinterpret_cast<const uint4*>(crow + u0 + S * chunk));
+        }
         if (u0 < U) {
-          const uint4 vp = __ldg(reinterpret_cast<const uint4*>(prow + u0));
-          const uint4 vc = __ldg(reinterpret_cast<const uint4*>(crow + u0));
           const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
           uint32_t pc[8];
 #pragma unroll
@@ -188,12 +196,20 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3c(Transition3Args 
         if (c == ((w >> 14) & kNoTile)) atomicAdd(&s_cl[p], 1u);
       }
     };
+    uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+    if (vec && (uint64_t)rank * chunk + tid * 8u < U) {
+      n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + rank * chunk + tid * 8u));
+      n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + rank * chunk + tid * 8u + 4));
+    }
     for (uint64_t base = (uint64_t)rank * chunk; base < U; base += (uint64_t)S * chunk) {
       if (vec) {
         const uint32_t u0 = (uint32_t)base + tid * 8u;
+        const uint4 a0 = n0, a1 = n1;
+        if ((uint64_t)u0 + (uint64_t)S * chunk < U) {
+          n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + S * chunk));
+          n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + S * chunk + 4));
+        }
         if (u0 < U) {
-          const uint4 a0 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0));
-          const uint4 a1 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + 4));
           second_pass(u0, a0.x);
           second_pass(u0 + 1, a0.y);
           second_pass(u0 + 2, a0.z);
