@@ -174,62 +174,48 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     // ---- pass 1: (prev, cur) tiles of every common user, m_p, A[p][c] ----
     uint32_t nvalid = 0;
     if (vec) {
-      // block-uniform trip count: every lane reaches the __syncwarp that re-joins the warp after the
-      // (divergent) table updates
-      // the rows of 1M-user frames come from DRAM: the loads of step i+1 are issued before the table updates of
-      // step i (ncu: 43 % of the stall samples sat on the first use of these loads).  prefetch.global.L2 2..16
-      // steps further ahead was measured slower (2.13 -> 2.20..2.27 ms on 450 frames of 1M users).
-      uint4 nvp = make_uint4(0u, 0u, 0u, 0u), nvc = nvp;
-      if (tid * 8u < U) {
-        nvp = __ldg(reinterpret_cast<const uint4*>(prow + tid * 8u));
-        nvc = __ldg(reinterpret_cast<const uint4*>(crow + tid * 8u));
-      }
-      for (uint32_t base = 0; base < U; base += kT3Threads * 8u) {
-        const uint32_t u0 = base + tid * 8u;
+      // One step = 8 users per thread.  Block-uniform trip count: every lane reaches the __syncwarp that
+      // re-joins the warp after the (divergent) table updates.
+      auto step = [&](const uint32_t u0, const uint4 vp, const uint4 vc) {
         uint32_t pending = 0u;
         uint32_t pcs[8];
-        const uint4 vp = nvp, vc = nvc;
-        if (u0 + kT3Threads * 8u < U) {
-          nvp = __ldg(reinterpret_cast<const uint4*>(prow + u0 + kT3Threads * 8u));
-          nvc = __ldg(reinterpret_cast<const uint4*>(crow + u0 + kT3Threads * 8u));
-        }
         if (u0 < U) {
-        const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
-        uint32_t pc[8];
+          const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
+          uint32_t pc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t cp = (wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, cc = (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-          const bool ok = cp != 0xFFFFu && cc != 0xFFFFu;
-          pc[j] = ok ? (lut(ok ? cp : 0u) | (lut(ok ? cc : 0u) << 16)) : kNoPair;
-        }
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t cp = (wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, cc = (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+            const bool ok = cp != 0xFFFFu && cc != 0xFFFFu;
+            pc[j] = ok ? (lut(ok ? cp : 0u) | (lut(ok ? cc : 0u) << 16)) : kNoPair;
+          }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pcs[j] = pc[j];
-        *reinterpret_cast<uint4*>(pairs + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
-        *reinterpret_cast<uint4*>(pairs + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
-        if (p0row) {
-          *reinterpret_cast<uint4*>(p0row + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
-          *reinterpret_cast<uint4*>(p0row + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
-        }
-        if (MODE == kT3Dense) {
+          for (int j = 0; j < 8; ++j) pcs[j] = pc[j];
+          *reinterpret_cast<uint4*>(pairs + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
+          *reinterpret_cast<uint4*>(pairs + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
+          if (p0row) {
+            *reinterpret_cast<uint4*>(p0row + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
+            *reinterpret_cast<uint4*>(p0row + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
+          }
+          if (MODE == kT3Dense) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (pc[j] != kNoPair) {
-              const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
-              ++nvalid;
-              t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
-            }
-        } else {
-          // users that stay in their tile (the majority) take the short dense path together; the others are
-          // queued in a bit mask and go through the hash table in a compacted loop below
+            for (int j = 0; j < 8; ++j)
+              if (pc[j] != kNoPair) {
+                const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
+                ++nvalid;
+                t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
+              }
+          } else {
+            // users that stay in their tile (the majority) take the short dense path together; the others are
+            // queued in a bit mask and go through the hash table in a compacted loop below
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (pc[j] != kNoPair) {
-              const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
-              ++nvalid;
-              if (p == c) t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
-              else pending |= 1u << j;
-            }
-        }
+            for (int j = 0; j < 8; ++j)
+              if (pc[j] != kNoPair) {
+                const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
+                ++nvalid;
+                if (p == c) t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
+                else pending |= 1u << j;
+              }
+          }
         }
         if (MODE == kT3Hash) {
           while (__any_sync(kFull, pending != 0u)) {
@@ -245,6 +231,35 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
           }
         }
         __syncwarp();
+      };
+      // The rows of 1M-user frames come from DRAM (ncu: 43 % of the stall samples sat on the first use of the
+      // loads when they were issued in the step that consumes them).  kT3Ring register buffers, the loop unrolled
+      // over them so that no buffer is copied (a rotating copy waits for the youngest load): the rows of step
+      // i + kT3Ring are requested when step i starts.  prefetch.global.L2 further ahead was measured slower.
+      constexpr uint32_t kStep = kT3Threads * 8u;
+      constexpr int kT3Ring = MODE == kT3Dense ? 3 : 2;
+      uint4 bp[kT3Ring], bc[kT3Ring];
+#pragma unroll
+      for (int j = 0; j < kT3Ring; ++j) {
+        bp[j] = bc[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid * 8u + j * kStep < U) {
+          bp[j] = __ldg(reinterpret_cast<const uint4*>(prow + tid * 8u + j * kStep));
+          bc[j] = __ldg(reinterpret_cast<const uint4*>(crow + tid * 8u + j * kStep));
+        }
+      }
+      for (uint32_t base = 0; base < U; base += kT3Ring * kStep) {
+#pragma unroll
+        for (int j = 0; j < kT3Ring; ++j) {
+          if (base + j * kStep < U) {  // block-uniform
+            const uint32_t u0 = base + j * kStep + tid * 8u;
+            const uint4 vp = bp[j], vc = bc[j];
+            if (u0 + kT3Ring * kStep < U) {
+              bp[j] = __ldg(reinterpret_cast<const uint4*>(prow + u0 + kT3Ring * kStep));
+              bc[j] = __ldg(reinterpret_cast<const uint4*>(crow + u0 + kT3Ring * kStep));
+            }
+            step(u0, vp, vc);
+          }
+        }
       }
     } else {
       for (uint32_t base = 0; base < U; base += kT3Threads) {
