@@ -732,21 +732,21 @@ def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs, monkeypatch):
     e = engine(vet, tcs, use_w=False)
     res = {}
     e.profile(True)
-    for cl in ("0", "1"):
+    for cl in ("0", "force"):      # force: also below the frame size from which the host picks it by itself
         monkeypatch.setenv("VET_T3_CLUSTER", cl)
         tr = e.transition(p)
         _, tr2 = e.analyze(p)
         assert e.poll_flags() == 0
         res[cl] = (tr, tr2, e.profile_read()["transition_tail"][1])
     e.profile(False)
-    assert res["0"][2] == 0 and res["1"][2] == 2 * len(tcs), "one cluster launch per tile count and call"
-    for a, b in ((res["0"][0], res["1"][0]), (res["0"][0], res["1"][1])):
+    assert res["0"][2] == 0 and res["force"][2] == 2 * len(tcs), "one cluster launch per tile count and call"
+    for a, b in ((res["0"][0], res["force"][0]), (res["0"][0], res["force"][1])):
         assert torch.equal(a.pairs0, b.pairs0) and torch.equal(a.prev_count0, b.prev_count0)
         assert np.array_equal(a.per_k.cpu().numpy(), b.per_k.cpu().numpy(), equal_nan=True)
         assert np.array_equal(a.entropy.cpu().numpy(), b.entropy.cpu().numpy(), equal_nan=True)
     if F <= 3:
         ref = orc.transition_analyzer(p.cpu().numpy(), W0, H0, tcs, mode="literal")
-        b = res["1"][0]
+        b = res["force"][0]
         assert np.array_equal(b.pairs0.cpu().numpy(), ref["pairs0"])
         assert np.array_equal(b.prev_count0.cpu().numpy(), ref["prev_count0"])
         np.testing.assert_allclose(b.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)

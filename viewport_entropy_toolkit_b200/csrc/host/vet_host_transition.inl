@@ -153,10 +153,11 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
   }();
   // two-pass kernel, one launch per tile count; rows it cannot hold (hash overflow) are flagged in d_redo
   // and recomputed by k_transition2 below
-  // VET_T3_CLUSTER=0 keeps every frame pair on k_transition3 (A/B runs, tests)
-  const bool cluster_tail = [] {
+  // VET_T3_CLUSTER=0 keeps every frame pair on k_transition3 (A/B runs, tests); =force takes the cluster kernel
+  // whenever it can run, also where it does not pay (small frames; tests)
+  const int cluster_tail = [] {
     const char* e = getenv("VET_T3_CLUSTER");
-    return !(e && std::string(e) == "0");
+    return (e && std::string(e) == "0") ? 0 : (e && std::string(e) == "force") ? 2 : 1;
   }();
   bool redo_only = false;
   if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1 && !force_v2 && a.cell16 && U < ((int64_t)1 << 31)) {
@@ -252,7 +253,12 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         A3.out = out_k;
         A3.prev_count0 = k == 0 ? a.prev_count0 : nullptr;
         A3.pairs0 = k == 0 ? a.pairs0 : nullptr;
-        A3.pair_scratch = h->d_pairs;
+        // VET_T3_SCRATCH=1 keeps the pair scratch with the identity table too (A/B runs)
+        const bool keep_scratch = [] {
+          const char* e = getenv("VET_T3_SCRATCH");
+          return e && std::string(e) == "1";
+        }();
+        A3.pair_scratch = (pl.lw == vet::kLutIdentity && !keep_scratch) ? nullptr : h->d_pairs;
         A3.redo = h->d_redo;
         A3.flags = a.flags;
         // dense tables: the rows % SMs pairs left after the full rounds go to k_transition3c, one pair per
@@ -261,12 +267,17 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         int tail_S = 0;
         if (pl.mode == vet::kT3Dense && cluster_tail) {
           const int64_t rem = rows % h->sm_count;
+          // a pair costs ~0.33 ns per user on one CTA; the cluster barriers, the merge of the tables and the extra
+          // launch ~20-40 us: worth it from ~130k users saved per CTA (measured neutral to slower at 100k users)
           for (int S = 8; S >= 2 && rem > 0 && !tail_S; S >>= 1)
-            if (U >= (int64_t)S * vet::kT3Threads * 8 && rem <= t3c_max_clusters(h, pl.lw, S, pl.smem)) tail_S = S;
+            if (U >= (int64_t)S * vet::kT3Threads * 8 && (cluster_tail == 2 || U * (S - 1) >= (int64_t)131072 * S) &&
+                rem <= t3c_max_clusters(h, pl.lw, S, pl.smem))
+              tail_S = S;
           if (tail_S) tail_rows = rem;
         }
         if (tail_rows) {
           vet::Transition3Args AT = A3;
+          AT.pair_scratch = h->d_pairs;
           const int64_t r0 = rows - tail_rows;
           AT.cell16 = A3.cell16 + r0 * U;
           AT.F = tail_rows + 1;

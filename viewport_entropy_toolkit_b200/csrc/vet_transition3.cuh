@@ -52,7 +52,7 @@ struct Transition3Args {
   double* out;             // [F-1] normalised entropy of this tile count
   int32_t* prev_count0;    // [F-1,T] or null
   uint16_t* pairs0;        // [F-1,U,2] or null
-  uint32_t* pair_scratch;  // [gridDim.x, U]
+  uint32_t* pair_scratch;  // [gridDim.x, U]; null with kLutIdentity: pass 2 rebuilds the pairs from the rows (k_transition3 only)
   uint32_t* redo;          // [F-1] rows to be recomputed by k_transition2 (HASH overflow)
   uint32_t* flags;
 };
@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     s_overflow = 0u;
     s_valid = 0u;
   }
-  uint32_t* __restrict__ pairs = a.pair_scratch + (size_t)blockIdx.x * a.U;
+  // Tile ids straight from the streaming kernel (identity LUT): the packed pair of a user is just its two row
+  // entries, so pass 2 re-reads the rows (4 B/user, like the scratch) and pass 1 skips the 4 B/user scratch write.
+  const bool scratch = !(LW == kLutIdentity && a.pair_scratch == nullptr);
+  uint32_t* __restrict__ pairs = scratch ? a.pair_scratch + (size_t)blockIdx.x * a.U : nullptr;
   const uint32_t U = a.U;
   const bool vec = (U & 7u) == 0u;
 
@@ -190,8 +193,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) pcs[j] = pc[j];
-          *reinterpret_cast<uint4*>(pairs + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
-          *reinterpret_cast<uint4*>(pairs + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
+          if (scratch) {
+            *reinterpret_cast<uint4*>(pairs + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
+            *reinterpret_cast<uint4*>(pairs + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
+          }
           if (p0row) {
             *reinterpret_cast<uint4*>(p0row + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
             *reinterpret_cast<uint4*>(p0row + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
         const bool ok = cp != 0xFFFFu && cc != 0xFFFFu;
         const uint32_t pc = ok ? (lut(ok ? cp : 0u) | (lut(ok ? cc : 0u) << 16)) : kNoPair;
         if (u < U) {
-          pairs[u] = pc;
+          if (scratch) pairs[u] = pc;
           if (p0row) p0row[u] = pc;
         }
         if (ok) {
@@ -395,7 +400,30 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
         if (c == ((w >> 14) & kNoTile)) atomicAdd(&s_cl[p], 1u);
       }
     };
-    if (vec) {
+    if (!scratch) {
+      // identity LUT: pairs rebuilt from the two rows
+      auto from_rows = [&](uint32_t cp, uint32_t cc) { return (cp != 0xFFFFu && cc != 0xFFFFu) ? (cp | (cc << 16)) : kNoPair; };
+      if (vec) {
+        uint4 np = make_uint4(0u, 0u, 0u, 0u), nc = np;
+        if (tid * 8u < U) {
+          np = __ldg(reinterpret_cast<const uint4*>(prow + tid * 8u));
+          nc = __ldg(reinterpret_cast<const uint4*>(crow + tid * 8u));
+        }
+        for (uint32_t u0 = tid * 8u; u0 < U; u0 += kT3Threads * 8u) {
+          const uint4 vp = np, vc = nc;
+          if (u0 + kT3Threads * 8u < U) {
+            np = __ldg(reinterpret_cast<const uint4*>(prow + u0 + kT3Threads * 8u));
+            nc = __ldg(reinterpret_cast<const uint4*>(crow + u0 + kT3Threads * 8u));
+          }
+          const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            second_pass(u0 + j, from_rows((wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
+        }
+      } else {
+        for (uint32_t u = tid; u < U; u += kT3Threads) second_pass(u, from_rows(prow[u], crow[u]));
+      }
+    } else if (vec) {
       uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;  // prefetched like in pass 1
       if (tid * 8u < U) {
         n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + tid * 8u));
