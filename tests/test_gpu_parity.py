@@ -740,6 +740,15 @@ def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs, monkeypatch):
         res[cl] = (tr, tr2, e.profile_read()["transition_tail"][1])
     e.profile(False)
     assert res["0"][2] == 0 and res["force"][2] == 2 * len(tcs), "one cluster launch per tile count and call"
+    # the same without the shortcuts of k_transition3: missing-user tests kept for complete frames, pair scratch kept
+    monkeypatch.setenv("VET_T3_CLUSTER", "0")
+    monkeypatch.setenv("VET_T3_NOFULL", "1")
+    monkeypatch.setenv("VET_T3_SCRATCH", "1")
+    plain = e.transition(p)
+    monkeypatch.delenv("VET_T3_NOFULL")
+    monkeypatch.delenv("VET_T3_SCRATCH")
+    assert torch.equal(plain.pairs0, res["0"][0].pairs0) and torch.equal(plain.prev_count0, res["0"][0].prev_count0)
+    assert np.array_equal(plain.entropy.cpu().numpy(), res["0"][0].entropy.cpu().numpy(), equal_nan=True)
     for a, b in ((res["0"][0], res["force"][0]), (res["0"][0], res["force"][1])):
         assert torch.equal(a.pairs0, b.pairs0) and torch.equal(a.prev_count0, b.prev_count0)
         assert np.array_equal(a.per_k.cpu().numpy(), b.per_k.cpu().numpy(), equal_nan=True)

@@ -1,5 +1,5 @@
 """A/B timing of vet_analyze / vet_transition on the configs[4] shard (1M users x 450 frames, 200 tiles, weighted):
-python tools/time_analyze.py [frames] [users].  VET_T3_CLUSTER and VET_T3_SCRATCH are read at every call; VET_ANALYZE_OVERLAP once
+python tools/time_analyze.py [frames] [users].  VET_T3_CLUSTER, VET_T3_SCRATCH and VET_T3_NOFULL are read at every call; VET_ANALYZE_OVERLAP once
 per process (run the script twice for that one)."""
 import os
 import sys
@@ -29,10 +29,13 @@ def timed(fn, n=5):
     return a.elapsed_time(b) / n
 
 
-for cl, scr in (("0", "0"), ("1", "1"), ("1", "0")):
+for cl, scr, nofull in (("0", "0", ""), ("1", "1", "1"), ("1", "0", "1"), ("1", "0", "")):
     os.environ["VET_T3_CLUSTER"] = cl
     os.environ["VET_T3_SCRATCH"] = scr
+    os.environ.pop("VET_T3_NOFULL", None)
+    if nofull:
+        os.environ["VET_T3_NOFULL"] = "1"
     t_an = timed(lambda: eng.analyze(p, want_per_k=False, want_assign0=True, want_pairs0=False))
     t_tr = timed(lambda: eng.transition(p, want_pairs0=False, want_per_k=False))
-    print(f"F={F} U={U} overlap={os.environ.get('VET_ANALYZE_OVERLAP', '1')} cluster={cl} scratch={scr}: "
+    print(f"F={F} U={U} overlap={os.environ.get('VET_ANALYZE_OVERLAP', '1')} cluster={cl} scratch={scr} nofull={nofull or 0}: "
           f"analyze {t_an:.4f} ms, transition {t_tr:.4f} ms", flush=True)

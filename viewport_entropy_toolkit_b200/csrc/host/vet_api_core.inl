@@ -397,6 +397,7 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
     a.pairs0 = pairs0_dev ? pairs0_dev + f0 * U * 2 : nullptr;
     a.mode = mode;
     a.flags = h->d_flags;
+    a.nvalid = h->d_nvalid;  // of this batch, written by the streaming kernel above
     if (int rc = launch_transition(h, a, nf - 1, U, h->maxT, st)) return rc;
     if (nf == F - f0) break;
   }
@@ -477,6 +478,7 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
       a.pairs0 = pairs0_dev ? pairs0_dev + f0 * U * 2 : nullptr;
       a.mode = mode;
       a.flags = h->d_flags;
+      a.nvalid = h->d_nvalid;  // of this batch, written by the streaming kernel above
       if (int rc = launch_transition(h, a, nf - 1, U, h->maxT, st)) return rc;
     }
     if (side) {

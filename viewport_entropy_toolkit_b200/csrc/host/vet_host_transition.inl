@@ -261,6 +261,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         A3.pair_scratch = (pl.lw == vet::kLutIdentity && !keep_scratch) ? nullptr : h->d_pairs;
         A3.redo = h->d_redo;
         A3.flags = a.flags;
+        A3.nvalid = getenv("VET_T3_NOFULL") ? nullptr : a.nvalid;  // VET_T3_NOFULL: always test for missing users (A/B runs)
         // dense tables: the rows % SMs pairs left after the full rounds go to k_transition3c, one pair per
         // cluster of S CTAs (users split across the cluster) instead of one more, mostly idle, round
         int64_t tail_rows = 0;
@@ -278,6 +279,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         if (tail_rows) {
           vet::Transition3Args AT = A3;
           AT.pair_scratch = h->d_pairs;
+          AT.nvalid = nullptr;
           const int64_t r0 = rows - tail_rows;
           AT.cell16 = A3.cell16 + r0 * U;
           AT.F = tail_rows + 1;

@@ -72,6 +72,7 @@ struct TransitionArgs {
   uint16_t* pairs0;        // [F-1,U,2] or null
   int mode;
   uint32_t* flags;
+  const uint32_t* nvalid;  // [F] present users per frame from the streaming kernel of the same batch, or null
   // pair tables: in shared memory (SMEM variant), else one global region per block
   uint32_t cap;            // slots per table (power of two)
   uint32_t* g_tables;      // [gridDim.x, 4, cap] for the global variant (keys pre-set to kEmpty, firsts to kEmpty, counts to 0)

@@ -25,6 +25,8 @@
 // One CTA (1024 threads) per frame pair; users are taken 8 per thread with 128-bit loads when
 // U % 8 == 0, the tile LUT is staged in shared memory when it fits.
 #pragma once
+#include <type_traits>
+
 #include "vet_transition2.cuh"
 
 namespace vet {
@@ -55,6 +57,7 @@ struct Transition3Args {
   uint32_t* pair_scratch;  // [gridDim.x, U]; null with kLutIdentity: pass 2 rebuilds the pairs from the rows (k_transition3 only)
   uint32_t* redo;          // [F-1] rows to be recomputed by k_transition2 (HASH overflow)
   uint32_t* flags;
+  const uint32_t* nvalid;  // [F] present users per frame (streaming kernel), or null: pairs of two complete frames skip the missing-user tests
 };
 
 template <int LW>
@@ -176,7 +179,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
 
     // ---- pass 1: (prev, cur) tiles of every common user, m_p, A[p][c] ----
     uint32_t nvalid = 0;
-    if (vec) {
+    // both frames complete (no missing user): the 0xFFFF tests of both passes drop out (block-uniform)
+    const bool full = a.nvalid && __ldg(a.nvalid + r) == U && __ldg(a.nvalid + r + 1) == U;
+    auto pass1_vec = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
       // One step = 8 users per thread.  Block-uniform trip count: every lane reaches the __syncwarp that
       // re-joins the warp after the (divergent) table updates.
       auto step = [&](const uint32_t u0, const uint4 vp, const uint4 vc) {
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t cp = (wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, cc = (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-            const bool ok = cp != 0xFFFFu && cc != 0xFFFFu;
+            const bool ok = FULL || (cp != 0xFFFFu && cc != 0xFFFFu);
             pc[j] = ok ? (lut(ok ? cp : 0u) | (lut(ok ? cc : 0u) << 16)) : kNoPair;
           }
 #pragma unroll
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
           if (MODE == kT3Dense) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (pc[j] != kNoPair) {
+              if (FULL || pc[j] != kNoPair) {
                 const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
                 ++nvalid;
                 t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
             // queued in a bit mask and go through the hash table in a compacted loop below
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (pc[j] != kNoPair) {
+              if (FULL || pc[j] != kNoPair) {
                 const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
                 ++nvalid;
                 if (p == c) t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
@@ -266,6 +272,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
           }
         }
       }
+    };
+    if (vec) {
+      if (full) pass1_vec(std::true_type{});
+      else pass1_vec(std::false_type{});
     } else {
       for (uint32_t base = 0; base < U; base += kT3Threads) {
         const uint32_t u = base + tid;
@@ -384,8 +394,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     // ---- pass 2: users per previous tile split into cur == c_f / other, occurrences of l'_p, and whether a
     // non-first user of (p, c_f) comes before the first user of l'_p ("early": then l'_p is the latest key).
     // One 32-bit load and one increment per user; the early test stops once its bit is set.
-    auto second_pass = [&](uint32_t u, uint32_t pc) {
-      if (pc == kNoPair) return;
+    auto second_pass = [&](auto full_c, uint32_t u, uint32_t pc) {
+      if (!decltype(full_c)::value && pc == kNoPair) return;
       const uint32_t p = pc & 0xFFFFu, c = pc >> 16;
       const uint32_t w = lds_u32(&s_cfl[p]);
       if (c == (w & kNoTile)) {
@@ -400,53 +410,58 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
         if (c == ((w >> 14) & kNoTile)) atomicAdd(&s_cl[p], 1u);
       }
     };
-    if (!scratch) {
-      // identity LUT: pairs rebuilt from the two rows
-      auto from_rows = [&](uint32_t cp, uint32_t cc) { return (cp != 0xFFFFu && cc != 0xFFFFu) ? (cp | (cc << 16)) : kNoPair; };
-      if (vec) {
-        uint4 np = make_uint4(0u, 0u, 0u, 0u), nc = np;
+    auto pass2 = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
+      if (!scratch) {
+        // identity LUT: pairs rebuilt from the two rows
+        auto from_rows = [&](uint32_t cp, uint32_t cc) { return (FULL || (cp != 0xFFFFu && cc != 0xFFFFu)) ? (cp | (cc << 16)) : kNoPair; };
+        if (vec) {
+          uint4 np = make_uint4(0u, 0u, 0u, 0u), nc = np;
+          if (tid * 8u < U) {
+            np = __ldg(reinterpret_cast<const uint4*>(prow + tid * 8u));
+            nc = __ldg(reinterpret_cast<const uint4*>(crow + tid * 8u));
+          }
+          for (uint32_t u0 = tid * 8u; u0 < U; u0 += kT3Threads * 8u) {
+            const uint4 vp = np, vc = nc;
+            if (u0 + kT3Threads * 8u < U) {
+              np = __ldg(reinterpret_cast<const uint4*>(prow + u0 + kT3Threads * 8u));
+              nc = __ldg(reinterpret_cast<const uint4*>(crow + u0 + kT3Threads * 8u));
+            }
+            const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              second_pass(full_c, u0 + j, from_rows((wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
+          }
+        } else {
+          for (uint32_t u = tid; u < U; u += kT3Threads) second_pass(full_c, u, from_rows(prow[u], crow[u]));
+        }
+      } else if (vec) {
+        uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;  // prefetched like in pass 1
         if (tid * 8u < U) {
-          np = __ldg(reinterpret_cast<const uint4*>(prow + tid * 8u));
-          nc = __ldg(reinterpret_cast<const uint4*>(crow + tid * 8u));
+          n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + tid * 8u));
+          n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + tid * 8u + 4));
         }
         for (uint32_t u0 = tid * 8u; u0 < U; u0 += kT3Threads * 8u) {
-          const uint4 vp = np, vc = nc;
+          const uint4 a0 = n0, a1 = n1;
           if (u0 + kT3Threads * 8u < U) {
-            np = __ldg(reinterpret_cast<const uint4*>(prow + u0 + kT3Threads * 8u));
-            nc = __ldg(reinterpret_cast<const uint4*>(crow + u0 + kT3Threads * 8u));
+            n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + kT3Threads * 8u));
+            n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + kT3Threads * 8u + 4));
           }
-          const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            second_pass(u0 + j, from_rows((wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
+          second_pass(full_c, u0, a0.x);
+          second_pass(full_c, u0 + 1, a0.y);
+          second_pass(full_c, u0 + 2, a0.z);
+          second_pass(full_c, u0 + 3, a0.w);
+          second_pass(full_c, u0 + 4, a1.x);
+          second_pass(full_c, u0 + 5, a1.y);
+          second_pass(full_c, u0 + 6, a1.z);
+          second_pass(full_c, u0 + 7, a1.w);
         }
       } else {
-        for (uint32_t u = tid; u < U; u += kT3Threads) second_pass(u, from_rows(prow[u], crow[u]));
+        for (uint32_t u = tid; u < U; u += kT3Threads) second_pass(full_c, u, __ldcg(pairs + u));
       }
-    } else if (vec) {
-      uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;  // prefetched like in pass 1
-      if (tid * 8u < U) {
-        n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + tid * 8u));
-        n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + tid * 8u + 4));
-      }
-      for (uint32_t u0 = tid * 8u; u0 < U; u0 += kT3Threads * 8u) {
-        const uint4 a0 = n0, a1 = n1;
-        if (u0 + kT3Threads * 8u < U) {
-          n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + kT3Threads * 8u));
-          n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + kT3Threads * 8u + 4));
-        }
-        second_pass(u0, a0.x);
-        second_pass(u0 + 1, a0.y);
-        second_pass(u0 + 2, a0.z);
-        second_pass(u0 + 3, a0.w);
-        second_pass(u0 + 4, a1.x);
-        second_pass(u0 + 5, a1.y);
-        second_pass(u0 + 6, a1.z);
-        second_pass(u0 + 7, a1.w);
-      }
-    } else {
-      for (uint32_t u = tid; u < U; u += kT3Threads) second_pass(u, __ldcg(pairs + u));
-    }
+    };
+    if (full) pass2(std::true_type{});
+    else pass2(std::false_type{});
     __syncthreads();
 
     // ---- EU:297-330 ----
