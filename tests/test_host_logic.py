@@ -31,6 +31,10 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in declared:
         assert getattr(lib, name) is not None
     assert b"sm_100a" in lib.vet_version()
+    # the profile slots of vet_profile_read: same order and count as the header's VET_KERNEL_* enum
+    slots = re.findall(r"\bVET_KERNEL_([A-Z_]+)\s*=\s*(\d+)", header)
+    assert [n.lower() for n, _ in slots if n != "COUNT"] == list(_native.KERNEL_NAMES)
+    assert dict(slots)["COUNT"] == str(len(_native.KERNEL_NAMES))
     # argument validation happens before any CUDA call
     h = ctypes.c_void_p()
     assert lib.vet_create(ctypes.byref(h), None) == _native.VET_ERR_INVALID_ARG
