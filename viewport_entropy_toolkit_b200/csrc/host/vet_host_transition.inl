@@ -278,9 +278,8 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         }
         if (tail_rows) {
           vet::Transition3Args AT = A3;
-          AT.pair_scratch = h->d_pairs;
-          AT.nvalid = nullptr;
           const int64_t r0 = rows - tail_rows;
+          AT.nvalid = A3.nvalid ? A3.nvalid + r0 : nullptr;
           AT.cell16 = A3.cell16 + r0 * U;
           AT.F = tail_rows + 1;
           AT.out = A3.out + r0;

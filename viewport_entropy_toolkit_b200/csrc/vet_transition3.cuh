@@ -54,7 +54,7 @@ struct Transition3Args {
   double* out;             // [F-1] normalised entropy of this tile count
   int32_t* prev_count0;    // [F-1,T] or null
   uint16_t* pairs0;        // [F-1,U,2] or null
-  uint32_t* pair_scratch;  // [gridDim.x, U]; null with kLutIdentity: pass 2 rebuilds the pairs from the rows (k_transition3 only)
+  uint32_t* pair_scratch;  // [gridDim.x, U]; null with kLutIdentity: pass 2 rebuilds the pairs from the rows
   uint32_t* redo;          // [F-1] rows to be recomputed by k_transition2 (HASH overflow)
   uint32_t* flags;
   const uint32_t* nvalid;  // [F] present users per frame (streaming kernel), or null: pairs of two complete frames skip the missing-user tests

@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3c(Transition3Args 
     lut.p = smem_raw + a.lut_off;
   }
   if (tid == 0) s_valid = 0u;
-  uint32_t* __restrict__ pairs = a.pair_scratch + (size_t)cid * a.U;  // one row per cluster, chunks owned by their CTA
+  // identity LUT without a scratch: pass 2 rebuilds the pairs from the two tile-id rows (see k_transition3)
+  const bool scratch = !(LW == kLutIdentity && a.pair_scratch == nullptr);
+  uint32_t* __restrict__ pairs = scratch ? a.pair_scratch + (size_t)cid * a.U : nullptr;  // one row per cluster, chunks owned by their CTA
   const uint32_t U = a.U;
   const bool vec = (U & 7u) == 0u;
   const uint32_t chunk = vec ? kT3Threads * 8u : kT3Threads;  // users per CTA step; chunk i belongs to CTA i % S
@@ -78,57 +80,66 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3c(Transition3Args 
 
     // ---- pass 1 over this CTA's chunks ----
     uint32_t nvalid = 0;
-    uint4 nvp = make_uint4(0u, 0u, 0u, 0u), nvc = nvp;  // loads of the next step, issued before the updates of this one
-    if (vec && (uint64_t)rank * chunk + tid * 8u < U) {
-      nvp = __ldg(reinterpret_cast<const uint4*>(prow + rank * chunk + tid * 8u));
-      nvc = __ldg(reinterpret_cast<const uint4*>(crow + rank * chunk + tid * 8u));
-    }
-    for (uint64_t base = (uint64_t)rank * chunk; base < U; base += (uint64_t)S * chunk) {
-      if (vec) {
-        const uint32_t u0 = (uint32_t)base + tid * 8u;
-        const uint4 vp = nvp, vc = nvc;
-        if ((uint64_t)u0 + (uint64_t)S * chunk < U) {
-          nvp = __ldg(reinterpret_cast<const uint4*>(prow + u0 + S * chunk));
-          nvc = __ldg(reinterpret_cast<const uint4*>(crow + u0 + S * chunk));
-        }
-        if (u0 < U) {
-          const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
-          uint32_t pc[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t cp = (wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, cc = (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-            const bool ok = cp != 0xFFFFu && cc != 0xFFFFu;
-            pc[j] = ok ? (lut(ok ? cp : 0u) | (lut(ok ? cc : 0u) << 16)) : kNoPair;
-          }
-          *reinterpret_cast<uint4*>(pairs + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
-          *reinterpret_cast<uint4*>(pairs + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
-          if (p0row) {
-            *reinterpret_cast<uint4*>(p0row + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
-            *reinterpret_cast<uint4*>(p0row + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (pc[j] != kNoPair) {
-              ++nvalid;
-              t3_update<kT3Dense>(s_tab, nullptr, T, pc[j] & 0xFFFFu, pc[j] >> 16, u0 + j, nullptr, nullptr);
-            }
-        }
-      } else {
-        const uint32_t u = (uint32_t)base + tid;
-        const uint32_t cp = u < U ? prow[u] : 0xFFFFu, cc = u < U ? crow[u] : 0xFFFFu;
-        const bool ok = cp != 0xFFFFu && cc != 0xFFFFu;
-        const uint32_t pc = ok ? (lut(ok ? cp : 0u) | (lut(ok ? cc : 0u) << 16)) : kNoPair;
-        if (u < U) {
-          pairs[u] = pc;
-          if (p0row) p0row[u] = pc;
-        }
-        if (ok) {
-          ++nvalid;
-          t3_update<kT3Dense>(s_tab, nullptr, T, pc & 0xFFFFu, pc >> 16, u, nullptr, nullptr);
-        }
+    // both frames complete (no missing user): the 0xFFFF tests of both passes drop out (block- and cluster-uniform)
+    const bool full = a.nvalid && __ldg(a.nvalid + r) == U && __ldg(a.nvalid + r + 1) == U;
+    auto pass1 = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
+      uint4 nvp = make_uint4(0u, 0u, 0u, 0u), nvc = nvp;  // loads of the next step, issued before the updates of this one
+      if (vec && (uint64_t)rank * chunk + tid * 8u < U) {
+        nvp = __ldg(reinterpret_cast<const uint4*>(prow + rank * chunk + tid * 8u));
+        nvc = __ldg(reinterpret_cast<const uint4*>(crow + rank * chunk + tid * 8u));
       }
-      __syncwarp();
-    }
+      for (uint64_t base = (uint64_t)rank * chunk; base < U; base += (uint64_t)S * chunk) {
+        if (vec) {
+          const uint32_t u0 = (uint32_t)base + tid * 8u;
+          const uint4 vp = nvp, vc = nvc;
+          if ((uint64_t)u0 + (uint64_t)S * chunk < U) {
+            nvp = __ldg(reinterpret_cast<const uint4*>(prow + u0 + S * chunk));
+            nvc = __ldg(reinterpret_cast<const uint4*>(crow + u0 + S * chunk));
+          }
+          if (u0 < U) {
+            const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
+            uint32_t pc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t cp = (wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, cc = (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+              const bool ok = FULL || (cp != 0xFFFFu && cc != 0xFFFFu);
+              pc[j] = ok ? (lut(ok ? cp : 0u) | (lut(ok ? cc : 0u) << 16)) : kNoPair;
+            }
+            if (scratch) {
+              *reinterpret_cast<uint4*>(pairs + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
+              *reinterpret_cast<uint4*>(pairs + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
+            }
+            if (p0row) {
+              *reinterpret_cast<uint4*>(p0row + u0) = make_uint4(pc[0], pc[1], pc[2], pc[3]);
+              *reinterpret_cast<uint4*>(p0row + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (FULL || pc[j] != kNoPair) {
+                ++nvalid;
+                t3_update<kT3Dense>(s_tab, nullptr, T, pc[j] & 0xFFFFu, pc[j] >> 16, u0 + j, nullptr, nullptr);
+              }
+          }
+        } else {
+          const uint32_t u = (uint32_t)base + tid;
+          const uint32_t cp = u < U ? prow[u] : 0xFFFFu, cc = u < U ? crow[u] : 0xFFFFu;
+          const bool ok = cp != 0xFFFFu && cc != 0xFFFFu;
+          const uint32_t pc = ok ? (lut(ok ? cp : 0u) | (lut(ok ? cc : 0u) << 16)) : kNoPair;
+          if (u < U) {
+            if (scratch) pairs[u] = pc;
+            if (p0row) p0row[u] = pc;
+          }
+          if (ok) {
+            ++nvalid;
+            t3_update<kT3Dense>(s_tab, nullptr, T, pc & 0xFFFFu, pc >> 16, u, nullptr, nullptr);
+          }
+        }
+        __syncwarp();
+      }
+    };
+    if (full) pass1(std::true_type{});
+    else pass1(std::false_type{});
     nvalid = __reduce_add_sync(kFull, nvalid);
     if (lane == 0 && nvalid) atomicAdd(&s_valid, nvalid);
     cluster.sync();  // every table of the cluster is complete
@@ -180,8 +191,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3c(Transition3Args 
     cluster.sync();
 
     // ---- pass 2 over this CTA's chunks (see k_transition3) ----
-    auto second_pass = [&](uint32_t u, uint32_t pc) {
-      if (pc == kNoPair) return;
+    auto second_pass = [&](auto full_c, uint32_t u, uint32_t pc) {
+      if (!decltype(full_c)::value && pc == kNoPair) return;
       const uint32_t p = pc & 0xFFFFu, c = pc >> 16;
       const uint32_t w = lds_u32(&s_cfl[p]);
       if (c == (w & kNoTile)) {
@@ -196,34 +207,47 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3c(Transition3Args 
         if (c == ((w >> 14) & kNoTile)) atomicAdd(&s_cl[p], 1u);
       }
     };
-    uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
-    if (vec && (uint64_t)rank * chunk + tid * 8u < U) {
-      n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + rank * chunk + tid * 8u));
-      n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + rank * chunk + tid * 8u + 4));
-    }
-    for (uint64_t base = (uint64_t)rank * chunk; base < U; base += (uint64_t)S * chunk) {
-      if (vec) {
-        const uint32_t u0 = (uint32_t)base + tid * 8u;
-        const uint4 a0 = n0, a1 = n1;
-        if ((uint64_t)u0 + (uint64_t)S * chunk < U) {
-          n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + S * chunk));
-          n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + S * chunk + 4));
-        }
-        if (u0 < U) {
-          second_pass(u0, a0.x);
-          second_pass(u0 + 1, a0.y);
-          second_pass(u0 + 2, a0.z);
-          second_pass(u0 + 3, a0.w);
-          second_pass(u0 + 4, a1.x);
-          second_pass(u0 + 5, a1.y);
-          second_pass(u0 + 6, a1.z);
-          second_pass(u0 + 7, a1.w);
-        }
-      } else {
-        const uint32_t u = (uint32_t)base + tid;
-        if (u < U) second_pass(u, __ldcg(pairs + u));
+    auto pass2 = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
+      // without the scratch the two row loads stand in for the two halves of the 8 packed pairs
+      const uint4* __restrict__ src0 = scratch ? nullptr : reinterpret_cast<const uint4*>(prow);
+      const uint4* __restrict__ src1 = scratch ? nullptr : reinterpret_cast<const uint4*>(crow);
+      auto load0 = [&](uint32_t u0) { return scratch ? __ldcg(reinterpret_cast<const uint4*>(pairs + u0)) : __ldg(src0 + (u0 >> 3)); };
+      auto load1 = [&](uint32_t u0) { return scratch ? __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + 4)) : __ldg(src1 + (u0 >> 3)); };
+      auto from_rows = [&](uint32_t cp, uint32_t cc) { return (FULL || (cp != 0xFFFFu && cc != 0xFFFFu)) ? (cp | (cc << 16)) : kNoPair; };
+      uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+      if (vec && (uint64_t)rank * chunk + tid * 8u < U) {
+        n0 = load0(rank * chunk + tid * 8u);
+        n1 = load1(rank * chunk + tid * 8u);
       }
-    }
+      for (uint64_t base = (uint64_t)rank * chunk; base < U; base += (uint64_t)S * chunk) {
+        if (vec) {
+          const uint32_t u0 = (uint32_t)base + tid * 8u;
+          const uint4 a0 = n0, a1 = n1;
+          if ((uint64_t)u0 + (uint64_t)S * chunk < U) {
+            n0 = load0(u0 + S * chunk);
+            n1 = load1(u0 + S * chunk);
+          }
+          if (u0 < U) {
+            if (scratch) {
+              const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+              for (int q = 0; q < 8; ++q) second_pass(full_c, u0 + q, w[q]);
+            } else {
+              const uint32_t wp[4] = {a0.x, a0.y, a0.z, a0.w}, wc[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                second_pass(full_c, u0 + q, from_rows((wp[q >> 1] >> (16 * (q & 1))) & 0xFFFFu, (wc[q >> 1] >> (16 * (q & 1))) & 0xFFFFu));
+            }
+          }
+        } else {
+          const uint32_t u = (uint32_t)base + tid;
+          if (u < U) second_pass(full_c, u, scratch ? __ldcg(pairs + u) : from_rows(prow[u], crow[u]));
+        }
+      }
+    };
+    if (full) pass2(std::true_type{});
+    else pass2(std::false_type{});
     cluster.sync();  // every CTA's partial counts are complete
 
     // ---- EU:297-330, CTA 0 over the partial counts of the cluster ----
