@@ -20,6 +20,10 @@ def packed(F, U, dtype=np.float32):
 e = Engine(100, 200, [200, 20], EntropyConfig(fov_angle=90.0))
 r = e.spatial(packed(70, 2501))                     # k_stream_tma (odd U: unaligned tile heads) + k_whist + k_entropy_rows
 t = e.transition(packed(4, 9000))                   # k_stream_tma<cells> + k_transition3 (dense) per tile count + k_mean_rows
+os.environ["VET_T3_CLUSTER"] = "force"
+tc = e.transition(packed(3, 16384))                 # k_transition3c: a frame pair per cluster of 2 CTAs (tables merged through DSMEM)
+sa, ta = e.analyze(packed(3, 16384))                # the same with the spatial epilogue on the side stream beside it
+del os.environ["VET_T3_CLUSTER"]
 os.environ["VET_WHIST_IMPL"] = "i8"
 hot = packed(140, 2504)
 hot[:, :600, 1:] = 0.5                              # 600 users in one cell: second count plane
@@ -53,4 +57,4 @@ r9 = e.spatial(packed(2, 300))                      # direct regime: k_decode + 
 e.close()
 torch.cuda.synchronize()
 print("sanitize case ok", float(r.entropy[0]), float(t.entropy[0]), float(r2.entropy[0]), float(r3.entropy[0]),
-      float(t2.entropy[0]), float(t3.entropy[0]), float(r4.entropy[0]))
+      float(t2.entropy[0]), float(t3.entropy[0]), float(r4.entropy[0]), float(tc.entropy[0]), float(ta.entropy[0]))
