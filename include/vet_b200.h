@@ -179,7 +179,9 @@ int vet_transition(vet_handle* h, const void* packed_dev, int dtype, int64_t F, 
  * transition entropy"): the streaming kernel emits the cell histogram, the tile assignment and the
  * cell ids together, then the spatial epilogue and the transition kernel run on them.  Outputs as in
  * vet_spatial (sp_*, hist0, assign0) and vet_transition (tr_*, prev_count0, pairs0); optional ones may
- * be NULL.  Equivalent to calling vet_spatial and vet_transition, minus one read of the input. */
+ * be NULL.  Equivalent to calling vet_spatial and vet_transition, minus one read of the input.
+ * The spatial epilogue runs on a stream owned by the handle, forked from and joined back into
+ * `stream` with events inside the call: for the caller everything is ordered on `stream`. */
 int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U,
                 double* sp_entropy_dev, double* sp_per_k_dev, double* hist0_dev, uint16_t* assign0_dev,
                 double* tr_entropy_dev, double* tr_per_k_dev, int32_t* prev_count0_dev,
