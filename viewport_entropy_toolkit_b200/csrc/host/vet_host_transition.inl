@@ -214,7 +214,15 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
     }
     if (ok) {
       const int blocks3 = (int)std::min<int64_t>(rows, h->sm_count);
-      if (int rc = grow((void**)&h->d_pairs, &h->pairs_bytes, (size_t)std::max(blocks, blocks3) * U * 4)) return rc;
+      // VET_T3_SCRATCH=1 keeps the pair scratch with the identity table too (A/B runs)
+      const bool keep_scratch = [] {
+        const char* e = getenv("VET_T3_SCRATCH");
+        return e && std::string(e) == "1";
+      }();
+      bool need_scratch = keep_scratch;  // packed (prev | cur << 16) per user, one row per CTA: not with the identity table
+      for (int k = 0; k < a.K; ++k) need_scratch = need_scratch || (plan[k].mode >= 0 && plan[k].lw != vet::kLutIdentity);
+      if (need_scratch)
+        if (int rc = grow((void**)&h->d_pairs, &h->pairs_bytes, (size_t)std::max(blocks, blocks3) * U * 4)) return rc;
       if (int rc = grow((void**)&h->d_redo, &h->redo_bytes, (size_t)rows * 4)) return rc;
       VET_CUDA(cudaMemsetAsync(h->d_redo, 0, (size_t)rows * 4, st));
       double* per_k = a.per_k;
@@ -253,11 +261,6 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         A3.out = out_k;
         A3.prev_count0 = k == 0 ? a.prev_count0 : nullptr;
         A3.pairs0 = k == 0 ? a.pairs0 : nullptr;
-        // VET_T3_SCRATCH=1 keeps the pair scratch with the identity table too (A/B runs)
-        const bool keep_scratch = [] {
-          const char* e = getenv("VET_T3_SCRATCH");
-          return e && std::string(e) == "1";
-        }();
         A3.pair_scratch = (pl.lw == vet::kLutIdentity && !keep_scratch) ? nullptr : h->d_pairs;
         A3.redo = h->d_redo;
         A3.flags = a.flags;
