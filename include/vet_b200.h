@@ -90,10 +90,37 @@ typedef struct {
    * 360 % tile_width == 0 and 180 % tile_height == 0 are required (EU:414-417). */
   int32_t naive_tile_width;
   int32_t naive_tile_height;
+  /* VET_REGIME_AUTO (0): cell tables whenever the video is small enough for them.  VET_REGIME_DIRECT: evaluate
+   * every (sample, tile) pair in fp64 without cell tables (the regime of videos too large for the tables; exact,
+   * O(users x tiles) per frame) -- what the parity suite compares the table regimes against. */
+  int32_t regime;
 } vet_config;
+
+enum { VET_REGIME_AUTO = 0, VET_REGIME_DIRECT = 1 };
 
 const char* vet_last_error(void);
 const char* vet_version(void);
+
+/* Kernel selection per handle.  The library chooses among its kernels by problem size; an option pins the
+ * choice.  Production leaves every option at its default (0 unless stated).  VET_OPT_WEIGHTED_KERNEL is
+ * the one a caller may want: the FOV-weighted histogram has two precision modes (see vet_spatial) and results
+ * are bit-reproducible across different frame batchings / shardings only when one mode is pinned.  The others exist
+ * so that the parity suite can run the kernel generations against each other bit for bit.  The library reads no
+ * environment variable. */
+enum {
+  VET_OPT_WEIGHTED_KERNEL = 0,   /* 0 auto (tensor cores from 512 frames per call), 1 FP64 pipe, 2 tensor cores (int8 slices) */
+  VET_OPT_STREAM_KERNEL = 1,     /* 0 auto, 1 plain loads (k_stream_simple), 2 cell histograms only (no direct tile
+                                    histograms), 3 global-table regime without the 16-bit privatised histogram */
+  VET_OPT_TRANSITION_KERNEL = 2, /* 0 auto (two-pass kernels), 1 k_transition, 2 k_transition2 */
+  VET_OPT_CLUSTER_TAIL = 3,      /* default 1: pairs left after the full rounds go to the cluster kernel when it pays;
+                                    0 never, 2 whenever it can run */
+  VET_OPT_T3_PAIR_SCRATCH = 4,   /* 1: keep the 4 B/user pair scratch also when the rows hold tile ids */
+  VET_OPT_T3_ASSUME_MISSING = 5, /* 1: always test for missing users (no complete-frame variant) */
+  VET_OPT_ANALYZE_OVERLAP = 6,   /* default 1: vet_analyze overlaps its spatial and transition stages; 0 runs them in sequence */
+  VET_OPT_COUNT = 7
+};
+int vet_set_option(vet_handle* h, int option, int value);
+int vet_get_option(const vet_handle* h, int option, int* value);
 
 /* Replaces SpatialEntropyAnalyzer.__init__ / TransitionEntropyAnalyzer.__init__
  * (SA:53-66, TA:53-66): validates the configuration, builds the Fibonacci
@@ -136,6 +163,11 @@ int vet_tile_weights(vet_handle* h, int k, const double* vec_dev, int64_t n, dou
  * radians (the reference returns [tile_index, distance] pairs; the index is the column). */
 int vet_angular_distances(vet_handle* h, int k, const double* vec_dev, int64_t n, double* d_dev,
                           void* stream);
+
+/* vector_angle_distance (EU:41-67) for n independent pairs: d_dev[i] = arccos(clip(dot(a_i/|a_i|, b_i/|b_i|))), radians.
+ * Uses the handle only for its device (no tables): one handle serves any number of distinct vectors. */
+int vet_vector_angles(vet_handle* h, const double* a_dev, const double* b_dev, int64_t n, double* d_dev,
+                      void* stream);
 
 /* compute_spatial_entropy (EU:147-211) for frames of ARBITRARY direction vectors:
  * vec_dev[F,U,3] float64, NaN = absent user.  Same outputs as vet_spatial.  Every

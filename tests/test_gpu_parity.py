@@ -455,17 +455,15 @@ def test_functional_api_arbitrary_centres(vet):
 
 @pytest.mark.parametrize("dims,regime", [((200, 400), "global"), ((200, 400), "direct"), ((1920, 1080), "direct"),
                                          ((1920, 1080), "global")])   # 2M cells: global LUTs when unweighted, else direct
-def test_large_video_direct_mode(vet, dims, regime, monkeypatch):
+def test_large_video_direct_mode(vet, dims, regime):
     """Videos whose cell grid does not fit the shared-memory tables: up to 262,144 cells (the 200x400 of the
     reference's README) the per-cell tables stay in global memory (k_stream_global + the usual epilogues),
-    beyond that -- or with VET_REGIME=direct -- the direct per-sample path (decode -> vectors -> brute force)
+    beyond that -- or with regime="direct" (vet_config.regime) -- the direct per-sample path (decode -> vectors -> brute force)
     runs; results must match the oracle all the same."""
     W, H = dims
-    if regime == "direct":
-        monkeypatch.setenv("VET_REGIME", "direct")   # read when the handle is created
     p = synth(4, 300, 4242, iid=True, missing=0.1, dtype=np.float64)
     for use_w, tcs in ((True, [20, 50]), (False, [200])):
-        e = engine(vet, tcs, fov=100.0, use_w=use_w, W=W, H=H)
+        e = engine(vet, tcs, fov=100.0, use_w=use_w, W=W, H=H, regime="direct" if regime == "direct" else "auto")
         sp = e.spatial(dev(p))
         assert e.poll_flags() == 0
         ref = orc.spatial_analyzer(p, W, H, tcs, 100.0, use_w, 2.0)
@@ -623,8 +621,8 @@ def test_full_size_properties_configs2(vet):
 # tensor-core weighted histogram (k_whist_i8): exact integer GEMM over count byte planes and
 # 39-bit fixed-point weight slices.  Stated tolerance of this path: entropies 1e-9 relative
 # (north_star); weighted histogram entries |d| <= users * 2^-40 absolute (weight quantisation)
-# on top of the 1e-9 relative bar.  VET_WHIST_IMPL forces the kernel for frame counts below
-# the heuristic threshold; it is read at every call.
+# on top of the 1e-9 relative bar.  The handle option "weighted_kernel" (vet_set_option) forces the
+# kernel for frame counts below the heuristic threshold.
 # ---------------------------------------------------------------------------------
 I8_QUANT = 2.0 ** -40
 
@@ -638,11 +636,11 @@ I8_QUANT = 2.0 ** -40
     dict(F=131, U=257, tcs=[200, 50], fov=90.0, iid=True, missing=0.05),  # two frame blocks, partial second one
     dict(F=3, U=70000, tcs=[200], fov=90.0, iid=True),                  # frames in several chunks: k_cnt_planes
 ])
-def test_weighted_tensor_core_path_vs_oracle(vet, cfg, monkeypatch):
-    monkeypatch.setenv("VET_WHIST_IMPL", "i8")
+def test_weighted_tensor_core_path_vs_oracle(vet, cfg):
     p = synth(cfg["F"], cfg["U"], 4100 + cfg["U"], cfg.get("iid", False), cfg.get("missing", 0.0))
     pf = cfg.get("pf", 2.0)
     e = engine(vet, cfg["tcs"], cfg["fov"], True, pf)
+    e.set_option("weighted_kernel", "i8")
     sp = e.spatial(dev(p))
     assert e.poll_flags() == 0
     ref = orc.spatial_analyzer(p, W0, H0, cfg["tcs"], cfg["fov"], True, pf)
@@ -650,14 +648,14 @@ def test_weighted_tensor_core_path_vs_oracle(vet, cfg, monkeypatch):
     np.testing.assert_allclose(sp.hist0.cpu().numpy(), ref["hist0"], rtol=RTOL, atol=cfg["U"] * I8_QUANT)
     np.testing.assert_allclose(sp.per_k.cpu().numpy(), ref["per_k"], rtol=RTOL, atol=ATOL, equal_nan=True)
     np.testing.assert_allclose(sp.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
-    monkeypatch.setenv("VET_WHIST_IMPL", "fp64")
+    e.set_option("weighted_kernel", "fp64")
     sp64 = e.spatial(dev(p))
     np.testing.assert_allclose(sp.hist0.cpu().numpy(), sp64.hist0.cpu().numpy(), rtol=RTOL, atol=cfg["U"] * I8_QUANT)
     np.testing.assert_allclose(sp.entropy.cpu().numpy(), sp64.entropy.cpu().numpy(), rtol=RTOL, atol=ATOL, equal_nan=True)
     e.close()
 
 
-def test_weighted_tensor_core_count_planes(vet, monkeypatch):
+def test_weighted_tensor_core_count_planes(vet):
     """Counts of 256 and more (second byte plane) and of 65536 and more (third plane, second GEMM
     pass), rows of the higher planes left dirty by one call and cleaned by the next, analyze() ==
     spatial(); all against the FP64 kernel on the same input."""
@@ -672,7 +670,7 @@ def test_weighted_tensor_core_count_planes(vet, monkeypatch):
     cold = bench.synth_on_device(torch, F - 60, U, 4243, torch.device("cuda"))
     res = {}
     for impl in ("fp64", "i8"):
-        monkeypatch.setenv("VET_WHIST_IMPL", impl)
+        e.set_option("weighted_kernel", impl)
         a = e.spatial(hot)
         b = e.spatial(cold)          # same plane rows as `hot`, now without large counts
         c, _ = e.analyze(hot)
@@ -691,7 +689,7 @@ def test_weighted_tensor_core_count_planes(vet, monkeypatch):
 
 
 @pytest.mark.parametrize("U", [100_000, 20_001])
-def test_transition_two_pass_kernel_equals_three_pass_kernel(vet, U, monkeypatch):
+def test_transition_two_pass_kernel_equals_three_pass_kernel(vet, U):
     """k_transition3 (two passes, one launch per tile count; dense table for 201 tiles, shared-memory
     hash for 501/1001, rows that overflow it handed to k_transition2) against k_transition2 alone on
     frames too large for the oracle: counts and pairs bit-exact, entropies to 1e-12."""
@@ -704,7 +702,7 @@ def test_transition_two_pass_kernel_equals_three_pass_kernel(vet, U, monkeypatch
     e = engine(vet, [200, 500, 1000], use_w=False)
     res = {}
     for impl in ("v2", "v3"):
-        monkeypatch.setenv("VET_TRANSITION_IMPL", impl)
+        e.set_option("transition_kernel", "v2" if impl == "v2" else "auto")
         res[impl] = e.transition(p)
         assert e.poll_flags() == 0
     a, b = res["v2"], res["v3"]
@@ -720,7 +718,7 @@ def test_transition_two_pass_kernel_equals_three_pass_kernel(vet, U, monkeypatch
     (152, 16_384, [200]),        # 151 pairs: one full round of k_transition3 + 3 pairs on clusters of 2
     (21, 131_072, [100, 200]),   # 20 pairs: more than the co-resident clusters of 8
 ])
-def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs, monkeypatch):
+def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs):
     """k_transition3c (the users of one frame pair split over a thread-block cluster, for the pairs left after
     the full rounds) against k_transition3 alone: every output bit for bit, transition() and analyze();
     the small cases also against the oracle."""
@@ -733,7 +731,7 @@ def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs, monkeypatch):
     res = {}
     e.profile(True)
     for cl in ("0", "force"):      # force: also below the frame size from which the host picks it by itself
-        monkeypatch.setenv("VET_T3_CLUSTER", cl)
+        e.set_option("cluster_tail", "off" if cl == "0" else "force")
         tr = e.transition(p)
         _, tr2 = e.analyze(p)
         assert e.poll_flags() == 0
@@ -741,12 +739,12 @@ def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs, monkeypatch):
     e.profile(False)
     assert res["0"][2] == 0 and res["force"][2] == 2 * len(tcs), "one cluster launch per tile count and call"
     # the same without the shortcuts of k_transition3: missing-user tests kept for complete frames, pair scratch kept
-    monkeypatch.setenv("VET_T3_CLUSTER", "0")
-    monkeypatch.setenv("VET_T3_NOFULL", "1")
-    monkeypatch.setenv("VET_T3_SCRATCH", "1")
+    e.set_option("cluster_tail", "off")
+    e.set_option("t3_assume_missing", "on")
+    e.set_option("t3_pair_scratch", "on")
     plain = e.transition(p)
-    monkeypatch.delenv("VET_T3_NOFULL")
-    monkeypatch.delenv("VET_T3_SCRATCH")
+    e.set_option("t3_assume_missing", "off")
+    e.set_option("t3_pair_scratch", "off")
     assert torch.equal(plain.pairs0, res["0"][0].pairs0) and torch.equal(plain.prev_count0, res["0"][0].prev_count0)
     assert np.array_equal(plain.entropy.cpu().numpy(), res["0"][0].entropy.cpu().numpy(), equal_nan=True)
     for a, b in ((res["0"][0], res["force"][0]), (res["0"][0], res["force"][1])):
@@ -941,7 +939,7 @@ def test_full_size_properties_configs4_shard(vet):
     e.close()
 
 
-def test_global_table_regime_at_scale(vet, monkeypatch):
+def test_global_table_regime_at_scale(vet):
     """200x400 video (80,601 cells: global-table regime) with enough frames for the tensor-core weighted
     histogram (K = 80,640 cells) and the FP64 one: against the oracle, against each other, and the float32 /
     several-tile-count / analyze() variants against the per-sample direct regime."""
@@ -955,9 +953,8 @@ def test_global_table_regime_at_scale(vet, monkeypatch):
     assert np.array_equal(a.assign0.cpu().numpy()[sel], ref["assign0"])
     np.testing.assert_allclose(a.hist0.cpu().numpy()[sel], ref["hist0"], rtol=RTOL, atol=700 * I8_QUANT)
     np.testing.assert_allclose(a.entropy.cpu().numpy()[sel], ref["entropy"], rtol=RTOL, atol=ATOL)
-    monkeypatch.setenv("VET_WHIST_IMPL", "fp64")
+    e.set_option("weighted_kernel", "fp64")
     b = e.spatial(dev(p))
-    monkeypatch.delenv("VET_WHIST_IMPL")
     np.testing.assert_allclose(a.hist0.cpu().numpy(), b.hist0.cpu().numpy(), rtol=RTOL, atol=700 * I8_QUANT)
     np.testing.assert_allclose(a.entropy.cpu().numpy(), b.entropy.cpu().numpy(), rtol=RTOL, atol=0)
     e.close()
@@ -966,9 +963,7 @@ def test_global_table_regime_at_scale(vet, monkeypatch):
         g = engine(vet, tcs, fov=120.0, use_w=use_w, W=W, H=H)
         sp, tr = g.analyze(dev(q))
         assert g.poll_flags() == 0
-        monkeypatch.setenv("VET_REGIME", "direct")
-        d = engine(vet, tcs, fov=120.0, use_w=use_w, W=W, H=H)
-        monkeypatch.delenv("VET_REGIME")
+        d = engine(vet, tcs, fov=120.0, use_w=use_w, W=W, H=H, regime="direct")
         sp2, tr2 = d.spatial(dev(q)), d.transition(dev(q))
         assert torch.equal(sp.assign0, sp2.assign0) and torch.equal(tr.pairs0, tr2.pairs0) and torch.equal(tr.prev_count0, tr2.prev_count0)
         np.testing.assert_allclose(sp.per_k.cpu().numpy(), sp2.per_k.cpu().numpy(), rtol=RTOL, atol=ATOL)

@@ -1,6 +1,5 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
 every kernel family once, sizes of a few thousand samples."""
-import os
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -20,19 +19,19 @@ def packed(F, U, dtype=np.float32):
 e = Engine(100, 200, [200, 20], EntropyConfig(fov_angle=90.0))
 r = e.spatial(packed(70, 2501))                     # k_stream_tma (odd U: unaligned tile heads) + k_whist + k_entropy_rows
 t = e.transition(packed(4, 9000))                   # k_stream_tma<cells> + k_transition3 (dense) per tile count + k_mean_rows
-os.environ["VET_T3_CLUSTER"] = "force"
+e.set_option("cluster_tail", "force")
 tc = e.transition(packed(3, 16384))                 # k_transition3c: a frame pair per cluster of 2 CTAs (tables merged through DSMEM)
 sa, ta = e.analyze(packed(3, 16384))                # the same with the spatial epilogue on the side stream beside it
-del os.environ["VET_T3_CLUSTER"]
-os.environ["VET_WHIST_IMPL"] = "i8"
+e.set_option("cluster_tail", "auto")
+e.set_option("weighted_kernel", "i8")
 hot = packed(140, 2504)
 hot[:, :600, 1:] = 0.5                              # 600 users in one cell: second count plane
 r5 = e.spatial(hot)                                 # k_stream_tma (byte planes) + k_whist_i8 (TMA, tcgen05, TMEM), both passes
 r6 = e.spatial(packed(3, 70001))                    # frames in chunks: k_cnt_planes + k_whist_i8
-del os.environ["VET_WHIST_IMPL"]
-os.environ["VET_TRANSITION_IMPL"] = "v2"
+e.set_option("weighted_kernel", "auto")
+e.set_option("transition_kernel", "v2")
 t4 = e.transition(packed(4, 9000))                  # k_transition2 (dense)
-del os.environ["VET_TRANSITION_IMPL"]
+e.set_option("transition_kernel", "auto")
 e.close()
 e = Engine(100, 200, [1], EntropyConfig(), naive_tiles=(30, 30))
 r7 = e.spatial(packed(5, 999))                      # grid tiling: k_stream_tiles with the grid-code table
@@ -50,9 +49,7 @@ e.close()
 e = Engine(200, 400, [20, 50], EntropyConfig(use_weight_distribution=False))
 r8 = e.spatial(packed(2, 300))                      # global-table regime, unweighted: k_stream_global + k_entropy_rows
 e.close()
-os.environ["VET_REGIME"] = "direct"
-e = Engine(200, 400, [20], EntropyConfig())
-del os.environ["VET_REGIME"]
+e = Engine(200, 400, [20], EntropyConfig(), regime="direct")
 r9 = e.spatial(packed(2, 300))                      # direct regime: k_decode + k_nearest + k_spatial_vectors
 e.close()
 torch.cuda.synchronize()

@@ -1,7 +1,6 @@
-"""A/B timing of vet_analyze / vet_transition on the configs[4] shard (1M users x 450 frames, 200 tiles, weighted):
-python tools/time_analyze.py [frames] [users].  VET_T3_CLUSTER, VET_T3_SCRATCH and VET_T3_NOFULL are read at every call; VET_ANALYZE_OVERLAP once
-per process (run the script twice for that one)."""
-import os
+"""Timing of vet_analyze / vet_transition on the configs[4] shard (1M users x 450 frames, 200 tiles, weighted),
+with the handle options of the transition stage switched (vet_set_option):
+python tools/time_analyze.py [frames] [users]"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -29,13 +28,13 @@ def timed(fn, n=5):
     return a.elapsed_time(b) / n
 
 
-for cl, scr, nofull in (("0", "0", ""), ("1", "1", "1"), ("1", "0", "1"), ("1", "0", "")):
-    os.environ["VET_T3_CLUSTER"] = cl
-    os.environ["VET_T3_SCRATCH"] = scr
-    os.environ.pop("VET_T3_NOFULL", None)
-    if nofull:
-        os.environ["VET_T3_NOFULL"] = "1"
+for overlap, cl in (("on", "auto"), ("off", "auto"), ("on", "off")):
+    eng.set_option("analyze_overlap", overlap)
+    eng.set_option("cluster_tail", cl)
+    eng.profile(True)
     t_an = timed(lambda: eng.analyze(p, want_per_k=False, want_assign0=True, want_pairs0=False))
+    prof = eng.profile_read()
+    eng.profile(False)
     t_tr = timed(lambda: eng.transition(p, want_pairs0=False, want_per_k=False))
-    print(f"F={F} U={U} overlap={os.environ.get('VET_ANALYZE_OVERLAP', '1')} cluster={cl} scratch={scr} nofull={nofull or 0}: "
-          f"analyze {t_an:.4f} ms, transition {t_tr:.4f} ms", flush=True)
+    print(f"F={F} U={U} overlap={overlap} cluster_tail={cl}: analyze {t_an:.4f} ms, transition {t_tr:.4f} ms, "
+          f"per kernel (ms, launches over 7 calls) {prof}", flush=True)

@@ -60,16 +60,13 @@ if "c4" in which:  # BASELINE configs[3] at full size on one GPU, and its single
         eng.profile(False)
     del p
 if "mid" in which:  # the reference README's custom configuration: 200x400 video, tile_counts=[50,100,200], default weighting
-    import os
     F, U = 900, 100_000
     p = bench.synth_on_device(torch, F, U, 6, dev)
     for regime in ("global", "direct"):
         if regime == "direct":
-            os.environ["VET_REGIME"] = "direct"
             p = p[:30].contiguous()   # the per-sample regime is O(U*T) per frame: time a slice
         from viewport_entropy_toolkit_b200.engine import Engine
-        eng = Engine(200, 400, [50, 100, 200], EntropyConfig(), dev)
-        os.environ.pop("VET_REGIME", None)
+        eng = Engine(200, 400, [50, 100, 200], EntropyConfig(), dev, regime="direct" if regime == "direct" else "auto")
         eng.profile(True)
         ms = timeit(lambda: eng.spatial(p, want_per_k=False), n=2, warm=1)
         out[f"mid_200x400_{regime}"] = dict(frames=int(p.shape[0]), users=U, ms=ms, gsamples=p.shape[0] * U / ms / 1e6,

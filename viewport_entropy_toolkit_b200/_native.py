@@ -22,6 +22,17 @@ VET_F32, VET_F64 = 0, 1
 VET_TRANSITION_LITERAL, VET_TRANSITION_TEXTBOOK = 0, 1
 VET_MISSING = 0xFFFF
 VET_FLAG_OUT_OF_RANGE, VET_FLAG_EMPTY_FRAME, VET_FLAG_NO_COMMON_USER = 1, 2, 4
+VET_REGIME_AUTO, VET_REGIME_DIRECT = 0, 1
+# vet_set_option: name -> (option id, {value name -> value})
+OPTIONS = {
+    "weighted_kernel": (0, {"auto": 0, "fp64": 1, "i8": 2}),
+    "stream_kernel": (1, {"auto": 0, "simple": 1, "cells": 2, "global": 3}),
+    "transition_kernel": (2, {"auto": 0, "v1": 1, "v2": 2}),
+    "cluster_tail": (3, {"off": 0, "auto": 1, "force": 2}),
+    "t3_pair_scratch": (4, {"off": 0, "on": 1}),
+    "t3_assume_missing": (5, {"off": 0, "on": 1}),
+    "analyze_overlap": (6, {"off": 0, "on": 1}),
+}
 
 
 class VetConfig(C.Structure):
@@ -41,6 +52,7 @@ class VetConfig(C.Structure):
         ("num_tiles", C.POINTER(C.c_int32)),
         ("naive_tile_width", C.c_int32),
         ("naive_tile_height", C.c_int32),
+        ("regime", C.c_int32),
     ]
 
 
@@ -50,6 +62,8 @@ _I64 = C.c_int64
 SYMBOLS = {
     "vet_last_error": (C.c_char_p, []),
     "vet_version": (C.c_char_p, []),
+    "vet_set_option": (C.c_int, [_P, C.c_int, C.c_int]),
+    "vet_get_option": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "vet_create": (C.c_int, [C.POINTER(_P), C.POINTER(VetConfig)]),
     "vet_destroy": (C.c_int, [_P]),
     "vet_num_tiles": (C.c_int, [_P, C.c_int]),
@@ -60,6 +74,7 @@ SYMBOLS = {
     "vet_nearest_tile": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P]),
     "vet_tile_weights": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P]),
     "vet_angular_distances": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P]),
+    "vet_vector_angles": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
     "vet_spatial_vectors": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, _P]),
     "vet_transition_vectors": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, C.c_int, _P]),
     "vet_spatial": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, _P]),

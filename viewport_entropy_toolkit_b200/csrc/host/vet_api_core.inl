@@ -96,15 +96,15 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   }
   // table regime: the per-frame cell histogram (u32) and the LUT must fit in shared memory;
   // larger videos use the direct per-sample path (decode -> vectors)
+  if (cfg->regime != VET_REGIME_AUTO && cfg->regime != VET_REGIME_DIRECT) return fail(VET_ERR_INVALID_ARG, "bad regime");
   h->direct_only = stream_smem_bytes(h) + kStaticSmemSlack > h->smem_optin ||
                    epilogue_smem_bytes(h) + kStaticSmemSlack > h->smem_optin;
   // weighted handles need per-cell weight tables (C x T): bounded; unweighted ones only the cell -> tile LUTs
-  if (h->direct_only && (h->C <= kGlobalTableCells || (!h->use_weight && h->C <= kGlobalLutCells))) {
-    const char* e = getenv("VET_REGIME");  // "direct" pins the per-sample path for A/B runs and tests
-    if (!(e && std::string(e) == "direct")) {
-      h->direct_only = false;
-      h->global_tables = true;
-    }
+  if (cfg->regime == VET_REGIME_DIRECT && !naive) {
+    h->direct_only = true;  // pinned: per-sample evaluation without cell tables
+  } else if (h->direct_only && (h->C <= kGlobalTableCells || (!h->use_weight && h->C <= kGlobalLutCells))) {
+    h->direct_only = false;
+    h->global_tables = true;
   }
   if (h->C >= ((int64_t)1 << 31)) return fail(VET_ERR_UNSUPPORTED, "video %dx%d has too many cells", h->W, h->H);
   if (naive && h->direct_only) return fail(VET_ERR_UNSUPPORTED, "video %dx%d is too large for the grid-tiling tables", h->W, h->H);
@@ -150,10 +150,6 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
     VET_CUDA(cudaMalloc((void**)&h->d_cellvec, (size_t)h->C * 3 * sizeof(double)));
     VET_CUDA(cudaFuncSetAttribute(vet::k_whist<vet::WhistWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   vet::kWhStages * vet::WhistWide::kChunkBytes));
-    VET_CUDA(cudaFuncSetAttribute(vet::k_whist<vet::WhistTall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  vet::kWhStages * vet::WhistTall::kChunkBytes));
-    VET_CUDA(cudaFuncSetAttribute(vet::k_whist<vet::WhistQuad>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  vet::kWhStages * vet::WhistQuad::kChunkBytes));
     vet::k_cell_vectors<<<std::min<int64_t>((h->C + 255) / 256, 1024), 256>>>(h->d_cosT, h->d_sinT, h->d_sinP, h->d_cosP,
                                                                                h->W, h->H, h->d_cellvec);
     h->launches++;
@@ -441,12 +437,8 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
     if (int rc = launch_stream(h, in, dtype, nf, U, asg, !tiles_direct, st)) return rc;
     // The two consumers of the streaming kernel's outputs are independent: the transition kernel goes first on
     // the caller's stream (its persistent CTAs take every SM), the spatial epilogue on a side stream fills the SMs
-    // that fall idle in the transition kernel's last, partial round.  VET_ANALYZE_OVERLAP=0 runs them in sequence.
-    static const bool overlap = [] {
-      const char* e = getenv("VET_ANALYZE_OVERLAP");
-      return !(e && std::string(e) == "0");
-    }();
-    const bool side = overlap && nf >= 2;
+    // that fall idle in the transition kernel's last, partial round.  VET_OPT_ANALYZE_OVERLAP=0 runs them in sequence.
+    const bool side = h->opt[VET_OPT_ANALYZE_OVERLAP] && nf >= 2;
     cudaStream_t se = side ? h->s_exec : st;
     if (side) {
       if (!h->ev_fork) {

@@ -37,6 +37,20 @@ extern "C" int vet_naive_points(vet_handle* h, const double* lonlat_dev, int64_t
   return VET_OK;
 }
 
+extern "C" int vet_set_option(vet_handle* h, int option, int value) {
+  if (!h || option < 0 || option >= VET_OPT_COUNT) return fail(VET_ERR_INVALID_ARG, "bad option");
+  static const int max_value[VET_OPT_COUNT] = {2, 3, 2, 2, 1, 1, 1};
+  if (value < 0 || value > max_value[option]) return fail(VET_ERR_INVALID_ARG, "option %d: value %d out of range", option, value);
+  h->opt[option] = value;
+  return VET_OK;
+}
+
+extern "C" int vet_get_option(const vet_handle* h, int option, int* value) {
+  if (!h || !value || option < 0 || option >= VET_OPT_COUNT) return fail(VET_ERR_INVALID_ARG, "bad option");
+  *value = h->opt[option];
+  return VET_OK;
+}
+
 extern "C" int vet_poll_flags(vet_handle* h, void* stream, uint32_t* flags) {
   if (!h || !flags) return fail(VET_ERR_INVALID_ARG, "null argument");
   DeviceGuard guard(h->device);

@@ -160,6 +160,17 @@ extern "C" int vet_angular_distances(vet_handle* h, int k, const double* vec_dev
   return VET_OK;
 }
 
+extern "C" int vet_vector_angles(vet_handle* h, const double* a_dev, const double* b_dev, int64_t n, double* d_dev, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!a_dev || !b_dev || !d_dev))) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return VET_OK;
+  DeviceGuard guard(h->device);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
+  vet::k_pair_angles<<<blocks, 256, 0, (cudaStream_t)stream>>>(a_dev, b_dev, n, d_dev);
+  h->launches++;
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
 extern "C" int vet_spatial_vectors(vet_handle* h, const double* vec_dev, int64_t F, int64_t U, double* entropy_dev,
                                    double* per_k_dev, double* hist0_dev, uint16_t* assign0_dev, void* stream) {
   if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_spatial_vectors: not available for the latitude/longitude grid tiling (the reference has no such path)");

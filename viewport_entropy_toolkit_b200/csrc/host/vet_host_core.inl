@@ -131,6 +131,7 @@ struct vet_handle {
   };
   std::vector<T3cOcc> t3c_occ;  // co-resident clusters of k_transition3c per (LUT variant, cluster size, shared memory)
   int64_t launches = 0;
+  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
   // optional per-kernel timing (vet_profile_*): CUDA events recorded around each launch
   bool profiling = false;
   struct Span {

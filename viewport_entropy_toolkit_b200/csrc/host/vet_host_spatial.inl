@@ -12,11 +12,7 @@ size_t epilogue_smem_bytes(const vet_handle* h) {
   return (size_t)h->Cpad * 4 + (size_t)h->maxT * 8 + (size_t)h->maxT * 4 + 16;
 }
 bool use_tma_stream(const vet_handle* h, const void* packed) {
-  static const bool force_simple = [] {
-    const char* e = getenv("VET_STREAM_IMPL");
-    return e && std::string(e) == "simple";
-  }();
-  if (force_simple) return false;
+  if (h->opt[VET_OPT_STREAM_KERNEL] == 1) return false;
   if (((uintptr_t)packed & 15) != 0) return false;  // bulk copies need a 16 B aligned tensor base
   const bool lut8 = h->ts[0].d_lut8 != nullptr;
   return stream_tma_smem_bytes(h, lut8) + kStaticSmemSlack <= h->smem_optin;
@@ -41,12 +37,7 @@ int64_t frames_per_batch(const vet_handle* h, int64_t F, int64_t U, bool need_ce
 // Grid of a persistent kernel whose equal-cost items are dealt round-robin: the fewest CTAs that need the same
 // number of rounds as one CTA per SM would.
 int balanced_grid(int64_t items, int sm_count) {
-  static const bool per_sm = [] {
-    const char* e = getenv("VET_STREAM_GRID");
-    return e && std::string(e) == "sm";
-  }();
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(items, sm_count));
-  if (per_sm) return blocks;
   const int64_t rounds = (items + blocks - 1) / blocks;
   return (int)((items + rounds - 1) / rounds);
 }
@@ -94,10 +85,7 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
     }
     // weighted, and the grid fits shared memory as 16-bit counters: privatised histogram per (frame, chunk)
     const size_t smem16 = (size_t)((h->Cpad + 1) / 2) * 4;
-    static const bool no16 = [] {
-      const char* e = getenv("VET_STREAM_IMPL");
-      return e && std::string(e) == "global";
-    }();
+    const bool no16 = h->opt[VET_OPT_STREAM_KERNEL] == 3;
     if (h->use_weight && !no16 && smem16 + kStaticSmemSlack <= h->smem_optin) {
       vet::StreamArgs b = a;
       const int64_t cpf = std::max<int64_t>((U + 65534) / 65535, std::min<int64_t>((U + 16383) / 16384, ((int64_t)h->sm_count * 8 + F - 1) / F));
@@ -138,7 +126,7 @@ int launch_stream(vet_handle* h, const void* packed, int dtype, int64_t F, int64
   const int64_t items = F * a.chunks_per_frame;
   // Items are dealt round-robin and cost the same, so the kernel takes ceil(items / CTAs) rounds: use the fewest
   // CTAs that still need that many rounds (3600 frames: 144 CTAs x 25 instead of 148 CTAs of which 100 do only 24).
-  // Measured on configs[2]: 0.790 -> 0.782 ms (97.6 -> 98.6 % of the HBM peak).  VET_STREAM_GRID=sm pins one CTA per SM.
+  // Measured on configs[2]: 0.790 -> 0.782 ms (97.6 -> 98.6 % of the HBM peak).
   const int blocks = balanced_grid(items, h->sm_count);
   if (use_tma_stream(h, packed)) {
     const bool lut8 = h->ts[0].d_lut8 != nullptr;
@@ -213,11 +201,7 @@ TilesPlan plan_tiles(const vet_handle* h, const void* packed, int64_t U) {
   TilesPlan p;
   if (h->use_weight || h->direct_only || h->global_tables) return p;
   if (((uintptr_t)packed & 15) != 0) return p;
-  static const bool disabled = [] {
-    const char* e = getenv("VET_STREAM_IMPL");
-    return e && (std::string(e) == "simple" || std::string(e) == "cells");
-  }();
-  if (disabled) return p;
+  if (h->opt[VET_OPT_STREAM_KERNEL] == 1 || h->opt[VET_OPT_STREAM_KERNEL] == 2) return p;
   // worth it when there is a single tile count or the frames are small against the cell grid
   if (!(h->K == 1 || U < 2 * h->C)) return p;
   int off = 0, hoff = 0, soff = 0;
@@ -336,11 +320,8 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
 // k_whist for tile count k over F frames of the cell histogram `cnt` -> hist[F,T_k]
 int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* hist, cudaStream_t st) {
   TileSet& t = h->ts[k];
-  const int shape = whist_shape();
-  const int frames_per_cta = shape == 1 ? vet::WhistTall::kFramesPerCta : vet::WhistWide::kFramesPerCta;
-  const size_t wh_smem = (size_t)vet::kWhStages * (shape == 1   ? vet::WhistTall::kChunkBytes
-                                                   : shape == 2 ? vet::WhistQuad::kChunkBytes
-                                                                : vet::WhistWide::kChunkBytes);
+  const int frames_per_cta = vet::WhistWide::kFramesPerCta;
+  const size_t wh_smem = (size_t)vet::kWhStages * vet::WhistWide::kChunkBytes;
   const int64_t fblocks = (F + frames_per_cta - 1) / frames_per_cta;
   const int blocks = (int)std::min<int64_t>(fblocks * t.G, h->sm_count);
   if (t.sched_F != F || t.sched_blocks != blocks) {
@@ -363,12 +344,7 @@ int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* h
   a.max_items = t.sched_max_items;
   {
     LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-    if (shape == 1)
-      vet::k_whist<vet::WhistTall><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
-    else if (shape == 2)
-      vet::k_whist<vet::WhistQuad><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
-    else
-      vet::k_whist<vet::WhistWide><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
+    vet::k_whist<vet::WhistWide><<<blocks, vet::kWhThreads, wh_smem, st>>>(a);
   }
   VET_CUDA(cudaGetLastError());
   return VET_OK;
@@ -408,16 +384,9 @@ int make_u8_map(CUtensorMap* m, const void* base, uint64_t kp, uint64_t rows, ui
 
 int64_t i8_kp(const vet_handle* h) { return (h->C + vet::kI8BK - 1) / vet::kI8BK * vet::kI8BK; }
 
-// 0 = heuristic, 1 = always the FP64 kernel, 2 = the tensor-core kernel whenever it applies
-int whist_impl() {
-  const char* e = getenv("VET_WHIST_IMPL");
-  if (e && std::string(e) == "fp64") return 1;
-  if (e && std::string(e) == "i8") return 2;
-  return 0;
-}
-
 bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U) {
-  const int impl = whist_impl();
+  // 0 = heuristic, 1 = always the FP64 kernel, 2 = the tensor-core kernel whenever it applies
+  const int impl = h->opt[VET_OPT_WEIGHTED_KERNEL];
   if (impl == 1 || !encode_tiled_fn()) return false;
   if (U * 255 >= ((int64_t)1 << 31)) return false;  // int32 accumulators: D <= 255 * sum(count plane) <= 255 U
   if ((size_t)vet::kI8SmemBytes + kStaticSmemSlack > h->smem_optin) return false;

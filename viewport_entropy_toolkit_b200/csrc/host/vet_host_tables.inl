@@ -3,18 +3,6 @@
 // Textual fragment of vet_b200.cu.
 namespace {
 
-// Blocking of k_whist: "wide" = 8 tiles x 8 frames per warp, "tall" = 4 tiles x 16 frames.
-// 0 = wide (default), 1 = tall, 2 = quad
-int whist_shape() {
-  static const int shape = [] {
-    const char* e = getenv("VET_WHIST_SHAPE");
-    if (e && std::string(e) == "tall") return 1;  // measured: wide 0.49 ms, tall 0.67 ms on configs[2]
-    if (e && std::string(e) == "quad") return 2;
-    return 0;
-  }();
-  return shape;
-}
-
 // Longest-processing-time schedule of the (frame block, group) items of k_whist over the
 // CTAs (items differ in size: a group's cost is its number of weight chunks); each CTA's
 // list is then put in frame-block-major order for L2 locality.
@@ -205,11 +193,7 @@ int build_tile_set(vet_handle* h, TileSet& t) {
                                             t.d_cell_idx, t.d_w_val);
     h->launches++;
     VET_CUDA(cudaGetLastError());
-    const int shape = whist_shape();
-    if (int rc = shape == 1   ? build_weight_groups<vet::WhistTall>(h, t, ptr, unit)
-                 : shape == 2 ? build_weight_groups<vet::WhistQuad>(h, t, ptr, unit)
-                              : build_weight_groups<vet::WhistWide>(h, t, ptr, unit))
-      return rc;
+    if (int rc = build_weight_groups<vet::WhistWide>(h, t, ptr, unit)) return rc;
   }
   return VET_OK;
 }

@@ -142,23 +142,14 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
   }
   a.cap = cap;
   a.g_tables = h->d_tables;
-  // VET_TRANSITION_IMPL = v1 | v2 pins an older kernel generation (A/B runs, tests); read at every call
-  const bool force_v1 = [] {
-    const char* e = getenv("VET_TRANSITION_IMPL");
-    return e && std::string(e) == "v1";
-  }();
-  const bool force_v2 = [] {
-    const char* e = getenv("VET_TRANSITION_IMPL");
-    return e && std::string(e) == "v2";
-  }();
+  // VET_OPT_TRANSITION_KERNEL pins k_transition (1) or k_transition2 (2): the parity suite runs them against the two-pass kernels
+  const bool force_v1 = h->opt[VET_OPT_TRANSITION_KERNEL] == 1;
+  const bool force_v2 = h->opt[VET_OPT_TRANSITION_KERNEL] == 2;
   // two-pass kernel, one launch per tile count; rows it cannot hold (hash overflow) are flagged in d_redo
   // and recomputed by k_transition2 below
-  // VET_T3_CLUSTER=0 keeps every frame pair on k_transition3 (A/B runs, tests); =force takes the cluster kernel
-  // whenever it can run, also where it does not pay (small frames; tests)
-  const int cluster_tail = [] {
-    const char* e = getenv("VET_T3_CLUSTER");
-    return (e && std::string(e) == "0") ? 0 : (e && std::string(e) == "force") ? 2 : 1;
-  }();
+  // VET_OPT_CLUSTER_TAIL: 0 keeps every frame pair on k_transition3, 2 takes the cluster kernel whenever it can
+  // run, also where it does not pay (small frames; tests)
+  const int cluster_tail = h->opt[VET_OPT_CLUSTER_TAIL];
   bool redo_only = false;
   if (a.mode == VET_TRANSITION_LITERAL && !in_smem && !force_v1 && !force_v2 && a.cell16 && U < ((int64_t)1 << 31)) {
     const size_t budget = h->smem_optin - kStaticSmemSlack;
@@ -214,11 +205,8 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
     }
     if (ok) {
       const int blocks3 = (int)std::min<int64_t>(rows, h->sm_count);
-      // VET_T3_SCRATCH=1 keeps the pair scratch with the identity table too (A/B runs)
-      const bool keep_scratch = [] {
-        const char* e = getenv("VET_T3_SCRATCH");
-        return e && std::string(e) == "1";
-      }();
+      // VET_OPT_T3_PAIR_SCRATCH keeps the pair scratch with the identity table too (variant compared by the tests)
+      const bool keep_scratch = h->opt[VET_OPT_T3_PAIR_SCRATCH] != 0;
       bool need_scratch = keep_scratch;  // packed (prev | cur << 16) per user, one row per CTA: not with the identity table
       for (int k = 0; k < a.K; ++k) need_scratch = need_scratch || (plan[k].mode >= 0 && plan[k].lw != vet::kLutIdentity);
       if (need_scratch)
@@ -264,7 +252,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         A3.pair_scratch = (pl.lw == vet::kLutIdentity && !keep_scratch) ? nullptr : h->d_pairs;
         A3.redo = h->d_redo;
         A3.flags = a.flags;
-        A3.nvalid = getenv("VET_T3_NOFULL") ? nullptr : a.nvalid;  // VET_T3_NOFULL: always test for missing users (A/B runs)
+        A3.nvalid = h->opt[VET_OPT_T3_ASSUME_MISSING] ? nullptr : a.nvalid;  // option: always test for missing users
         // dense tables: the rows % SMs pairs left after the full rounds go to k_transition3c, one pair per
         // cluster of S CTAs (users split across the cluster) instead of one more, mostly idle, round
         int64_t tail_rows = 0;

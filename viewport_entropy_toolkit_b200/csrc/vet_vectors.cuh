@@ -131,4 +131,15 @@ __global__ void k_angular_distances(const double* __restrict__ vec, int64_t n, c
   }
 }
 
+// vector_angle_distance (EU:41-67) for n independent pairs: both operands re-normalised, arccos(clip(dot))
+__global__ void k_pair_angles(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double ax = a[3 * i], ay = a[3 * i + 1], az = a[3 * i + 2];
+    double bx = b[3 * i], by = b[3 * i + 1], bz = b[3 * i + 2];
+    normalize3(ax, ay, az);
+    normalize3(bx, by, bz);
+    out[i] = acos(clip1(dot3(ax, ay, az, bx, by, bz)));
+  }
+}
+
 }  // namespace vet

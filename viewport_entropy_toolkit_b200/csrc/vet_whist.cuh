@@ -53,9 +53,9 @@ struct WhistShape {
   static constexpr int kFramesPerCta = kWhWarps * FW;
   static_assert(TG * FW == 64, "the warp reduction below is written for 64 accumulators");
 };
-using WhistWide = WhistShape<8, 8, 2, 4>;   // 8 tiles x 8 frames, counts as aligned pairs, 3 steps of prefetch
-using WhistTall = WhistShape<4, 16, 1, 4>;  // 4 tiles x 16 frames: 25 % less padding in the dense blocks
-using WhistQuad = WhistShape<8, 8, 4, 2>;   // counts as aligned quads (LDG.128): half the load instructions
+// 8 tiles x 8 frames, counts as aligned pairs, 3 steps of prefetch.  (Measured on configs[2] against 4 tiles x 16 frames
+// and against aligned quads: 0.49 ms vs 0.67 / 0.52 ms; those shapes are gone.)
+using WhistWide = WhistShape<8, 8, 2, 4>;
 
 struct WhistArgs {
   const uint32_t* cnt;     // [F + kWhRowPad, cpad]: readable past F (rows of a partial last frame block)

@@ -67,15 +67,18 @@ class Engine:
     def __init__(self, video_width: int, video_height: int, tile_counts: Sequence[int],
                  entropy_config: Optional[EntropyConfig] = None, device: Optional[torch.device] = None,
                  native_tables: bool = False, centres: Optional[Sequence[np.ndarray]] = None,
-                 naive_tiles: Optional[Tuple[int, int]] = None):
+                 naive_tiles: Optional[Tuple[int, int]] = None, regime: str = "auto"):
         """native_tables=True lets the library derive the lattice and axis tables itself
         (libm) instead of receiving the numpy-made ones; used by tests to show both agree.
         centres: optional list of [T_k,3] arrays of ARBITRARY tile centres (the reference's
         free functions take any List[Vector]); tile_counts is then only a label.
         naive_tiles=(tile_width, tile_height) in degrees selects the latitude/longitude grid tiling
         of NaiveSpatialEntropyAnalyzer (NA:39-241) instead of the lattice: one tile set whose tile
-        ids are grid codes lon_idx * (180/tile_height + 1) + lat_idx; tile_counts is ignored."""
+        ids are grid codes lon_idx * (180/tile_height + 1) + lat_idx; tile_counts is ignored.
+        regime="direct" pins the per-sample evaluation without cell tables (vet_config.regime)."""
         self._h = None
+        if regime not in ("auto", "direct"):
+            raise ValueError("regime must be 'auto' or 'direct'")
         lib = N.load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("viewport_entropy_toolkit_b200 needs a CUDA device; there is no CPU path")
@@ -115,7 +118,8 @@ class Engine:
             lat_by_py=None if native_tables else lat.ctypes.data_as(C.POINTER(C.c_double)),
             num_tiles=ntiles,
             naive_tile_width=self.naive_tiles[0] if self.naive_tiles else 0,
-            naive_tile_height=self.naive_tiles[1] if self.naive_tiles else 0)
+            naive_tile_height=self.naive_tiles[1] if self.naive_tiles else 0,
+            regime=N.VET_REGIME_DIRECT if regime == "direct" else N.VET_REGIME_AUTO)
         h = C.c_void_p()
         _check(lib.vet_create(C.byref(h), C.byref(cfg)))
         self._h = h
@@ -150,6 +154,18 @@ class Engine:
         if packed.shape[-1] != 3:
             raise ValueError("packed must have shape [..., 3] = (time, 2dmu, 2dmv)")
         return packed.contiguous(), (N.VET_F32 if packed.dtype == torch.float32 else N.VET_F64)
+
+    def set_option(self, name: str, value) -> None:
+        """vet_set_option: pins a kernel choice of this handle, e.g. set_option("weighted_kernel", "i8")
+        (names and values: _native.OPTIONS).  Production leaves the defaults."""
+        opt, values = N.OPTIONS[name]
+        _check(self._lib.vet_set_option(self._h, opt, values[value] if isinstance(value, str) else int(value)))
+
+    def get_option(self, name: str) -> str:
+        opt, values = N.OPTIONS[name]
+        v = C.c_int(0)
+        _check(self._lib.vet_get_option(self._h, opt, C.byref(v)))
+        return next(k for k, x in values.items() if x == v.value)
 
     def launch_count(self) -> int:
         return int(self._lib.vet_launch_count(self._h))
@@ -228,6 +244,16 @@ class Engine:
         n = v.numel() // 3
         d = torch.empty(v.shape[:-1] + (self.num_tiles[k],), dtype=torch.float64, device=self.device)
         _check(self._lib.vet_angular_distances(self._h, k, v.data_ptr(), n, d.data_ptr(), self._stream()))
+        return d
+
+    def vector_angles(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """vector_angle_distance (EU:41-67) for pairs a[..., 3], b[..., 3] -> float64[...] radians."""
+        a = a.to(device=self.device, dtype=torch.float64).contiguous()
+        b = b.to(device=self.device, dtype=torch.float64).contiguous()
+        if a.shape != b.shape or a.shape[-1] != 3:
+            raise ValueError("a and b must both be [..., 3]")
+        d = torch.empty(a.shape[:-1], dtype=torch.float64, device=self.device)
+        _check(self._lib.vet_vector_angles(self._h, a.data_ptr(), b.data_ptr(), a.numel() // 3, d.data_ptr(), self._stream()))
         return d
 
     def spatial_vectors(self, vectors: torch.Tensor, want_per_k: bool = True, want_hist0: bool = True,
@@ -429,7 +455,9 @@ def _host_ptr(arr) -> int:
     return arr.data_ptr() if isinstance(arr, torch.Tensor) else arr.ctypes.data
 
 
-_ENGINES: Dict[tuple, Engine] = {}
+_ENGINES: Dict[tuple, Engine] = {}        # lattice / grid configurations (analyzers, bench): kept until clear_engines()
+_ADHOC_ENGINES: Dict[tuple, Engine] = {}  # arbitrary centre lists of the functional API: small LRU
+_ADHOC_LIMIT = 16
 
 
 def get_engine(video_width: int, video_height: int, tile_counts: Sequence[int],
@@ -447,17 +475,22 @@ def get_engine(video_width: int, video_height: int, tile_counts: Sequence[int],
     key = (idx, int(video_width), int(video_height), tuple(int(c) for c in tile_counts), float(ec.fov_angle),
            bool(ec.use_weight_distribution), float(ec.power_factor), ckey,
            None if naive_tiles is None else (int(naive_tiles[0]), int(naive_tiles[1])))
-    eng = _ENGINES.get(key)
+    cache = _ENGINES if centres is None else _ADHOC_ENGINES
+    eng = cache.get(key)
     if eng is None:
-        if len(_ENGINES) >= 32:  # bound the cache (functional calls with ad-hoc centre lists)
-            _ENGINES.pop(next(iter(_ENGINES))).close()
+        # An evicted engine is only dropped from the cache, never closed: whoever still holds it keeps a live
+        # handle, and Engine.__del__ frees it with the last reference.
+        while cache is _ADHOC_ENGINES and len(cache) >= _ADHOC_LIMIT:
+            cache.pop(next(iter(cache)))
         eng = Engine(video_width, video_height, tile_counts, ec, torch.device("cuda", idx), centres=centres,
                      naive_tiles=naive_tiles)
-        _ENGINES[key] = eng
+    elif cache is _ADHOC_ENGINES:
+        cache.pop(key)  # re-inserted below: most recently used last
+    cache[key] = eng
     return eng
 
 
 def clear_engines() -> None:
-    for e in _ENGINES.values():
-        e.close()
+    """Empties the caches.  Engines still referenced elsewhere stay usable; the others free their handle."""
     _ENGINES.clear()
+    _ADHOC_ENGINES.clear()

@@ -77,9 +77,10 @@ def pixel_to_spherical(point: Point, video_width: int, video_height: int) -> Rad
 
 def vector_angle_distance(v1: Vector, v2: Vector) -> float:
     """EU:41-67: angle between two vectors in radians."""
-    eng = _engine_for([v2])
-    d = eng.angular_distances(torch.tensor([_vec(v1)], dtype=torch.float64), 0)
-    return float(d[0, 0].item())
+    # one table-free handle serves every pair (vet_vector_angles): no engine per distinct v2
+    eng = get_engine(_TINY_VIDEO[0], _TINY_VIDEO[1], [1], EntropyConfig())
+    d = eng.vector_angles(torch.tensor([_vec(v1)], dtype=torch.float64), torch.tensor([_vec(v2)], dtype=torch.float64))
+    return float(d[0].item())
 
 
 def find_angular_distances(vector: Vector, tile_centers: List[Vector]) -> np.ndarray:
