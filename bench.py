@@ -543,7 +543,25 @@ def main():
                "h2d_bytes_per_step": int(host.numel() * 4),
                "d2h_bytes_per_step": int(res["entropy"].nbytes + res["hist0"].nbytes + res["assign0"].nbytes),
                "steps": args.e2e_steps, "api": "Engine.spatial_host (vet_spatial_host), pinned host input"}
-        del host, res
+        # the same through vet_analyze_host: both analyzers, one upload (transition rows come back as well)
+        eng.analyze_host(host, want_per_k=False, want_pairs0=False, reuse_buffers=True)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            rs, rt = eng.analyze_host(host, want_per_k=False, want_pairs0=False, reuse_buffers=True)
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt = float(t_e.item())
+        e2e["analyze"] = {"value": samples_per_step * args.e2e_steps / dt, "unit": UNIT,
+                          "h2d_bytes_per_step": int(host.numel() * 4),
+                          "d2h_bytes_per_step": int(rs["entropy"].nbytes + rs["hist0"].nbytes + rs["assign0"].nbytes +
+                                                    rt["entropy"].nbytes + rt["prev_count0"].nbytes),
+                          "steps": args.e2e_steps,
+                          "api": "Engine.analyze_host (vet_analyze_host): spatial + transition entropy, pinned host input"}
+        del host, res, rs, rt
 
     del packed, outs, out, gathered
     torch.cuda.empty_cache()

@@ -117,7 +117,8 @@ enum {
   VET_OPT_T3_PAIR_SCRATCH = 4,   /* 1: keep the 4 B/user pair scratch also when the rows hold tile ids */
   VET_OPT_T3_ASSUME_MISSING = 5, /* 1: always test for missing users (no complete-frame variant) */
   VET_OPT_ANALYZE_OVERLAP = 6,   /* default 1: vet_analyze overlaps its spatial and transition stages; 0 runs them in sequence */
-  VET_OPT_COUNT = 7
+  VET_OPT_HOST_BATCH_FRAMES = 7, /* frames per batch of the host-buffer pipelines; 0 = auto (about 256 MiB of input per batch) */
+  VET_OPT_COUNT = 8
 };
 int vet_set_option(vet_handle* h, int option, int value);
 int vet_get_option(const vet_handle* h, int option, int* value);
@@ -229,6 +230,14 @@ int vet_spatial_host(vet_handle* h, const void* packed_host, int dtype, int64_t 
 int vet_transition_host(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U,
                         double* entropy_host, double* per_k_host, int32_t* prev_count0_host,
                         uint16_t* pairs0_host, int mode);
+/* vet_analyze on a host tensor: both compute_entropy methods (SA:107-164, TA:107-175) with one upload of the
+ * input.  Like vet_transition_host it walks the tensor in frame batches on three streams (upload | kernels |
+ * download); the last frame of a batch stays on the device as the first frame of the next one, so no frame is
+ * uploaded twice and the device never holds more than two batches (tensors larger than device memory are fine). */
+int vet_analyze_host(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U,
+                     double* sp_entropy_host, double* sp_per_k_host, double* hist0_host, uint16_t* assign0_host,
+                     double* tr_entropy_host, double* tr_per_k_host, int32_t* prev_count0_host,
+                     uint16_t* pairs0_host, int mode);
 
 /* compute_naive_spatial_entropy (EU:362-453) for frames of ARBITRARY RadialPoints:
  * lonlat_dev[F,U,2] float64 degrees (NaN = absent user, EU:426-427) ->

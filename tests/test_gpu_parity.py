@@ -988,3 +988,46 @@ def test_host_path_equals_device_path_at_scale(vet):
     np.testing.assert_allclose(h["entropy"][1090:], ref["entropy"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(h["hist0"][1090:], ref["hist0"], rtol=RTOL, atol=1500 * I8_QUANT)
     e.close()
+
+
+# ---------------------------------------------------------------------------------
+# host-buffer pipelines (vet_spatial_host / vet_transition_host / vet_analyze_host): frame batches on three streams,
+# the last frame of a batch carried over on the device as the halo of the next
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(F=23, U=4096, tcs=[200], use_w=True, batch=5, dtype=np.float32),          # 5 batches, the last one short (3 frames)
+    dict(F=11, U=3001, tcs=[20, 50], use_w=False, batch=2, dtype=np.float64, missing=0.1),   # batches of 2 frames, odd U, f64, missing users
+    dict(F=9, U=2000, tcs=[200, 500], use_w=True, batch=8, dtype=np.float32),      # last batch = 1 new frame + halo
+    dict(F=6, U=1500, tcs=[100], use_w=True, batch=0, dtype=np.float32),           # auto batch size: one batch
+    dict(F=1, U=700, tcs=[50], use_w=True, batch=4, dtype=np.float32),             # a single frame: no transition row
+])
+def test_host_pipelines_equal_device_calls(vet, cfg):
+    """analyze_host / transition_host / spatial_host return, bit for bit, what the device entry points return
+    for the same tensor, whatever the batching (weighted kernel pinned: its choice depends on the frames per call)."""
+    p = synth(cfg["F"], cfg["U"], 7100 + cfg["U"], iid=False, missing=cfg.get("missing", 0.0), dtype=cfg["dtype"])
+    e = engine(vet, cfg["tcs"], 90.0, cfg["use_w"])
+    e.set_option("weighted_kernel", "fp64")
+    e.set_option("host_batch_frames", cfg["batch"])
+    sp, tr = e.analyze(dev(p))
+    assert e.poll_flags() == 0
+    hs, ht = e.analyze_host(p)
+    ht2 = e.transition_host(p)
+    hs2 = e.spatial_host(p)
+    assert e.poll_flags() == 0
+    for got in (hs, hs2):
+        assert np.array_equal(got["entropy"], sp.entropy.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(got["per_k"], sp.per_k.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(got["hist0"], sp.hist0.cpu().numpy()) and np.array_equal(got["assign0"], sp.assign0.cpu().numpy())
+    for got in (ht, ht2):
+        assert np.array_equal(got["entropy"], tr.entropy.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(got["per_k"], tr.per_k.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(got["prev_count0"], tr.prev_count0.cpu().numpy())
+        assert np.array_equal(got["pairs0"], tr.pairs0.cpu().numpy())
+    if cfg["F"] <= 11 and cfg["F"] > 1:   # and the oracle itself
+        ref = orc.transition_analyzer(p, W0, H0, cfg["tcs"], mode="literal")
+        assert np.array_equal(ht["prev_count0"], ref["prev_count0"]) and np.array_equal(ht["pairs0"], ref["pairs0"])
+        np.testing.assert_allclose(ht["entropy"], ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    # optional outputs left out
+    hs3, ht3 = e.analyze_host(p, want_per_k=False, want_hist0=False, want_assign0=False, want_prev_count0=False, want_pairs0=False)
+    assert np.array_equal(hs3["entropy"], hs["entropy"], equal_nan=True) and np.array_equal(ht3["entropy"], ht["entropy"], equal_nan=True)
+    e.close()

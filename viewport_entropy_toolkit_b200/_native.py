@@ -32,6 +32,7 @@ OPTIONS = {
     "t3_pair_scratch": (4, {"off": 0, "on": 1}),
     "t3_assume_missing": (5, {"off": 0, "on": 1}),
     "analyze_overlap": (6, {"off": 0, "on": 1}),
+    "host_batch_frames": (7, {"auto": 0}),
 }
 
 
@@ -82,6 +83,7 @@ SYMBOLS = {
     "vet_analyze": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "vet_spatial_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P]),
     "vet_transition_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, C.c_int]),
+    "vet_analyze_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int]),
     "vet_naive_points": (C.c_int, [_P, _P, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "vet_poll_flags": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
     "vet_launch_count": (_I64, [_P]),

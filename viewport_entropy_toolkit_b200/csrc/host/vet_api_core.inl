@@ -194,6 +194,8 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   VET_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
   VET_CUDA(cudaStreamCreateWithFlags(&h->s_exec, cudaStreamNonBlocking));
   VET_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  VET_CUDA(cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
+  for (auto& e : h->ev_pipe) VET_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   VET_CUDA(cudaDeviceSynchronize());
   cleanup.armed = false;
   *out = h;
@@ -232,6 +234,10 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);
   for (void* p : h->d_hout) cudaFree(p);
+  for (void* p : h->d_hout2) cudaFree(p);
+  for (auto e : h->ev_pipe)
+    if (e) cudaEventDestroy(e);
+  if (h->s_side) cudaStreamDestroy(h->s_side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
@@ -314,16 +320,11 @@ extern "C" int vet_tile_weights(vet_handle* h, int k, const double* vec_dev, int
   return VET_OK;
 }
 
-extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
-                           double* per_k_dev, double* hist0_dev, uint16_t* assign0_dev, void* stream) {
-  if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
-  if (F == 0) return VET_OK;
-  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:168-169
-  if (!packed_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
-  DeviceGuard guard(h->device);
-  h->call_frames = F;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (h->direct_only) return spatial_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, hist0_dev, assign0_dev, st);
+namespace {
+
+// SpatialEntropyAnalyzer.compute_entropy on F resident frames (table regimes); per_k rows `per_k_stride` apart.
+int spatial_core(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
+                 double* per_k_dev, int64_t per_k_stride, double* hist0_dev, uint16_t* assign0_dev, cudaStream_t st) {
   const int64_t fb = frames_per_batch(h, F, U, false);
   if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, cnt_scratch_bytes(h, fb))) return rc;
   if (int rc = grow((void**)&h->d_nvalid, &h->nvalid_bytes, (size_t)fb * 4)) return rc;
@@ -335,32 +336,41 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
     TilesPlan tp = plan_tiles(h, in, U);
     if (tp.ok) {
       if (int rc = launch_stream_tiles(h, tp, in, dtype, nf, U, assign0_dev ? assign0_dev + f0 * U : nullptr, st)) return rc;
-      if (int rc = launch_tiles_epilogue(h, tp, nf, entropy_dev + f0, per_k_dev ? per_k_dev + f0 : nullptr, F,
+      if (int rc = launch_tiles_epilogue(h, tp, nf, entropy_dev + f0, per_k_dev ? per_k_dev + f0 : nullptr, per_k_stride,
                                          hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
         return rc;
       continue;
     }
     if (int rc = launch_stream(h, in, dtype, nf, U, assign0_dev ? assign0_dev + f0 * U : nullptr, false, st)) return rc;
-    if (int rc = launch_epilogue(h, nf, U, entropy_dev + f0, per_k_dev ? per_k_dev + f0 : nullptr, F,
+    if (int rc = launch_epilogue(h, nf, U, entropy_dev + f0, per_k_dev ? per_k_dev + f0 : nullptr, per_k_stride,
                                  hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
       return rc;
   }
   return VET_OK;
 }
 
-extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
-                              double* per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode, void* stream) {
-  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_transition: not available for the latitude/longitude grid tiling (the reference has no such path)");
+}  // namespace
+
+extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
+                           double* per_k_dev, double* hist0_dev, uint16_t* assign0_dev, void* stream) {
   if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
-  if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
-  if (F <= 1) return VET_OK;  // TA:143-146: the first frame yields no row
-  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:239-240
+  if (F == 0) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:168-169
   if (!packed_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
-  if (U >= 0xFFFFFFFFll) return fail(VET_ERR_UNSUPPORTED, "too many users");
   DeviceGuard guard(h->device);
+  h->call_frames = F;
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->direct_only)
-    return transition_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, prev_count0_dev, pairs0_dev, mode, st);
+  if (h->direct_only) return spatial_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, hist0_dev, assign0_dev, st);
+  return spatial_core(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, F, hist0_dev, assign0_dev, st);
+}
+
+namespace {
+
+// TransitionEntropyAnalyzer.compute_entropy on F resident frames (table regimes).  per_k rows are `per_k_stride` apart:
+// a caller that walks a longer video in pieces (the host-buffer pipeline) passes the row count of the whole video.
+int transition_core(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
+                    double* per_k_dev, int64_t per_k_stride, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode,
+                    cudaStream_t st) {
   const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
   const size_t csz = h->C <= 65535 ? 2 : 4;
   if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, cnt_scratch_bytes(h, fb))) return rc;
@@ -388,7 +398,7 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
     }
     a.entropy = entropy_dev + f0;
     a.per_k = per_k_dev ? per_k_dev + f0 : nullptr;
-    a.per_k_stride = F - 1;
+    a.per_k_stride = per_k_stride;
     a.prev_count0 = prev_count0_dev ? prev_count0_dev + f0 * T0 : nullptr;
     a.pairs0 = pairs0_dev ? pairs0_dev + f0 * U * 2 : nullptr;
     a.mode = mode;
@@ -400,23 +410,32 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
   return VET_OK;
 }
 
-extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* sp_entropy_dev,
-                           double* sp_per_k_dev, double* hist0_dev, uint16_t* assign0_dev, double* tr_entropy_dev,
-                           double* tr_per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode, void* stream) {
-  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_analyze: not available for the latitude/longitude grid tiling (the reference has no such path)");
+}  // namespace
+
+extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
+                              double* per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode, void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_transition: not available for the latitude/longitude grid tiling (the reference has no such path)");
   if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
   if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
-  if (F == 0) return VET_OK;
-  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");
-  if (!packed_dev || !sp_entropy_dev || (F > 1 && !tr_entropy_dev)) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  if (F <= 1) return VET_OK;  // TA:143-146: the first frame yields no row
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");  // EU:239-240
+  if (!packed_dev || !entropy_dev) return fail(VET_ERR_INVALID_ARG, "null buffer");
   if (U >= 0xFFFFFFFFll) return fail(VET_ERR_UNSUPPORTED, "too many users");
   DeviceGuard guard(h->device);
-  h->call_frames = F;
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->direct_only || F == 1) {  // no shared pass to gain: run the two stages one after the other
-    if (int rc = vet_spatial(h, packed_dev, dtype, F, U, sp_entropy_dev, sp_per_k_dev, hist0_dev, assign0_dev, stream)) return rc;
-    return vet_transition(h, packed_dev, dtype, F, U, tr_entropy_dev, tr_per_k_dev, prev_count0_dev, pairs0_dev, mode, stream);
-  }
+  if (h->direct_only)
+    return transition_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, prev_count0_dev, pairs0_dev, mode, st);
+  return transition_core(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, F - 1, prev_count0_dev, pairs0_dev, mode, st);
+}
+
+namespace {
+
+// Both analyzers on F resident frames with one read of the input (table regimes, F >= 2); per_k rows sp_stride /
+// tr_stride apart.
+int analyze_core(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* sp_entropy_dev,
+                 double* sp_per_k_dev, int64_t sp_stride, double* hist0_dev, uint16_t* assign0_dev, double* tr_entropy_dev,
+                 double* tr_per_k_dev, int64_t tr_stride, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode,
+                 cudaStream_t st) {
   const int64_t fb = std::max<int64_t>(2, frames_per_batch(h, F, U, true));
   const size_t csz = h->C <= 65535 ? 2 : 4;
   if (int rc = grow((void**)&h->d_cnt, &h->cnt_bytes, cnt_scratch_bytes(h, fb))) return rc;
@@ -439,16 +458,16 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
     // the caller's stream (its persistent CTAs take every SM), the spatial epilogue on a side stream fills the SMs
     // that fall idle in the transition kernel's last, partial round.  VET_OPT_ANALYZE_OVERLAP=0 runs them in sequence.
     const bool side = h->opt[VET_OPT_ANALYZE_OVERLAP] && nf >= 2;
-    cudaStream_t se = side ? h->s_exec : st;
+    cudaStream_t se = side ? h->s_side : st;
     if (side) {
       if (!h->ev_fork) {
         VET_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         VET_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
       }
       VET_CUDA(cudaEventRecord(h->ev_fork, st));
-      VET_CUDA(cudaStreamWaitEvent(h->s_exec, h->ev_fork, 0));
+      VET_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_fork, 0));
     } else {
-      if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
+      if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, sp_stride,
                                    hist0_dev ? hist0_dev + f0 * T0 : nullptr, st))
         return rc;
     }
@@ -465,7 +484,7 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
       }
       a.entropy = tr_entropy_dev + f0;
       a.per_k = tr_per_k_dev ? tr_per_k_dev + f0 : nullptr;
-      a.per_k_stride = F - 1;
+      a.per_k_stride = tr_stride;
       a.prev_count0 = prev_count0_dev ? prev_count0_dev + f0 * T0 : nullptr;
       a.pairs0 = pairs0_dev ? pairs0_dev + f0 * U * 2 : nullptr;
       a.mode = mode;
@@ -474,7 +493,7 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
       if (int rc = launch_transition(h, a, nf - 1, U, h->maxT, st)) return rc;
     }
     if (side) {
-      if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, F,
+      if (int rc = launch_epilogue(h, nf, U, sp_entropy_dev + f0, sp_per_k_dev ? sp_per_k_dev + f0 : nullptr, sp_stride,
                                    hist0_dev ? hist0_dev + f0 * T0 : nullptr, se))
         return rc;
       VET_CUDA(cudaEventRecord(h->ev_join, se));
@@ -483,4 +502,27 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
     if (nf == F - f0) break;
   }
   return VET_OK;
+}
+
+}  // namespace
+
+extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* sp_entropy_dev,
+                           double* sp_per_k_dev, double* hist0_dev, uint16_t* assign0_dev, double* tr_entropy_dev,
+                           double* tr_per_k_dev, int32_t* prev_count0_dev, uint16_t* pairs0_dev, int mode, void* stream) {
+  if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_analyze: not available for the latitude/longitude grid tiling (the reference has no such path)");
+  if (!h || F < 0 || U < 0 || (dtype != VET_F32 && dtype != VET_F64)) return fail(VET_ERR_INVALID_ARG, "bad argument");
+  if (mode != VET_TRANSITION_LITERAL && mode != VET_TRANSITION_TEXTBOOK) return fail(VET_ERR_INVALID_ARG, "bad mode");
+  if (F == 0) return VET_OK;
+  if (U == 0) return fail(VET_ERR_INVALID_ARG, "Empty vector dictionary");
+  if (!packed_dev || !sp_entropy_dev || (F > 1 && !tr_entropy_dev)) return fail(VET_ERR_INVALID_ARG, "null buffer");
+  if (U >= 0xFFFFFFFFll) return fail(VET_ERR_UNSUPPORTED, "too many users");
+  DeviceGuard guard(h->device);
+  h->call_frames = F;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->direct_only || F == 1) {  // no shared pass to gain: run the two stages one after the other
+    if (int rc = vet_spatial(h, packed_dev, dtype, F, U, sp_entropy_dev, sp_per_k_dev, hist0_dev, assign0_dev, stream)) return rc;
+    return vet_transition(h, packed_dev, dtype, F, U, tr_entropy_dev, tr_per_k_dev, prev_count0_dev, pairs0_dev, mode, stream);
+  }
+  return analyze_core(h, packed_dev, dtype, F, U, sp_entropy_dev, sp_per_k_dev, F, hist0_dev, assign0_dev, tr_entropy_dev,
+                      tr_per_k_dev, F - 1, prev_count0_dev, pairs0_dev, mode, st);
 }

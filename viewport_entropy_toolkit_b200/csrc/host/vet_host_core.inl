@@ -122,8 +122,12 @@ struct vet_handle {
   size_t in_bytes = 0;
   void* d_hout[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // entropy, per_k, hist0, assign x2
   size_t hout_bytes[5] = {0, 0, 0, 0, 0};
+  void* d_hout2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // transition rows: entropy, per_k, prev_count0, pairs x2
+  size_t hout2_bytes[5] = {0, 0, 0, 0, 0};
   cudaStream_t s_copy = nullptr, s_exec = nullptr, s_out = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // vet_analyze: spatial epilogue beside the transition kernel
+  cudaStream_t s_side = nullptr;                     // vet_analyze: spatial epilogue beside the transition kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // host-buffer pipelines: in / exec / out done x 2
   struct T3cOcc {
     int lw, S;
     size_t smem;
@@ -131,7 +135,7 @@ struct vet_handle {
   };
   std::vector<T3cOcc> t3c_occ;  // co-resident clusters of k_transition3c per (LUT variant, cluster size, shared memory)
   int64_t launches = 0;
-  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
+  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1, 0};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
   // optional per-kernel timing (vet_profile_*): CUDA events recorded around each launch
   bool profiling = false;
   struct Span {

@@ -174,7 +174,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         break;
       }
       Plan& pl = plan[k];
-      pl.tab_off = (T * vet::kT3TileBytes + 15) & ~(size_t)15;
+      pl.tab_off = (T * vet::kT3TileBytes + 16 + 15) & ~(size_t)15;
       const size_t dense = T * vet::t3_row_stride((uint32_t)T) * 4, hash = (size_t)2 * vet::kT3Slots * 4;
       size_t tab;
       if (pl.tab_off + dense <= budget) {
@@ -253,6 +253,8 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         A3.redo = h->d_redo;
         A3.flags = a.flags;
         A3.nvalid = h->opt[VET_OPT_T3_ASSUME_MISSING] ? nullptr : a.nvalid;  // option: always test for missing users
+        A3.ush = 3;  // granularity of the "early" bound bytes of the dense pass 2: (U - 1) >> ush <= 254
+        while (((uint64_t)(U - 1) >> A3.ush) > 254) ++A3.ush;
         // dense tables: the rows % SMs pairs left after the full rounds go to k_transition3c, one pair per
         // cluster of S CTAs (users split across the cluster) instead of one more, mostly idle, round
         int64_t tail_rows = 0;

@@ -35,7 +35,7 @@ constexpr int kT3Threads = 1024;
 constexpr uint32_t kT3Slots = 16384;
 constexpr uint32_t kT3Limit = kT3Slots * 3 / 4;
 constexpr int kT3Probes = 128;
-constexpr int kT3TileBytes = 2 * 8 + 6 * 4;  // per-tile arrays below
+constexpr int kT3TileBytes = 2 * 8 + 6 * 4 + 2;  // per-tile arrays below (the byte array needs T + 3 <= 2 T)
 constexpr uint32_t kNoTile = 0x3FFFu;        // 14-bit tile fields of s_cfl
 constexpr uint32_t kEarlyBit = 0x80000000u;
 
@@ -58,6 +58,7 @@ struct Transition3Args {
   uint32_t* redo;          // [F-1] rows to be recomputed by k_transition2 (HASH overflow)
   uint32_t* flags;
   const uint32_t* nvalid;  // [F] present users per frame (streaming kernel), or null: pairs of two complete frames skip the missing-user tests
+  int ush;                 // >= 3 with (U - 1) >> ush <= 254: granularity of the per-tile "early" bound bytes (dense pass 2)
 };
 
 template <int LW>
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
   uint32_t* s_cf = s_cfl + T;     // cnt_cf
   uint32_t* s_cl = s_cf + T;      // cnt_l
   uint32_t* s_diag = s_cl + T;    // HASH: A[p][p]
+  uint8_t* s_ub = reinterpret_cast<uint8_t*>(s_diag + T);  // DENSE: only users with (u >> ush) < s_ub[p] can still set "early"
   uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem_raw + a.tab_off);
   __shared__ double s_red[32];
   __shared__ uint32_t s_used, s_overflow, s_valid;
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
       s_cf[t] = 0u;
       s_cl[t] = 0u;
       if (MODE == kT3Hash) s_diag[t] = kEmpty;
+      if (MODE == kT3Dense) s_ub[t] = (uint8_t)0;
     }
     __syncthreads();
 
@@ -208,13 +211,20 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
             *reinterpret_cast<uint4*>(p0row + u0 + 4) = make_uint4(pc[4], pc[5], pc[6], pc[7]);
           }
           if (MODE == kT3Dense) {
+            // all 8 table entries are requested before the first one is compared (ncu: short-scoreboard stalls on
+            // the load-compare chains were the top stall reason at 32 warps per SM)
+            uint32_t slot[8], cur[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (FULL || pc[j] != kNoPair) {
-                const uint32_t p = pc[j] & 0xFFFFu, c = pc[j] >> 16;
-                ++nvalid;
-                t3_update<MODE>(s_tab, s_diag, T, p, c, u0 + j, &s_used, &s_overflow);
-              }
+            for (int j = 0; j < 8; ++j) {
+              const bool ok = FULL || pc[j] != kNoPair;
+              slot[j] = ok ? (pc[j] & 0xFFFFu) * t3_row_stride(T) + (pc[j] >> 16) : 0u;
+              cur[j] = ok ? lds_u32(s_tab + slot[j]) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (!FULL && pc[j] != kNoPair) ++nvalid;
+              if (u0 + j < cur[j]) atomicMin(s_tab + slot[j], u0 + j);
+            }
           } else {
             // users that stay in their tile (the majority) take the short dense path together; the others are
             // queued in a bit mask and go through the hash table in a compacted loop below
@@ -297,7 +307,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
     nvalid = __reduce_add_sync(kFull, nvalid);
     if (lane == 0 && nvalid) atomicAdd(&s_valid, nvalid);
     __syncthreads();
-    const double total = (double)s_valid;
+    // complete frames walked 8 users at a time (dense table): every user is a common user, nothing was counted
+    const double total = (MODE == kT3Dense && vec && full) ? (double)U : (double)s_valid;
 
     if (MODE == kT3Hash && s_overflow) {
       // too many distinct pairs for the shared-memory table: wipe it, leave the row to k_transition2
@@ -336,7 +347,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
           const uint32_t v = row[c];
           if (v != kEmpty) {
             if (c != cf) top = max(top, ((unsigned long long)(v + 1u) << 32) | c);
-            row[c] = kEmpty;
+            row[c] = 0u;  // from here on the entry COUNTS the users of (p, c): pass 2
           }
         }
 #pragma unroll
@@ -346,6 +357,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
           s_rmin[p] = best;
           s_rmax[p] = top;
           s_cfl[p] = cf | ((top ? (uint32_t)top & kNoTile : kNoTile) << 14);
+          // "early" can only be set by a user below x_p (and only if there is an l'_p at all)
+          s_ub[p] = top ? (uint8_t)min((((uint32_t)(top >> 32) - 1u) >> a.ush) + 1u, 255u) : (uint8_t)0;
         }
       }
       __syncthreads();
@@ -460,8 +473,120 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
         for (uint32_t u = tid; u < U; u += kT3Threads) second_pass(full_c, u, __ldcg(pairs + u));
       }
     };
-    if (full) pass2(std::true_type{});
-    else pass2(std::false_type{});
+    // DENSE: the table is free again after the rows were read, so pass 2 simply counts the users of every (p, c) in
+    // it -- one increment per user, no per-tile lookup, no branch on the pair -- and the counts the closed form needs
+    // (cnt_cf, m_p, cnt_l) are read off row p afterwards.  "early" (a non-first user of (p, c_f) before x_p) keeps its
+    // exact test, but behind one byte load: s_ub[p] bounds the users that can still set it, and drops to 0 once it is set.
+    // the increment; returns the bound byte of the row (0 for a missing user)
+    auto count_pair = [&](auto full_c, uint32_t pc) -> uint32_t {
+      if (!decltype(full_c)::value && pc == kNoPair) return 0u;
+      const uint32_t p = pc & 0xFFFFu, c = pc >> 16;
+      atomicAdd(s_tab + p * t3_row_stride(T) + c, 1u);
+      return (uint32_t)s_ub[p];
+    };
+    auto early_test = [&](uint32_t u, uint32_t pc) {   // rare: u may still be the user that sets "early" for its row
+      const uint32_t p = pc & 0xFFFFu, c = pc >> 16;
+      const uint32_t w = lds_u32(&s_cfl[p]);
+      if (c == (w & kNoTile) && !(w & kEarlyBit)) {
+        const uint32_t f = reinterpret_cast<const uint32_t*>(s_rmin + p)[1];
+        const uint32_t x = reinterpret_cast<const uint32_t*>(s_rmax + p)[1] - 1u;
+        if (u != f && u < x) {
+          atomicOr(&s_cfl[p], kEarlyBit);
+          s_ub[p] = (uint8_t)0;
+        }
+      }
+    };
+    auto count_user = [&](auto full_c, uint32_t ushifted, uint32_t u, uint32_t pc) {
+      if (ushifted < count_pair(full_c, pc)) early_test(u, pc);
+    };
+    // 8 users: all increments and bound-byte loads first, then the (rare) early tests
+    auto count_users8 = [&](auto full_c, uint32_t us, uint32_t u0, const uint32_t (&w)[8]) {
+      uint32_t ub[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ub[j] = count_pair(full_c, w[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (us < ub[j]) early_test(u0 + j, w[j]);
+    };
+    auto pass2_dense = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
+      const uint32_t ush = (uint32_t)a.ush;
+      if (!scratch) {
+        auto from_rows = [&](uint32_t cp, uint32_t cc) { return (FULL || (cp != 0xFFFFu && cc != 0xFFFFu)) ? (cp | (cc << 16)) : kNoPair; };
+        if (vec) {
+          uint4 np = make_uint4(0u, 0u, 0u, 0u), nc = np;
+          if (tid * 8u < U) {
+            np = __ldg(reinterpret_cast<const uint4*>(prow + tid * 8u));
+            nc = __ldg(reinterpret_cast<const uint4*>(crow + tid * 8u));
+          }
+          for (uint32_t u0 = tid * 8u; u0 < U; u0 += kT3Threads * 8u) {
+            const uint4 vp = np, vc = nc;
+            if (u0 + kT3Threads * 8u < U) {
+              np = __ldg(reinterpret_cast<const uint4*>(prow + u0 + kT3Threads * 8u));
+              nc = __ldg(reinterpret_cast<const uint4*>(crow + u0 + kT3Threads * 8u));
+            }
+            const uint32_t wp[4] = {vp.x, vp.y, vp.z, vp.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              w[j] = from_rows((wp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu, (wc[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+            count_users8(full_c, u0 >> ush, u0, w);  // ush >= 3 and u0 % 8 == 0: one shifted index for the 8 users
+          }
+        } else {
+          for (uint32_t u = tid; u < U; u += kT3Threads) count_user(full_c, u >> ush, u, from_rows(prow[u], crow[u]));
+        }
+      } else if (vec) {
+        uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+        if (tid * 8u < U) {
+          n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + tid * 8u));
+          n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + tid * 8u + 4));
+        }
+        for (uint32_t u0 = tid * 8u; u0 < U; u0 += kT3Threads * 8u) {
+          const uint4 a0 = n0, a1 = n1;
+          if (u0 + kT3Threads * 8u < U) {
+            n0 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + kT3Threads * 8u));
+            n1 = __ldcg(reinterpret_cast<const uint4*>(pairs + u0 + kT3Threads * 8u + 4));
+          }
+          const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          count_users8(full_c, u0 >> ush, u0, w);
+        }
+      } else {
+        for (uint32_t u = tid; u < U; u += kT3Threads) count_user(full_c, u >> ush, u, __ldcg(pairs + u));
+      }
+    };
+    if (MODE == kT3Dense) {
+      if (full) pass2_dense(std::true_type{});
+      else pass2_dense(std::false_type{});
+      __syncthreads();
+      // counts of row p: m_p = sum, cnt_cf = N[p][c_f], cnt_l = N[p][l'_p]; the table is left empty for the next pair
+      for (uint32_t p = wid; p < T; p += kT3Threads / 32) {
+        if (s_rmin[p] == ~0ull) continue;  // warp-uniform
+        uint32_t* row = s_tab + p * t3_row_stride(T);
+        const uint32_t w = s_cfl[p];
+        const uint32_t cf = w & kNoTile, cl = (w >> 14) & kNoTile;
+        uint32_t sum = 0, ncf = 0, ncl = 0;
+        for (uint32_t c = lane; c < T; c += 32) {
+          const uint32_t v = row[c];
+          if (v != kEmpty) {
+            sum += v;
+            if (c == cf) ncf = v;
+            if (c == cl) ncl = v;
+            row[c] = kEmpty;
+          }
+        }
+        sum = __reduce_add_sync(kFull, sum);
+        ncf = __reduce_add_sync(kFull, ncf);
+        ncl = __reduce_add_sync(kFull, ncl);
+        if (lane == 0) {
+          s_cf[p] = ncf;
+          s_other[p] = sum - ncf;
+          s_cl[p] = ncl;
+        }
+      }
+    } else {
+      if (full) pass2(std::true_type{});
+      else pass2(std::false_type{});
+    }
     __syncthreads();
 
     // ---- EU:297-330 ----

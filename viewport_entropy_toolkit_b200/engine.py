@@ -165,7 +165,7 @@ class Engine:
         opt, values = N.OPTIONS[name]
         v = C.c_int(0)
         _check(self._lib.vet_get_option(self._h, opt, C.byref(v)))
-        return next(k for k, x in values.items() if x == v.value)
+        return next((k for k, x in values.items() if x == v.value), v.value)
 
     def launch_count(self) -> int:
         return int(self._lib.vet_launch_count(self._h))
@@ -408,19 +408,58 @@ class Engine:
                                           _np_ptr(hist0), _np_ptr(assign0)))
         return dict(entropy=ent, per_k=per_k, hist0=hist0, assign0=assign0)
 
+    def _host_buffers(self, key: tuple, make, reuse: bool) -> tuple:
+        bufs = self._host_out.get(key) if reuse else None
+        if bufs is None:
+            bufs = make()
+            if reuse:
+                self._host_out = {key: bufs}
+        return bufs
+
     def transition_host(self, packed: np.ndarray, mode: str = "literal", want_per_k: bool = True,
-                        want_prev_count0: bool = True, want_pairs0: bool = True) -> Dict[str, Optional[np.ndarray]]:
+                        want_prev_count0: bool = True, want_pairs0: bool = True,
+                        reuse_buffers: bool = False) -> Dict[str, Optional[np.ndarray]]:
+        """TransitionEntropyAnalyzer.compute_entropy on host memory (vet_transition_host): frame batches with a
+        one-frame halo, upload | kernels | download on three streams; results in page-locked memory."""
         arr, dt, F, U = _host_packed(packed)
+        if mode not in ("literal", "textbook"):
+            raise ValueError("mode must be 'literal' or 'textbook'")
         R = max(F - 1, 0)
         K, T0 = len(self.tile_counts), self.num_tiles[0]
-        ent = np.empty(R, dtype=np.float64)
-        per_k = np.empty((K, R), dtype=np.float64) if want_per_k else None
-        pc = np.empty((R, T0), dtype=np.int32) if want_prev_count0 else None
-        pairs = np.empty((R, U, 2), dtype=np.uint16) if want_pairs0 else None
+        ent, per_k, pc, pairs = self._host_buffers(
+            ("tr", F, U, want_per_k, want_prev_count0, want_pairs0),
+            lambda: (_pinned((R,), np.float64), _pinned((K, R), np.float64) if want_per_k else None,
+                     _pinned((R, T0), np.int32) if want_prev_count0 else None,
+                     _pinned((R, U, 2), np.uint16) if want_pairs0 else None), reuse_buffers)
         m = N.VET_TRANSITION_LITERAL if mode == "literal" else N.VET_TRANSITION_TEXTBOOK
         _check(self._lib.vet_transition_host(self._h, _host_ptr(arr), dt, F, U, ent.ctypes.data, _np_ptr(per_k),
                                              _np_ptr(pc), _np_ptr(pairs), m))
         return dict(entropy=ent, per_k=per_k, prev_count0=pc, pairs0=pairs)
+
+    def analyze_host(self, packed: np.ndarray, mode: str = "literal", want_per_k: bool = True, want_hist0: bool = True,
+                     want_assign0: bool = True, want_prev_count0: bool = True, want_pairs0: bool = True,
+                     reuse_buffers: bool = False) -> Tuple[Dict[str, Optional[np.ndarray]], Dict[str, Optional[np.ndarray]]]:
+        """Both analyzers on host memory with ONE upload of the input (vet_analyze_host) -> (spatial, transition)
+        dicts of numpy arrays like spatial_host / transition_host."""
+        arr, dt, F, U = _host_packed(packed)
+        if mode not in ("literal", "textbook"):
+            raise ValueError("mode must be 'literal' or 'textbook'")
+        R = max(F - 1, 0)
+        K, T0 = len(self.tile_counts), self.num_tiles[0]
+        bufs = self._host_buffers(
+            ("an", F, U, want_per_k, want_hist0, want_assign0, want_prev_count0, want_pairs0),
+            lambda: (_pinned((F,), np.float64), _pinned((K, F), np.float64) if want_per_k else None,
+                     _pinned((F, T0), np.float64) if want_hist0 else None,
+                     _pinned((F, U), np.uint16) if want_assign0 else None,
+                     _pinned((R,), np.float64), _pinned((K, R), np.float64) if want_per_k else None,
+                     _pinned((R, T0), np.int32) if want_prev_count0 else None,
+                     _pinned((R, U, 2), np.uint16) if want_pairs0 else None), reuse_buffers)
+        ent, per_k, hist0, assign0, tent, tper_k, pc, pairs = bufs
+        m = N.VET_TRANSITION_LITERAL if mode == "literal" else N.VET_TRANSITION_TEXTBOOK
+        _check(self._lib.vet_analyze_host(self._h, _host_ptr(arr), dt, F, U, ent.ctypes.data, _np_ptr(per_k), _np_ptr(hist0),
+                                          _np_ptr(assign0), tent.ctypes.data, _np_ptr(tper_k), _np_ptr(pc), _np_ptr(pairs), m))
+        return (dict(entropy=ent, per_k=per_k, hist0=hist0, assign0=assign0),
+                dict(entropy=tent, per_k=tper_k, prev_count0=pc, pairs0=pairs))
 
 
 _TORCH_OF = {np.float64: torch.float64, np.uint16: torch.uint16, np.int32: torch.int32}
