@@ -111,14 +111,17 @@ enum {
   VET_OPT_WEIGHTED_KERNEL = 0,   /* 0 auto (tensor cores from 512 frames per call), 1 FP64 pipe, 2 tensor cores (int8 slices) */
   VET_OPT_STREAM_KERNEL = 1,     /* 0 auto, 1 plain loads (k_stream_simple), 2 cell histograms only (no direct tile
                                     histograms), 3 global-table regime without the 16-bit privatised histogram */
-  VET_OPT_TRANSITION_KERNEL = 2, /* 0 auto (two-pass kernels), 1 k_transition, 2 k_transition2 */
+  VET_OPT_TRANSITION_KERNEL = 2, /* 0 auto (one-pass kernel k_transition4 where its tables fit, the two-pass kernels behind it),
+                                    1 k_transition, 2 k_transition2, 3 two-pass kernels (k_transition3 / 3c) */
   VET_OPT_CLUSTER_TAIL = 3,      /* default 1: pairs left after the full rounds go to the cluster kernel when it pays;
                                     0 never, 2 whenever it can run */
   VET_OPT_T3_PAIR_SCRATCH = 4,   /* 1: keep the 4 B/user pair scratch also when the rows hold tile ids */
   VET_OPT_T3_ASSUME_MISSING = 5, /* 1: always test for missing users (no complete-frame variant) */
   VET_OPT_ANALYZE_OVERLAP = 6,   /* default 1: vet_analyze overlaps its spatial and transition stages; 0 runs them in sequence */
   VET_OPT_HOST_BATCH_FRAMES = 7, /* frames per batch of the host-buffer pipelines; 0 = auto (about 256 MiB of input per batch) */
-  VET_OPT_COUNT = 8
+  VET_OPT_T4_LIST_CAP = 8,       /* one-pass kernel: capacity of the list of users with an unranked tile delta
+                                    (0 = 1024; smaller values send more pairs to the two-pass kernels: tests) */
+  VET_OPT_COUNT = 9
 };
 int vet_set_option(vet_handle* h, int option, int value);
 int vet_get_option(const vet_handle* h, int option, int* value);

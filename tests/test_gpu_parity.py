@@ -728,6 +728,7 @@ def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs):
     g = torch.Generator(device="cuda").manual_seed(7)
     p[F - 2:, :, 1:] = torch.rand((2, U, 2), generator=g, device="cuda")   # iid frames: every row of the table in use
     e = engine(vet, tcs, use_w=False)
+    e.set_option("transition_kernel", "v3")   # the two-pass kernels themselves (auto puts the one-pass kernel in front)
     res = {}
     e.profile(True)
     for cl in ("0", "force"):      # force: also below the frame size from which the host picks it by itself
@@ -754,6 +755,58 @@ def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs):
     if F <= 3:
         ref = orc.transition_analyzer(p.cpu().numpy(), W0, H0, tcs, mode="literal")
         b = res["force"][0]
+        assert np.array_equal(b.pairs0.cpu().numpy(), ref["pairs0"])
+        assert np.array_equal(b.prev_count0.cpu().numpy(), ref["prev_count0"])
+        np.testing.assert_allclose(b.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    e.close()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(F=40, U=100_000, tcs=[200], use_w=False),                                  # tile ids from the streaming kernel, 512-thread CTAs
+    dict(F=24, U=100_000, tcs=[200, 500, 1000], use_w=False),                       # LUT staged / from global memory, 1024-thread CTAs for 1001 tiles
+    dict(F=12, U=5000, tcs=[200], use_w=True, dtype=np.float64, missing=0.1),
+    dict(F=7, U=3001, tcs=[100, 20], use_w=False, missing=0.02),                    # odd U: scalar loads
+    dict(F=9, U=600, tcs=[200], use_w=False, iid=True),                             # iid: most users on the list of unranked deltas (sorted path)
+    dict(F=5, U=3000, tcs=[50], use_w=True, iid=True),                              # iid: lists overflow -> pairs redone by the two-pass kernels
+    dict(F=9, U=4000, tcs=[200, 500], use_w=False, cap=8),                          # tiny list: a mix of pairs kept and pairs handed on
+    dict(F=2, U=9, tcs=[200], use_w=False),
+])
+def test_one_pass_transition_kernel_equals_two_pass_kernels(vet, cfg):
+    """k_transition4 (one walk over the users: [16][T] tables of ranked tile deltas with first/second user and count,
+    sorted list of the unranked users, pairs with a full list handed to k_transition3) against k_transition3 alone on
+    the same tensors: every output bit for bit, for transition() and analyze(); small cases also against the oracle."""
+    import bench
+    F, U, tcs = cfg["F"], cfg["U"], cfg["tcs"]
+    if U >= 50_000:
+        p = bench.synth_on_device(torch, F, U, 717 + U, torch.device("cuda"))
+        p[3, ::9, 1] = float("nan")
+        g = torch.Generator(device="cuda").manual_seed(5)
+        p[F - 3:F - 1, :700, 1:] = torch.rand((2, 700, 2), generator=g, device="cuda")      # a burst of large jumps: list entries
+        p[F - 6:F - 4, :, 1:] = torch.rand((2, U, 2), generator=g, device="cuda")           # iid frames: lists overflow
+    else:
+        p = dev(synth(F, U, 818 + U, iid=cfg.get("iid", False), missing=cfg.get("missing", 0.0), dtype=cfg.get("dtype", np.float32)))
+    e = engine(vet, tcs, fov=90.0, use_w=cfg["use_w"])
+    e.set_option("weighted_kernel", "fp64")
+    e.set_option("t4_list_cap", cfg.get("cap", 0))
+    res = {}
+    e.profile(True)
+    for impl in ("v3", "auto"):
+        e.set_option("transition_kernel", impl)
+        tr = e.transition(p)
+        sp, tr2 = e.analyze(p)
+        assert e.poll_flags() == 0
+        res[impl] = (tr, tr2, sp)
+    e.profile(False)
+    for i in (0, 1):
+        a, b = res["v3"][i], res["auto"][i]
+        assert torch.equal(a.pairs0, b.pairs0) and torch.equal(a.prev_count0, b.prev_count0)
+        assert np.array_equal(a.per_k.cpu().numpy(), b.per_k.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(a.entropy.cpu().numpy(), b.entropy.cpu().numpy(), equal_nan=True)
+    a, b = res["v3"][2], res["auto"][2]
+    assert torch.equal(a.assign0, b.assign0) and torch.equal(a.hist0, b.hist0) and torch.equal(a.entropy, b.entropy)
+    if F * U <= 100_000:
+        ref = orc.transition_analyzer(p.cpu().numpy(), W0, H0, tcs, mode="literal")
+        b = res["auto"][0]
         assert np.array_equal(b.pairs0.cpu().numpy(), ref["pairs0"])
         assert np.array_equal(b.prev_count0.cpu().numpy(), ref["prev_count0"])
         np.testing.assert_allclose(b.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)

@@ -28,7 +28,8 @@ def timed(fn, n=5):
     return a.elapsed_time(b) / n
 
 
-for overlap, cl in (("on", "auto"), ("off", "auto"), ("on", "off")):
+for tk, overlap, cl in (("auto", "on", "auto"), ("v3", "on", "auto"), ("v3", "off", "auto")):
+    eng.set_option("transition_kernel", tk)   # auto: fused streaming + transition pass; v3: two-pass kernels behind the stream
     eng.set_option("analyze_overlap", overlap)
     eng.set_option("cluster_tail", cl)
     eng.profile(True)
@@ -36,5 +37,5 @@ for overlap, cl in (("on", "auto"), ("off", "auto"), ("on", "off")):
     prof = eng.profile_read()
     eng.profile(False)
     t_tr = timed(lambda: eng.transition(p, want_pairs0=False, want_per_k=False))
-    print(f"F={F} U={U} overlap={overlap} cluster_tail={cl}: analyze {t_an:.4f} ms, transition {t_tr:.4f} ms, "
+    print(f"F={F} U={U} transition_kernel={tk} overlap={overlap} cluster_tail={cl}: analyze {t_an:.4f} ms, transition {t_tr:.4f} ms, "
           f"per kernel (ms, launches over 7 calls) {prof}", flush=True)

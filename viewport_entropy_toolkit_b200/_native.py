@@ -27,12 +27,13 @@ VET_REGIME_AUTO, VET_REGIME_DIRECT = 0, 1
 OPTIONS = {
     "weighted_kernel": (0, {"auto": 0, "fp64": 1, "i8": 2}),
     "stream_kernel": (1, {"auto": 0, "simple": 1, "cells": 2, "global": 3}),
-    "transition_kernel": (2, {"auto": 0, "v1": 1, "v2": 2}),
+    "transition_kernel": (2, {"auto": 0, "v1": 1, "v2": 2, "v3": 3}),
     "cluster_tail": (3, {"off": 0, "auto": 1, "force": 2}),
     "t3_pair_scratch": (4, {"off": 0, "on": 1}),
     "t3_assume_missing": (5, {"off": 0, "on": 1}),
     "analyze_overlap": (6, {"off": 0, "on": 1}),
     "host_batch_frames": (7, {"auto": 0}),
+    "t4_list_cap": (8, {"auto": 0}),
 }
 
 

@@ -227,6 +227,8 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_tables);
   cudaFree(h->d_pairs);
   cudaFree(h->d_redo);
+  cudaFree(h->d_t4);
+  cudaFree(h->d_rows);
   cudaFree(h->d_trk);
   cudaFree(h->d_planes);
   cudaFree(h->d_dirty);

@@ -31,6 +31,11 @@ struct TileSet {
   uint16_t* d_lut = nullptr;      // [C]
   uint8_t* d_lut8 = nullptr;      // [C] same table in bytes when T <= 255 (halves the shared-memory LUT)
   std::vector<uint16_t> h_lut;
+  // one-pass transition kernel (vet_transition4.cuh)
+  uint16_t* d_drank = nullptr;    // [bands][2 win + 2] rank (as rank * T * 4) of the tile-index delta c - p of a transition,
+                                  // per band of 2^band_shift consecutive previous tiles (0xFFFF = unranked)
+  int* d_rank_delta = nullptr;    // [bands][16] delta of every rank (rank 0 = staying in the tile)
+  int band_shift = 0, win = 0, bands = 0;
   uint32_t* d_col_ptr = nullptr;  // [T+1]
   uint32_t* d_cell_idx = nullptr;
   double* d_w_val = nullptr;
@@ -113,6 +118,10 @@ struct vet_handle {
   int64_t call_frames = 0;       // frames of the API call in progress: its batches all take the same weighted kernel
   uint32_t* d_redo = nullptr;   // [rows] frame pairs the two-pass transition kernel left to k_transition2
   size_t redo_bytes = 0;
+  void* d_t4 = nullptr;         // one-pass transition kernel: per tile count the count and the flags of the pairs it
+  size_t t4_bytes = 0;          // leaves to the two-pass kernels
+  uint16_t* d_rows = nullptr;   // [frames, U] tile ids of one tile count, relabelled from the cell ids (several tile counts)
+  size_t rows_bytes = 0;
   double* d_trk = nullptr;      // [K, rows] per-tile-count transition entropies when the caller wants none
   size_t trk_bytes = 0;
   uint32_t tables_cap = 0;  // slot count the tables are currently laid out (and cleared) for
@@ -135,7 +144,7 @@ struct vet_handle {
   };
   std::vector<T3cOcc> t3c_occ;  // co-resident clusters of k_transition3c per (LUT variant, cluster size, shared memory)
   int64_t launches = 0;
-  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1, 0};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
+  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1, 0, 0};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
   // optional per-kernel timing (vet_profile_*): CUDA events recorded around each launch
   bool profiling = false;
   struct Span {

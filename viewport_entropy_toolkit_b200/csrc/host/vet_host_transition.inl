@@ -105,6 +105,38 @@ int t3c_max_clusters(vet_handle* h, int lw, int S, size_t smem) {
   return n;
 }
 
+// k_transition4 (one pass over rows of tile ids: [3][16][T] tables + list of unranked users): shared-memory layout
+struct Plan4 {
+  bool ok = false;
+  int threads = 512, ctas_per_sm = 1;
+  size_t tab_off = 0, key_off = 0, term_off = 0, rdelta_off = 0, drank_off = 0, smem = 0;
+};
+Plan4 plan_transition4(const vet_handle* h, const TileSet& ts) {
+  Plan4 p;
+  if (!ts.d_drank) return p;
+  const size_t T = (size_t)ts.T;
+  const size_t budget = h->smem_optin - kStaticSmemSlack;
+  p.tab_off = 0;
+  p.key_off = (size_t)3 * (vet::kT4Ranks * T + 4) * 4;  // three [16][T] tables with a dummy entry (+ padding) each
+  p.term_off = p.key_off + (size_t)vet::kT4OvfCap * 8;
+  p.rdelta_off = p.term_off + T * 8;
+  p.drank_off = (p.rdelta_off + (size_t)ts.bands * vet::kT4Ranks * 4 + 15) & ~(size_t)15;
+  p.smem = (p.drank_off + (size_t)ts.bands * (2 * ts.win + 2) * 2 + 15) & ~(size_t)15;
+  if (p.smem > budget) return p;
+  p.ok = true;
+  // 512 threads when several CTAs fit an SM (228 KB of shared memory; 64 registers per thread: 1024 threads), else
+  // one CTA of 1024
+  const int fit = (int)(((size_t)228 * 1024) / (p.smem + 1024));
+  if (fit >= 2) {
+    p.threads = 512;
+    p.ctas_per_sm = 2;
+  } else {
+    p.threads = 1024;
+    p.ctas_per_sm = 1;
+  }
+  return p;
+}
+
 int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st) {
   // capacity >= 2 x the most distinct (prev,cur) pairs a frame pair can hold
   const uint64_t max_pairs = std::min<uint64_t>((uint64_t)U, (uint64_t)Tmax * Tmax);
@@ -213,6 +245,14 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         if (int rc = grow((void**)&h->d_pairs, &h->pairs_bytes, (size_t)std::max(blocks, blocks3) * U * 4)) return rc;
       if (int rc = grow((void**)&h->d_redo, &h->redo_bytes, (size_t)rows * 4)) return rc;
       VET_CUDA(cudaMemsetAsync(h->d_redo, 0, (size_t)rows * 4, st));
+      // one-pass kernel in front (VET_OPT_TRANSITION_KERNEL auto): per tile count a counter and the flags of the pairs
+      // it leaves to the two-pass kernels
+      const bool use_t4 = h->opt[VET_OPT_TRANSITION_KERNEL] == 0;
+      const size_t t4_zero = (size_t)a.K * 16 + (size_t)a.K * rows * 4;
+      if (use_t4) {
+        if (int rc = grow(&h->d_t4, &h->t4_bytes, t4_zero)) return rc;
+        VET_CUDA(cudaMemsetAsync(h->d_t4, 0, t4_zero, st));
+      }
       double* per_k = a.per_k;
       int64_t stride = a.per_k_stride;
       if (a.K > 1 && !per_k) {
@@ -222,7 +262,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
       }
       bool any_hash = false;
       for (int k = 0; k < a.K; ++k) {
-        const Plan& pl = plan[k];
+        Plan pl = plan[k];
         double* out_k = a.K == 1 ? a.entropy : per_k + k * stride;
         if (pl.mode < 0) {
           vet::TransitionArgs a1 = a;
@@ -255,11 +295,71 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         A3.nvalid = h->opt[VET_OPT_T3_ASSUME_MISSING] ? nullptr : a.nvalid;  // option: always test for missing users
         A3.ush = 3;  // granularity of the "early" bound bytes of the dense pass 2: (U - 1) >> ush <= 254
         while (((uint64_t)(U - 1) >> A3.ush) > 254) ++A3.ush;
+        bool t4_done = false;
+        // the k-th tile set of the handle (cell LUT or, with tile ids in the rows, the identity table over it)
+        const TileSet& tsk = h->ts[std::min(k, h->K - 1)];
+        const Plan4 p4 = (use_t4 && k < h->K && tsk.T == a.T[k]) ? plan_transition4(h, tsk) : Plan4{};
+        if (p4.ok) {
+          if (pl.lw != vet::kLutIdentity) {
+            // several tile counts: the rows hold cell ids -> tile ids of this tile count first (one lookup per sample
+            // instead of two per user and pair inside the kernels)
+            if (int rc = grow((void**)&h->d_rows, &h->rows_bytes, (size_t)a.F * U * 2 + 16)) return rc;
+            const int64_t n = a.F * U;
+            LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+            vet::k_relabel_rows<<<(unsigned)std::min<int64_t>((n / 8 + 255) / 256 + 1, (int64_t)h->sm_count * 16), 256, 0, st>>>(
+                a.cell16, a.lut[k], n, h->d_rows);
+            VET_CUDA(cudaGetLastError());
+            A3.cell16 = h->d_rows;
+            A3.lut_src = nullptr;
+            A3.pair_scratch = keep_scratch ? h->d_pairs : nullptr;
+            pl.lw = vet::kLutIdentity;
+            pl.lut = nullptr;
+            pl.smem = pl.lut_off;
+          }
+          if (A3.pairs0) {
+            const int64_t n = rows * U;
+            LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+            vet::k_pairs_from_rows<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16), 256, 0, st>>>(
+                A3.cell16, a.F, U, reinterpret_cast<uint32_t*>(A3.pairs0));
+            VET_CUDA(cudaGetLastError());
+            A3.pairs0 = nullptr;
+          }
+          char* base = (char*)h->d_t4;
+          uint32_t* count4 = (uint32_t*)(base + (size_t)k * 16);
+          uint32_t* redo4 = (uint32_t*)(base + (size_t)a.K * 16 + (size_t)k * rows * 4);
+          vet::Transition4Args A4{};
+          A4.t = A3;
+          A4.t.tab_off = (int)p4.tab_off;
+          A4.t.pair_scratch = nullptr;
+          A4.t.redo = redo4;
+          A4.drank = tsk.d_drank;
+          A4.rank_delta = tsk.d_rank_delta;
+          A4.band_shift = tsk.band_shift;
+          A4.win = tsk.win;
+          A4.bands = tsk.bands;
+          A4.rdelta_off = (int)p4.rdelta_off;
+          A4.key_off = (int)p4.key_off;
+          A4.drank_off = (int)p4.drank_off;
+          A4.term_off = (int)p4.term_off;
+          A4.redo_count = count4;
+          A4.ovf_cap = h->opt[VET_OPT_T4_LIST_CAP] > 0 ? h->opt[VET_OPT_T4_LIST_CAP] : vet::kT4OvfCap;
+          const int blocks4 = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * p4.ctas_per_sm);
+          {
+            LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+            VET_CUDA(cudaFuncSetAttribute(vet::k_transition4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p4.smem));
+            vet::k_transition4<<<blocks4, p4.threads, p4.smem, st>>>(A4);
+            VET_CUDA(cudaGetLastError());
+          }
+          // the two-pass kernel below only takes the pairs the one-pass kernel flagged (its CTAs leave at once when none)
+          A3.only_rows = redo4;
+          A3.only_count = count4;
+          t4_done = true;
+        }
         // dense tables: the rows % SMs pairs left after the full rounds go to k_transition3c, one pair per
         // cluster of S CTAs (users split across the cluster) instead of one more, mostly idle, round
         int64_t tail_rows = 0;
         int tail_S = 0;
-        if (pl.mode == vet::kT3Dense && cluster_tail) {
+        if (pl.mode == vet::kT3Dense && cluster_tail && !t4_done) {
           const int64_t rem = rows % h->sm_count;
           // a pair costs ~0.33 ns per user on one CTA; the cluster barriers, the merge of the tables and the extra
           // launch ~20-40 us: worth it from ~130k users saved per CTA (measured neutral to slower at 100k users)
@@ -284,7 +384,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
           if (r0 == 0) continue;
         }
         const int blocks3k = (int)std::min<int64_t>(A3.F - 1, h->sm_count);
-        LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+        LaunchTimer lt(h, t4_done ? VET_KERNEL_TRANSITION_TAIL : VET_KERNEL_TRANSITION, st);
 #define VET_T3(MODE, LW)                                                                                              \
   do {                                                                                                                \
     VET_CUDA(cudaFuncSetAttribute(vet::k_transition3<MODE, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \

@@ -120,19 +120,27 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 //   H = -sum_{t: hist>0} p log2 p,  p = hist/total
 //   n = T if (weighted or total > T) else total;  Hn = H / (-n * (1/n) * log2(1/n))
 // Called by all threads of the block; hist in shared memory.
+// The sum runs on warp 0 alone, lane = t mod 32 and a butterfly at the end: the same order as k_entropy_rows, so a
+// histogram gives the same bits whichever kernel finishes it (the unweighted cell and tile paths are interchangeable).
 // norm_T: the tile count of the normalisation when it differs from the histogram length (naive
 // lat/lon tiling: codes of the closed upper edges exist beyond num_tiles, EU:409,443-448); 0 = T.
 __device__ __forceinline__ double normalized_entropy(const double* hist, int T, double total, bool by_tiles_always,
                                                      double* red, int norm_T = 0) {
-  double acc = 0.0;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const double w = hist[t];
-    if (w > 0.0) {
-      const double p = w / total;
-      acc -= p * log2(p);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < T; t += 32) {
+      const double w = hist[t];
+      if (w > 0.0) {
+        const double p = w / total;
+        acc -= p * log2(p);
+      }
     }
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) red[0] = acc;
   }
-  const double Hs = block_sum(acc, red);
+  __syncthreads();
+  const double Hs = red[0];
   const double nt = (double)(norm_T > 0 ? norm_T : T);
   const double n = (by_tiles_always || total > nt) ? nt : total;
   const double mp = 1.0 / n;

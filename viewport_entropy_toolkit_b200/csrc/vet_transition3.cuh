@@ -59,6 +59,8 @@ struct Transition3Args {
   uint32_t* flags;
   const uint32_t* nvalid;  // [F] present users per frame (streaming kernel), or null: pairs of two complete frames skip the missing-user tests
   int ush;                 // >= 3 with (U - 1) >> ush <= 254: granularity of the per-tile "early" bound bytes (dense pass 2)
+  const uint32_t* only_rows;   // optional [F-1]: process only the flagged pairs (left over by the fused pass, vet_stream_trans.cuh)
+  const uint32_t* only_count;  // with only_rows: number of flagged pairs (0: the CTAs leave at once)
 };
 
 template <int LW>
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
+  if (a.only_rows && __ldg(a.only_count) == 0u) return;  // nothing was left over
   {
     const uint32_t words = MODE == kT3Dense ? T * t3_row_stride(T) : 2u * kT3Slots;
     for (uint32_t i = tid; i < words; i += kT3Threads) s_tab[i] = kEmpty;
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_transition3(Transition3Args a
   const bool vec = (U & 7u) == 0u;
 
   for (int64_t r = blockIdx.x; r < a.F - 1; r += gridDim.x) {
+    if (a.only_rows && __ldg(a.only_rows + r) == 0u) continue;  // uniform over the CTA
     const uint16_t* __restrict__ prow = a.cell16 + r * (int64_t)U;
     const uint16_t* __restrict__ crow = prow + U;
     uint32_t* __restrict__ p0row = a.pairs0 ? reinterpret_cast<uint32_t*>(a.pairs0) + r * (int64_t)U : nullptr;
