@@ -533,6 +533,38 @@ def test_analyzers_end_to_end_vs_reference(vet, tmp_path):
     assert (tmp_path / "out" / "e2e_test.csv").exists()
 
 
+def test_analyzer_results_are_lazy_at_scale(vet, tmp_path):
+    """SpatialEntropyAnalyzer.compute_entropy() on a configs[2]-size video (100k users x 3600 frames, 4.3 GB on the
+    host): the DataFrame comes back in seconds because the per-frame `tile_weights` / `tile_assignments` dicts
+    (SA:152-163) are views that build themselves on access; a row that is read equals the eagerly built dict."""
+    import time
+    import bench
+    F, U = 3600, 100_000
+    packed = bench.synth_on_device(torch, F, U, 4711, torch.device("cuda")).cpu().numpy()
+    cfg = vet.AnalyzerConfig(tile_counts=[200], output_dir=tmp_path, entropy_config=vet.EntropyConfig(fov_angle=90.0))
+    sa = vet.SpatialEntropyAnalyzer(cfg)
+    sa.load_packed(packed, identifiers=[f"u{u}" for u in range(U)])
+    t0 = time.perf_counter()
+    df = sa.compute_entropy()
+    dt = time.perf_counter() - t0
+    assert dt < 30.0, f"compute_entropy took {dt:.1f} s"
+    assert list(df.columns) == ["time", "entropy", "tile_weights", "tile_assignments"] and len(df) == F
+    assert all(row._d is None for row in df["tile_assignments"]), "no per-frame dict built before it is read"
+    ref = sa.engine.spatial(dev(packed[1000:1002]))
+    w = df["tile_weights"][1000]
+    a = df["tile_assignments"][1001]
+    assert len(a) == U and a["u5"] == int(ref.assign0[1, 5]) and "nobody" not in a
+    centres = sa._fibonacci_vectors[200]
+    h = ref.hist0[0].cpu().numpy()
+    want = {centres[i]: float(h[i]) for i in np.flatnonzero(h)}   # two frames alone: the FP64 weighted kernel
+    assert set(w) == set(want)
+    np.testing.assert_allclose([w[k] for k in want], list(want.values()), rtol=RTOL)
+    assert df["tile_weights"][1000] == dict(w)                    # a view compares equal to the dict it stands for
+    np.testing.assert_allclose(df["entropy"][1000], float(ref.entropy[0]), rtol=RTOL)
+    sa.create_visualization("lazy_case")   # the CSV writer of SA:211-219 only needs time and entropy
+    assert (tmp_path / "lazy_case.csv").exists()
+
+
 @pytest.mark.parametrize("use_w,tcs", [(True, [200, 20]), (False, [50, 200, 1000]), (False, [200])])
 def test_analyze_equals_separate_stages(vet, use_w, tcs):
     """vet_analyze (one pass over the input) == vet_spatial + vet_transition: integer outputs bit for bit,
@@ -652,6 +684,42 @@ def test_weighted_tensor_core_path_vs_oracle(vet, cfg):
     sp64 = e.spatial(dev(p))
     np.testing.assert_allclose(sp.hist0.cpu().numpy(), sp64.hist0.cpu().numpy(), rtol=RTOL, atol=cfg["U"] * I8_QUANT)
     np.testing.assert_allclose(sp.entropy.cpu().numpy(), sp64.entropy.cpu().numpy(), rtol=RTOL, atol=ATOL, equal_nan=True)
+    e.close()
+
+
+def test_weighted_default_dispatch_sparse_frames(vet):
+    """The DEFAULT dispatch (no kernel pinned) on 600 frames of 1-5 users each -- the tensor-core histogram from 512
+    frames per call on -- against the oracle: the support of every hist0 row (tiles with d < fov/2, EU:133) is the
+    oracle's, entries above the quantisation floor users * 2^-39 / 1e-9 agree to a pure relative 1e-9, all entries to
+    users * 2^-39 absolute, entropies to 1e-9; and the first 300 frames on their own (FP64 kernel: fewer than 512
+    frames) give the same support and the same values to 1e-9."""
+    rng = np.random.default_rng(4242)
+    F, U = 600, 5
+    p = synth(F, U, 9191, iid=True)
+    present = rng.integers(1, U + 1, F)                      # 1..5 users per frame
+    for f in range(F):
+        p[f, present[f]:, 1:] = np.nan
+    e = engine(vet, [200, 50], fov=90.0)
+    assert e.get_option("weighted_kernel") == "auto"
+    e.profile(True)
+    d = e.spatial(dev(p))
+    assert e.poll_flags() == 0
+    ref = orc.spatial_analyzer(p, W0, H0, [200, 50], 90.0, True, 2.0)
+    h, rh = d.hist0.cpu().numpy(), ref["hist0"]
+    assert np.array_equal(h > 0, rh > 0), "support of the weighted histogram rows"
+    quantum = 2.0 ** -39
+    floor = present[:, None] * quantum / 1e-9
+    big = rh > floor
+    assert big.sum() > 0.8 * (rh > 0).sum()   # the entries below the floor are the weights at the very edge of the FOV
+    np.testing.assert_allclose(h[big], rh[big], rtol=1e-9, atol=0)
+    assert np.all(np.abs(h - rh) <= present[:, None] * quantum)
+    np.testing.assert_allclose(d.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(d.assign0.cpu().numpy(), ref["assign0"])
+    short = e.spatial(dev(p[:300]))                           # fewer than 512 frames: the FP64 kernel
+    hs = short.hist0.cpu().numpy()
+    assert np.array_equal(hs > 0, h[:300] > 0)
+    np.testing.assert_allclose(hs[big[:300]], h[:300][big[:300]], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(short.entropy.cpu().numpy(), d.entropy.cpu().numpy()[:300], rtol=RTOL, atol=ATOL)
     e.close()
 
 

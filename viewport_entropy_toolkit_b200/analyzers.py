@@ -13,6 +13,7 @@ return tensors instead of per-frame Python dicts.
 from __future__ import annotations
 
 import logging
+from collections.abc import Mapping
 from datetime import datetime
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence
@@ -29,6 +30,36 @@ from .engine import Engine, SpatialResult, TransitionResult, get_engine
 from .ingest import load_directory
 
 logger = logging.getLogger(__name__)
+
+
+class LazyRowDict(Mapping):
+    """Read-only dict view of one result row (`tile_weights` / `tile_assignments` of SA:152-163, TA:163-170): the
+    dict the reference stores per frame is built from the row of the result array on first access, so a
+    100k-user x 3600-frame video does not allocate 3.6e8 Python objects up front.  Compares equal to the dict it
+    stands for; `create_visualization`-style consumers (`.items()`, `len`, `in`, iteration) work unchanged."""
+    __slots__ = ("_make", "_d")
+
+    def __init__(self, make):
+        self._make = make
+        self._d = None
+
+    def _dict(self) -> dict:
+        if self._d is None:
+            self._d = self._make()
+            self._make = None
+        return self._d
+
+    def __getitem__(self, key):
+        return self._dict()[key]
+
+    def __iter__(self):
+        return iter(self._dict())
+
+    def __len__(self):
+        return len(self._dict())
+
+    def __repr__(self):
+        return repr(self._dict())
 
 
 def _lattice_vectors(tile_count: int) -> List[Vector]:
@@ -76,6 +107,11 @@ class _AnalyzerBase:
         if not self._data_cache:
             raise ValidationError("No data available. Call process_directory first.")
         return torch.from_numpy(np.ascontiguousarray(self._data_cache["packed"])).to(self.engine.device)
+
+    def _host_packed(self) -> np.ndarray:
+        if not self._data_cache:
+            raise ValidationError("No data available. Call process_directory first.")
+        return np.ascontiguousarray(self._data_cache["packed"])
 
     def _save_csv(self, base_name: str) -> Path:
         path = self.config.get_output_path(base_name, DEFAULT_OUTPUT_FORMATS["data"])
@@ -138,20 +174,25 @@ class SpatialEntropyAnalyzer(_AnalyzerBase):
     def compute_entropy(self) -> pd.DataFrame:
         if not self._data_cache:
             raise ValidationError("No data available. Call process_directory first.")
-        res = self.compute_entropy_packed(self._device_packed())
-        ent = res.entropy.cpu().numpy()
-        hist0 = res.hist0.cpu().numpy()
-        assign0 = res.assign0.cpu().numpy()
+        # host-buffer pipeline of the library (frame batches, upload | kernels | download on three streams): the
+        # video need not fit the GPU, the results arrive in page-locked host arrays
+        res = self.engine.spatial_host(self._host_packed())
+        self.engine.raise_for_flags()
+        ent, hist0, assign0 = res["entropy"], res["hist0"], res["assign0"]
         centres = self._fibonacci_vectors[self.config.tile_counts[0]]
         ids = self._data_cache["identifiers"]
-        rows = {"time": [], "entropy": [], "tile_weights": [], "tile_assignments": []}
-        for f, t in enumerate(self._data_cache["times"]):
-            nz = np.flatnonzero(hist0[f])
-            rows["time"].append(t)
-            rows["entropy"].append(ent[f])
-            rows["tile_weights"].append({centres[i]: float(hist0[f, i]) for i in nz})
-            rows["tile_assignments"].append({ids[u]: int(a) for u, a in enumerate(assign0[f]) if a != 0xFFFF})
-        self._entropy_results = pd.DataFrame(rows)
+
+        def weights(f):
+            return lambda: {centres[i]: float(hist0[f, i]) for i in np.flatnonzero(hist0[f])}
+
+        def assignments(f):
+            return lambda: {ids[u]: int(assign0[f, u]) for u in np.flatnonzero(assign0[f] != 0xFFFF)}
+
+        F = len(ent)
+        self._entropy_results = pd.DataFrame({
+            "time": list(self._data_cache["times"]), "entropy": list(ent),
+            "tile_weights": [LazyRowDict(weights(f)) for f in range(F)],
+            "tile_assignments": [LazyRowDict(assignments(f)) for f in range(F)]})
         return self._entropy_results
 
 
@@ -173,22 +214,24 @@ class TransitionEntropyAnalyzer(_AnalyzerBase):
     def compute_entropy(self) -> pd.DataFrame:
         if not self._data_cache:
             raise ValidationError("No data available. Call process_directory first.")
-        res = self.compute_entropy_packed(self._device_packed())
-        ent = res.entropy.cpu().numpy()
-        counts = res.prev_count0.cpu().numpy()
-        pairs = res.pairs0.cpu().numpy()
+        res = self.engine.transition_host(self._host_packed(), mode=self.mode)
+        self.engine.raise_for_flags()
+        ent, counts, pairs = res["entropy"], res["prev_count0"], res["pairs0"]
         centres = self._fibonacci_vectors[self.config.tile_counts[0]]
         ids = self._data_cache["identifiers"]
         times = self._data_cache["times"]
-        rows = {"time": [], "entropy": [], "tile_weights": [], "tile_assignments": []}
-        for r in range(len(ent)):
-            nz = np.flatnonzero(counts[r])
-            rows["time"].append(times[r + 1])
-            rows["entropy"].append(ent[r])
-            rows["tile_weights"].append({centres[i]: int(counts[r, i]) for i in nz})
-            rows["tile_assignments"].append(
-                {ids[u]: (int(p), int(c)) for u, (p, c) in enumerate(pairs[r]) if p != 0xFFFF})
-        self._entropy_results = pd.DataFrame(rows)
+
+        def weights(r):
+            return lambda: {centres[i]: int(counts[r, i]) for i in np.flatnonzero(counts[r])}
+
+        def assignments(r):
+            return lambda: {ids[u]: (int(pairs[r, u, 0]), int(pairs[r, u, 1])) for u in np.flatnonzero(pairs[r, :, 0] != 0xFFFF)}
+
+        R = len(ent)
+        self._entropy_results = pd.DataFrame({
+            "time": [times[r + 1] for r in range(R)], "entropy": list(ent),
+            "tile_weights": [LazyRowDict(weights(r)) for r in range(R)],
+            "tile_assignments": [LazyRowDict(assignments(r)) for r in range(R)]})
         return self._entropy_results
 
 

@@ -56,6 +56,8 @@ struct TileSet {
   size_t hist_bytes = 0;
   // int8 tensor-core path (vet_whist_i8.cuh), built on first use
   bool i8_built = false;
+  bool i8_ok = false;                  // weight quantisation within the entropy tolerance (build_i8_tables)
+  double i8_rho = 0.0;
   int i8_blocks = 0;                   // N blocks of 48 tiles
   uint8_t* d_w8 = nullptr;             // [i8_blocks*240, kp] weight slices, row nb*240 + s*48 + j
   int2* d_kb_range = nullptr;          // [i8_blocks] K-block range of every N block
@@ -277,6 +279,7 @@ constexpr int64_t kGlobalLutCells = (int64_t)1 << 24;  // the same for unweighte
 
 // tensor-core weighted histogram (defined with launch_whist_i8 below)
 bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U);
+int build_i8_tables(vet_handle* h, TileSet& t);
 int ensure_planes(vet_handle* h, int64_t F, cudaStream_t st);
 int64_t i8_kp(const vet_handle* h);
 uint32_t* i8_hi1(vet_handle* h);

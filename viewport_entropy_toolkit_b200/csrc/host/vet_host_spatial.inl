@@ -395,11 +395,26 @@ bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U) {
   // tiles); the FP64 kernel costs ~0.14 us per frame at 201 tiles.  From a few hundred frames on the
   // tensor cores win (measured: equal at 450 frames, 0.07 vs 0.50 ms at 3600).
   // decided per API call, not per internal batch, so that a short last batch does not switch kernels
-  return std::max(F, h->call_frames) >= 512;
+  if (std::max(F, h->call_frames) < 512) return false;
+  // and only where the weight quantisation keeps the entropies inside the stated tolerance (i8_ok, build_i8_tables)
+  vet_handle* hm = const_cast<vet_handle*>(h);
+  for (auto& t : hm->ts) {
+    if (build_i8_tables(hm, t) != VET_OK) return false;
+    if (!t.i8_ok) return false;
+  }
+  return true;
 }
 
 // Quantised weight slices of tile set t: row nb*240 + s*48 + j of [i8_blocks*240, kp] holds slice s of
-// rint(w(cell, nb*48+j) * 2^39) for every cell; plus the K-block range of every N block.
+// q = rint(w(cell, nb*48+j) * 2^39) for every cell (q = 1 for a positive weight below half a quantum, so that the
+// support of a histogram row -- the tiles with d < fov/2, EU:133 -- is the FP64 kernel's); plus the K-block range of
+// every N block.
+// Error of the quantisation, |dw| < 2^-39 =: delta per (cell, tile) entry: a user in cell c adds s_c = sum_t w(c,t) to
+// the total of its frame and at most n_c delta (n_c tiles in its FOV) of error, so sum_t |dh_t| / total <= rho :=
+// max_c n_c delta / s_c whatever the users do.  With dH/dh_t = -(log2 p_t + H) / total and p_t >= 2^-39 / (U T):
+// |dH| <= rho (39 + log2(U T) + log2 T) <= 77 rho, i.e. |dHn| <= 77 rho / log2 T on the normalised entropy (EU:201-209).
+// The automatic dispatch takes the tensor-core kernel only when that is <= 2.5e-10 (i8_ok): relative 1e-9 for every
+// frame with Hn >= 0.25 -- fov=90, pf=2, 201 tiles: rho = 1.1e-11, bound 1.1e-10; measured differences are ~5e-14.
 int build_i8_tables(vet_handle* h, TileSet& t) {
   if (t.i8_built) return VET_OK;
   const int T = t.T;
@@ -421,7 +436,8 @@ int build_i8_tables(vet_handle* h, TileSet& t) {
       if (tile >= T) break;
       for (uint32_t e = col_ptr[tile]; e < col_ptr[tile + 1]; ++e) {
         const uint32_t c = cell_idx[e];
-        const uint64_t q = (uint64_t)std::llrint(std::ldexp(w_val[e], vet::kI8FracBits));
+        uint64_t q = (uint64_t)std::llrint(std::ldexp(w_val[e], vet::kI8FracBits));
+        if (!q && w_val[e] > 0.0) q = 1;  // keeps the tile in the support of the row
         if (!q) continue;
         lo = std::min(lo, c);
         hi = std::max(hi, c);
@@ -435,6 +451,22 @@ int build_i8_tables(vet_handle* h, TileSet& t) {
   if (int rc = upload(&t.d_w8, w8.data(), w8.size())) return rc;
   if (int rc = upload(&t.d_kb_range, range.data(), range.size())) return rc;
   if (int rc = make_u8_map(&t.tm_w, t.d_w8, (uint64_t)kp, (uint64_t)nblk * vet::kI8N, vet::kI8N)) return rc;
+  {
+    std::vector<double> s_c(h->C, 0.0);
+    std::vector<uint32_t> n_c(h->C, 0);
+    for (int tile = 0; tile < T; ++tile)
+      for (uint32_t e = col_ptr[tile]; e < col_ptr[tile + 1]; ++e)
+        if (w_val[e] > 0.0) {
+          s_c[cell_idx[e]] += w_val[e];
+          n_c[cell_idx[e]]++;
+        }
+    double rho = 0.0;
+    const double delta = std::ldexp(1.0, -vet::kI8FracBits);
+    for (int64_t c = 0; c < h->C; ++c)
+      if (n_c[c]) rho = std::max(rho, n_c[c] * delta / s_c[c]);
+    t.i8_rho = rho;
+    t.i8_ok = 77.0 * rho / std::log2((double)std::max(T, 2)) <= 2.5e-10;
+  }
   t.i8_blocks = nblk;
   t.i8_built = true;
   return VET_OK;
