@@ -838,6 +838,9 @@ def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs):
     dict(F=5, U=3000, tcs=[50], use_w=True, iid=True),                              # iid: lists overflow -> pairs redone by the two-pass kernels
     dict(F=9, U=4000, tcs=[200, 500], use_w=False, cap=8),                          # tiny list: a mix of pairs kept and pairs handed on
     dict(F=2, U=9, tcs=[200], use_w=False),
+    dict(F=4, U=66_000, tcs=[200], use_w=False, cluster="force"),                  # 3 pairs on clusters of 8 CTAs (tables merged through DSMEM)
+    dict(F=152, U=16_384, tcs=[200, 500], use_w=False, cluster="force"),           # one full round + 3 pairs on clusters of 4
+    dict(F=10, U=600_000, tcs=[200], use_w=True),                                   # 9 pairs of 600k users: clusters picked by the host itself
 ])
 def test_one_pass_transition_kernel_equals_two_pass_kernels(vet, cfg):
     """k_transition4 (one walk over the users: [16][T] tables of ranked tile deltas with first/second user and count,
@@ -850,7 +853,8 @@ def test_one_pass_transition_kernel_equals_two_pass_kernels(vet, cfg):
         p[3, ::9, 1] = float("nan")
         g = torch.Generator(device="cuda").manual_seed(5)
         p[F - 3:F - 1, :700, 1:] = torch.rand((2, 700, 2), generator=g, device="cuda")      # a burst of large jumps: list entries
-        p[F - 6:F - 4, :, 1:] = torch.rand((2, U, 2), generator=g, device="cuda")           # iid frames: lists overflow
+        if F >= 8:
+            p[F - 6:F - 4, :, 1:] = torch.rand((2, U, 2), generator=g, device="cuda")       # iid frames: lists overflow
     else:
         p = dev(synth(F, U, 818 + U, iid=cfg.get("iid", False), missing=cfg.get("missing", 0.0), dtype=cfg.get("dtype", np.float32)))
     e = engine(vet, tcs, fov=90.0, use_w=cfg["use_w"])
@@ -860,11 +864,15 @@ def test_one_pass_transition_kernel_equals_two_pass_kernels(vet, cfg):
     e.profile(True)
     for impl in ("v3", "auto"):
         e.set_option("transition_kernel", impl)
+        e.set_option("cluster_tail", cfg.get("cluster", "auto") if impl == "auto" else "off")
         tr = e.transition(p)
         sp, tr2 = e.analyze(p)
         assert e.poll_flags() == 0
         res[impl] = (tr, tr2, sp)
+        tail_launches = e.profile_read()["transition_tail"][1]
     e.profile(False)
+    if "cluster" in cfg or U >= 500_000:
+        assert tail_launches >= 2 * len(tcs), "the cluster launch of the one-pass kernel ran (besides the two-pass pass over flagged pairs)"
     for i in (0, 1):
         a, b = res["v3"][i], res["auto"][i]
         assert torch.equal(a.pairs0, b.pairs0) and torch.equal(a.prev_count0, b.prev_count0)

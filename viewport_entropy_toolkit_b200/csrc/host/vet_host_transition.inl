@@ -111,7 +111,7 @@ struct Plan4 {
   int threads = 512, ctas_per_sm = 1;
   size_t tab_off = 0, key_off = 0, term_off = 0, rdelta_off = 0, drank_off = 0, smem = 0;
 };
-Plan4 plan_transition4(const vet_handle* h, const TileSet& ts) {
+Plan4 plan_transition4(const vet_handle* h, const TileSet& ts, int64_t rows) {
   Plan4 p;
   if (!ts.d_drank) return p;
   const size_t T = (size_t)ts.T;
@@ -126,15 +126,42 @@ Plan4 plan_transition4(const vet_handle* h, const TileSet& ts) {
   p.ok = true;
   // 512 threads when several CTAs fit an SM (228 KB of shared memory; 64 registers per thread: 1024 threads), else
   // one CTA of 1024
+  // With few pairs per SM the grid must not depend on where the CTAs land (two CTAs with two pairs each on one SM,
+  // two with one pair each on the next): one CTA per SM then, every SM takes the same number of pairs and the rest
+  // goes to clusters.  With many pairs two smaller CTAs overlap each other's per-pair serial parts.
   const int fit = (int)(((size_t)228 * 1024) / (p.smem + 1024));
-  if (fit >= 2) {
+  if (fit >= 2 && rows >= (int64_t)8 * h->sm_count) {
     p.threads = 512;
     p.ctas_per_sm = 2;
   } else {
-    p.threads = 1024;
+    p.threads = 1024;  // (768 threads with 85 registers each, no spills, measured slower: 0.60 vs 0.57 ms on configs[4])
     p.ctas_per_sm = 1;
   }
   return p;
+}
+
+// Co-resident clusters of k_transition4<true> with S CTAs of `threads` threads and `smem` bytes each (cached per handle).
+int t4c_max_clusters(vet_handle* h, int S, int threads, size_t smem) {
+  for (const auto& c : h->t3c_occ)
+    if (c.lw == -4 - threads && c.S == S && c.smem == smem) return c.n;
+  int n = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)S);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)S;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (cudaOccupancyMaxActiveClusters(&n, vet::k_transition4<true>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  h->t3c_occ.push_back({-4 - threads, S, smem, n});
+  return n;
 }
 
 int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st) {
@@ -298,7 +325,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         bool t4_done = false;
         // the k-th tile set of the handle (cell LUT or, with tile ids in the rows, the identity table over it)
         const TileSet& tsk = h->ts[std::min(k, h->K - 1)];
-        const Plan4 p4 = (use_t4 && k < h->K && tsk.T == a.T[k]) ? plan_transition4(h, tsk) : Plan4{};
+        const Plan4 p4 = (use_t4 && k < h->K && tsk.T == a.T[k]) ? plan_transition4(h, tsk, rows) : Plan4{};
         if (p4.ok) {
           if (pl.lw != vet::kLutIdentity) {
             // several tile counts: the rows hold cell ids -> tile ids of this tile count first (one lookup per sample
@@ -343,12 +370,52 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
           A4.term_off = (int)p4.term_off;
           A4.redo_count = count4;
           A4.ovf_cap = h->opt[VET_OPT_T4_LIST_CAP] > 0 ? h->opt[VET_OPT_T4_LIST_CAP] : vet::kT4OvfCap;
-          const int blocks4 = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * p4.ctas_per_sm);
-          {
+          // The rows % SMs pairs left after the full rounds of one pair per SM go to clusters (the users of a pair split
+          // over S CTAs, tables merged through distributed shared memory) instead of a last round on a few SMs -- from
+          // ~130k users saved per CTA on (VET_OPT_CLUSTER_TAIL: 0 never, 2 whenever it can run).
+          int64_t tail4 = 0;
+          int S4 = 0;
+          VET_CUDA(cudaFuncSetAttribute(vet::k_transition4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p4.smem));
+          VET_CUDA(cudaFuncSetAttribute(vet::k_transition4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p4.smem));
+          if (cluster_tail) {
+            const int64_t rem = rows % h->sm_count;
+            for (int S = 8; S >= 2 && rem > 0 && !S4; S >>= 1)
+              if (U >= (int64_t)S * p4.threads * 8 && (cluster_tail == 2 || U * (S - 1) >= (int64_t)131072 * S) &&
+                  rem <= t4c_max_clusters(h, S, p4.threads, p4.smem))
+                S4 = S;
+            if (S4) tail4 = rem;
+          }
+          const int64_t main4 = rows - tail4;
+          if (main4 > 0) {
+            vet::Transition4Args AM = A4;
+            AM.t.F = main4 + 1;
+            const int blocks4 = (int)std::min<int64_t>(main4, (int64_t)h->sm_count * p4.ctas_per_sm);
             LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
-            VET_CUDA(cudaFuncSetAttribute(vet::k_transition4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p4.smem));
-            vet::k_transition4<<<blocks4, p4.threads, p4.smem, st>>>(A4);
+            vet::k_transition4<false><<<blocks4, p4.threads, p4.smem, st>>>(AM);
             VET_CUDA(cudaGetLastError());
+          }
+          if (tail4 > 0) {
+            vet::Transition4Args AT = A4;
+            AT.t.nvalid = A4.t.nvalid ? A4.t.nvalid + main4 : nullptr;
+            AT.t.cell16 = A4.t.cell16 + main4 * U;
+            AT.t.F = tail4 + 1;
+            AT.t.out = A4.t.out + main4;
+            AT.t.prev_count0 = A4.t.prev_count0 ? A4.t.prev_count0 + main4 * A4.t.T : nullptr;
+            AT.t.redo = A4.t.redo + main4;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(tail4 * S4));
+            cfg.blockDim = dim3((unsigned)p4.threads);
+            cfg.dynamicSmemBytes = p4.smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)S4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            LaunchTimer lt(h, VET_KERNEL_TRANSITION_TAIL, st);
+            VET_CUDA(cudaLaunchKernelEx(&cfg, vet::k_transition4<true>, AT));
           }
           // the two-pass kernel below only takes the pairs the one-pass kernel flagged (its CTAs leave at once when none)
           A3.only_rows = redo4;

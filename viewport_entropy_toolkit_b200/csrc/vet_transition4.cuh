@@ -23,6 +23,8 @@
 // through minima of user indices -> deterministic, counts bit-exact; the entropy sum runs in the order of
 // k_transition3's block_sum, so both kernels return the same bits.
 #pragma once
+#include <cooperative_groups.h>
+
 #include <type_traits>
 
 #include "vet_stream_tma.cuh"
@@ -66,8 +68,15 @@ __device__ __forceinline__ void t4_inc(uint32_t addr) {
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
 
+// CL: one frame pair per thread-block CLUSTER (the pairs left after the full rounds, like k_transition3c): the CTAs of
+// a cluster take interleaved steps of the users into their own tables, then push their non-empty entries into the
+// tables of CTA 0 through distributed shared memory (add / two-level min -- the same integers as one CTA would
+// have collected), and CTA 0 finishes the pair.
+template <bool CL>
 __global__ void __launch_bounds__(kT3Threads) k_transition4(Transition4Args A) {
+  namespace cg = cooperative_groups;
   const Transition3Args& a = A.t;
+  const uint32_t S = CL ? cg::this_cluster().num_blocks() : 1u, crank = CL ? cg::this_cluster().block_rank() : 0u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // three tables of [16][T] entries + one DUMMY entry each (index TR): users without a ranked pair (unranked delta, or
   // a missing sample) are pointed at it instead of being branched around -- its `second` stays 0, so nobody takes it
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(kT3Threads) k_transition4(Transition4Args A) {
   const bool vec = (U & 7u) == 0u;
   const uint32_t sa_second = smem_u32(s_second), sa_cnt = smem_u32(s_cnt), sa_drank = smem_u32(smem_raw + A.drank_off);
 
-  for (int64_t r = blockIdx.x; r < a.F - 1; r += gridDim.x) {
+  for (int64_t r = blockIdx.x / S; r < a.F - 1; r += gridDim.x / S) {
     if (a.only_rows && __ldg(a.only_rows + r) == 0u) continue;  // uniform over the CTA
     const uint16_t* __restrict__ prow = a.cell16 + r * (int64_t)U;
     const uint16_t* __restrict__ crow = prow + U;
@@ -189,29 +198,30 @@ __global__ void __launch_bounds__(kT3Threads) k_transition4(Transition4Args A) {
         };
         // rows of 1M-user frames come from DRAM: two register buffers, refilled for step i + 2 right after step i
         uint4 bp[2], bc[2];
+        const uint32_t first = crank * kStep + tid * 8u, stride = S * kStep;  // CTA `crank` of S takes every S-th step
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           bp[j] = bc[j] = make_uint4(0u, 0u, 0u, 0u);
-          if (tid * 8u + j * kStep < U) {
-            bp[j] = __ldg(reinterpret_cast<const uint4*>(prow + tid * 8u + j * kStep));
-            bc[j] = __ldg(reinterpret_cast<const uint4*>(crow + tid * 8u + j * kStep));
+          if (first + j * stride < U) {
+            bp[j] = __ldg(reinterpret_cast<const uint4*>(prow + first + j * stride));
+            bc[j] = __ldg(reinterpret_cast<const uint4*>(crow + first + j * stride));
           }
         }
-        for (uint32_t base = 0; base < U; base += 2u * kStep) {
+        for (uint32_t base = first; base < U; base += 2u * stride) {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const uint32_t u0 = base + j * kStep + tid * 8u;
+            const uint32_t u0 = base + j * stride;
             if (u0 < U) {
               step(u0, bp[j], bc[j]);
-              if (u0 + 2u * kStep < U) {
-                bp[j] = __ldg(reinterpret_cast<const uint4*>(prow + u0 + 2u * kStep));
-                bc[j] = __ldg(reinterpret_cast<const uint4*>(crow + u0 + 2u * kStep));
+              if (u0 + 2u * stride < U) {
+                bp[j] = __ldg(reinterpret_cast<const uint4*>(prow + u0 + 2u * stride));
+                bc[j] = __ldg(reinterpret_cast<const uint4*>(crow + u0 + 2u * stride));
               }
             }
           }
         }
       } else {
-        for (uint32_t u = tid; u < U; u += NT) {
+        for (uint32_t u = crank * NT + tid; u < U; u += S * NT) {
           const uint32_t p = prow[u], c = crow[u];
           if (p != 0xFFFFu && c != 0xFFFFu) {
             ++nvalid;
@@ -228,6 +238,47 @@ __global__ void __launch_bounds__(kT3Threads) k_transition4(Transition4Args A) {
       if (lane == 0 && nvalid) atomicAdd(&s_valid, nvalid);
     }
     __syncthreads();
+    if (CL) {
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();  // every CTA of the cluster has finished its steps
+      if (crank != 0u) {
+        uint32_t* rf = cluster.map_shared_rank(s_first, 0);
+        uint32_t* rs = cluster.map_shared_rank(s_second, 0);
+        uint32_t* rc = cluster.map_shared_rank(s_cnt, 0);
+        for (uint32_t i = tid; i < TR; i += NT) {
+          const uint32_t c = s_cnt[i];
+          if (c) {
+            const uint32_t f = s_first[i], s2 = s_second[i];
+            s_cnt[i] = 0u;
+            s_first[i] = kEmpty;
+            s_second[i] = kEmpty;
+            atomicAdd(rc + i, c);
+            const uint32_t old = atomicMin(rf + i, f);  // the larger of (old, f) is a candidate for `second`
+            const uint32_t cand = min(max(old, f), s2);
+            if (cand != kEmpty) atomicMin(rs + i, cand);
+          }
+        }
+        __shared__ uint32_t s_base;
+        const uint32_t mine = s_novf;
+        if (tid == 0) {
+          s_base = mine ? atomicAdd(cluster.map_shared_rank(&s_novf, 0), mine) : 0u;
+          if (counted && s_valid) atomicAdd(cluster.map_shared_rank(&s_valid, 0), s_valid);
+        }
+        __syncthreads();
+        unsigned long long* rk = cluster.map_shared_rank(s_key, 0);
+        for (uint32_t i = tid; i < min(mine, (uint32_t)A.ovf_cap); i += NT)
+          if (s_base + i < (uint32_t)A.ovf_cap) rk[s_base + i] = s_key[i];
+      }
+      cluster.sync();  // the tables of CTA 0 are complete
+      if (crank != 0u) {
+        if (tid == 0) {
+          s_novf = 0u;
+          s_valid = 0u;
+        }
+        __syncthreads();
+        continue;
+      }
+    }
     const double total = counted ? (double)s_valid : (double)U;
     const uint32_t novf = s_novf;
     if (novf > (uint32_t)A.ovf_cap) {
