@@ -121,7 +121,10 @@ enum {
   VET_OPT_HOST_BATCH_FRAMES = 7, /* frames per batch of the host-buffer pipelines; 0 = auto (about 256 MiB of input per batch) */
   VET_OPT_T4_LIST_CAP = 8,       /* one-pass kernel: capacity of the list of users with an unranked tile delta
                                     (0 = 1024; smaller values send more pairs to the two-pass kernels: tests) */
-  VET_OPT_COUNT = 9
+  VET_OPT_CUDA_GRAPH = 9,        /* default 1: vet_spatial / vet_transition / vet_analyze replay their launch sequence as a CUDA
+                                    graph from the third identical call on (same buffers, sizes, options, a capturable
+                                    stream -- not the legacy default stream); 0: always launch kernel by kernel */
+  VET_OPT_COUNT = 10
 };
 int vet_set_option(vet_handle* h, int option, int value);
 int vet_get_option(const vet_handle* h, int option, int* value);
@@ -258,6 +261,9 @@ int vet_poll_flags(vet_handle* h, void* stream, uint32_t* flags);
 /* Number of kernel launches issued through this handle since creation
  * (bench.py's gpu_launches). */
 int64_t vet_launch_count(const vet_handle* h);
+/* API calls of this handle that ran as a CUDA graph replay (VET_OPT_CUDA_GRAPH); their kernels are included in
+ * vet_launch_count. */
+int64_t vet_graph_replays(const vet_handle* h);
 
 /* Per-kernel device timing for the benchmark's roofline line.  When enabled, every
  * launch of the streaming / epilogue / transition / transition-tail kernels is bracketed by a CUDA

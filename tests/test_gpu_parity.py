@@ -533,6 +533,51 @@ def test_analyzers_end_to_end_vs_reference(vet, tmp_path):
     assert (tmp_path / "out" / "e2e_test.csv").exists()
 
 
+@pytest.mark.parametrize("use_w,tcs,F,U", [(True, [200], 40, 20_000), (False, [50, 200, 1000], 12, 30_000), (True, [200, 20], 600, 3000)])
+def test_cuda_graph_replay_equals_eager_calls(vet, use_w, tcs, F, U):
+    """From the third identical call on a capturable stream, spatial / transition / analyze replay their launch sequence
+    as one CUDA graph: same bits as the eager calls, also after the input changed in place, and a different call in
+    between (other buffers -> other scratch sizes) does not corrupt the replay."""
+    import bench
+    e = engine(vet, tcs, fov=90.0, use_w=use_w)
+    p = bench.synth_on_device(torch, F, U, 4242 + U, torch.device("cuda"))
+    p[2, ::11, 1] = float("nan")
+    q = bench.synth_on_device(torch, F, U, 777, torch.device("cuda"))
+    eager = {}
+    for name, x in (("p", p), ("q", q)):
+        sp, tr = e.analyze(x)
+        eager[name] = (sp, tr, e.spatial(x), e.transition(x))
+    assert e.graph_replays() == 0, "calls on the legacy default stream stay eager"
+    s = torch.cuda.Stream()
+    buf = p.clone()
+    with torch.cuda.stream(s):
+        outs = []
+        sp_out = e.spatial(buf)     # the same output tensors are passed to every call below: same key
+        tr_out = e.transition(buf)
+        for it in range(6):
+            if it == 4:
+                buf.copy_(q)                                  # new data in the same buffer: the graph reads it
+            sp_i = e.spatial(buf, out=sp_out)
+            tr_i = e.transition(buf, out=tr_out)
+            if it == 2:
+                e.spatial(q[: F // 2])                        # another shape in between
+            outs.append((sp_i.entropy.clone(), sp_i.assign0.clone(), tr_i.entropy.clone(), tr_i.prev_count0.clone()))
+        s.synchronize()
+    assert e.poll_flags() == 0
+    assert e.graph_replays() >= 6, e.graph_replays()
+    for it, (se, sa, te, tc) in enumerate(outs):
+        ref = eager["q" if it >= 4 else "p"]
+        assert torch.equal(se, ref[2].entropy) and torch.equal(sa, ref[2].assign0), it
+        assert torch.equal(te.nan_to_num(-1), ref[3].entropy.nan_to_num(-1)) and torch.equal(tc, ref[3].prev_count0), it
+    e.set_option("cuda_graph", "off")
+    with torch.cuda.stream(s):
+        n0 = e.graph_replays()
+        e.spatial(buf, out=sp_out)
+        s.synchronize()
+    assert e.graph_replays() == n0
+    e.close()
+
+
 def test_analyzer_results_are_lazy_at_scale(vet, tmp_path):
     """SpatialEntropyAnalyzer.compute_entropy() on a configs[2]-size video (100k users x 3600 frames, 4.3 GB on the
     host): the DataFrame comes back in seconds because the per-frame `tile_weights` / `tile_assignments` dicts

@@ -11,12 +11,13 @@ from viewport_entropy_toolkit_b200 import EntropyConfig, get_engine
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 450
 U = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 dev = torch.device("cuda")
+torch.cuda.set_stream(torch.cuda.Stream(dev))   # a capturable stream: repeated calls replay as CUDA graphs
 p = bench.synth_on_device(torch, F, U, 20265000, dev, chunk=32 if U > 200_000 else 256)
 eng = get_engine(100, 200, [200], EntropyConfig(fov_angle=90.0, power_factor=2.0), dev)
 
 
 def timed(fn, n=5):
-    for _ in range(2):
+    for _ in range(4):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -34,6 +34,7 @@ OPTIONS = {
     "analyze_overlap": (6, {"off": 0, "on": 1}),
     "host_batch_frames": (7, {"auto": 0}),
     "t4_list_cap": (8, {"auto": 0}),
+    "cuda_graph": (9, {"off": 0, "on": 1}),
 }
 
 
@@ -88,6 +89,7 @@ SYMBOLS = {
     "vet_naive_points": (C.c_int, [_P, _P, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "vet_poll_flags": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
     "vet_launch_count": (_I64, [_P]),
+    "vet_graph_replays": (_I64, [_P]),
     "vet_profile_enable": (C.c_int, [_P, C.c_int]),
     "vet_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }

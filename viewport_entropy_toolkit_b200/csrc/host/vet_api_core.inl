@@ -206,6 +206,7 @@ extern "C" int vet_destroy(vet_handle* h) {
   if (!h) return VET_OK;
   DeviceGuard guard(h->device);
   for (auto& t : h->ts) free_tile_set(t);
+  drop_graphs(h);
   for (auto& s : h->spans) {
     cudaEventDestroy(s.a);
     cudaEventDestroy(s.b);
@@ -255,6 +256,7 @@ extern "C" int vet_num_tiles(const vet_handle* h, int k) {
 }
 extern "C" int64_t vet_num_cells(const vet_handle* h) { return h ? h->C : fail(VET_ERR_INVALID_ARG, "null handle"); }
 extern "C" int64_t vet_launch_count(const vet_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t vet_graph_replays(const vet_handle* h) { return h ? h->graph_replays : 0; }
 
 extern "C" int vet_lattice(const vet_handle* h, int k, double* centres_host) {
   if (h && h->naive) return fail(VET_ERR_UNSUPPORTED, "vet_lattice: not available for the latitude/longitude grid tiling (the reference has no such path)");
@@ -324,6 +326,90 @@ extern "C" int vet_tile_weights(vet_handle* h, int k, const double* vec_dev, int
 
 namespace {
 
+void drop_graphs(vet_handle* h) {
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+// Runs `body` (the launch sequence of one API call on stream st) -- eagerly the first two times a call with this key is
+// seen, captured into a CUDA graph the third time, replayed from then on: one graph launch instead of the 10-20 kernel,
+// memset and event calls of a step, whose gaps are ~3 % of the configs[2] step.  The key holds every buffer address,
+// size and option the sequence depends on plus the scratch epoch; the legacy default stream cannot be captured and
+// profiling wants per-kernel events, so both stay eager.  Any failure of the capture falls back to the eager path.
+template <typename Body>
+int run_graphed(vet_handle* h, vet_handle::GraphSlot key, cudaStream_t st, Body&& body) {
+  const bool eligible = h->opt[VET_OPT_CUDA_GRAPH] != 0 && !h->profiling && st != nullptr && st != cudaStreamLegacy &&
+                        st != cudaStreamPerThread;
+  if (!eligible) return body();
+  key.st = st;
+  vet_handle::GraphSlot* slot = nullptr;
+  for (auto& g : h->graphs) {
+    bool same = g.api == key.api && g.dtype == key.dtype && g.mode == key.mode && g.F == key.F && g.U == key.U && g.st == key.st;
+    for (int i = 0; i < 10 && same; ++i) same = g.ptr[i] == key.ptr[i];
+    if (same) slot = &g;
+  }
+  if (slot && slot->exec && slot->epoch == g_scratch_epoch) {
+    slot->used = ++h->graph_clock;
+    h->launches += slot->launches;
+    h->graph_replays++;
+    VET_CUDA(cudaGraphLaunch(slot->exec, st));
+    return VET_OK;
+  }
+  if (!slot) {
+    if (h->graphs.size() >= 8) {  // drop the least recently used
+      size_t lru = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i)
+        if (h->graphs[i].used < h->graphs[lru].used) lru = i;
+      if (h->graphs[lru].exec) cudaGraphExecDestroy(h->graphs[lru].exec);
+      h->graphs.erase(h->graphs.begin() + (long)lru);
+    }
+    key.seen = 0;
+    h->graphs.push_back(key);
+    slot = &h->graphs.back();
+  }
+  slot->used = ++h->graph_clock;
+  if (slot->exec) {  // stale: scratch was reallocated since the capture
+    cudaGraphExecDestroy(slot->exec);
+    slot->exec = nullptr;
+    slot->seen = 0;
+  }
+  if (++slot->seen < 3) return body();  // tables, scratch and lazy state settle in the eager calls
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return body();  // the caller is capturing this stream itself
+  }
+  const uint64_t epoch0 = g_scratch_epoch;
+  const int64_t launches0 = h->launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    slot->seen = -1000000;  // not capturable here: stay eager
+    return body();
+  }
+  const int rc = body();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (rc == VET_OK && ce == cudaSuccess && graph && epoch0 == g_scratch_epoch &&
+      cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess && exec) {
+    cudaGraphDestroy(graph);
+    slot->exec = exec;
+    slot->epoch = g_scratch_epoch;
+    slot->launches = h->launches - launches0;
+    h->graph_replays++;
+    VET_CUDA(cudaGraphLaunch(exec, st));
+    return VET_OK;
+  }
+  cudaGetLastError();
+  if (graph) cudaGraphDestroy(graph);
+  if (exec) cudaGraphExecDestroy(exec);
+  h->launches = launches0;
+  slot->seen = -1000000;
+  if (rc != VET_OK) return rc;
+  return body();  // nothing ran during the failed capture
+}
+
 // SpatialEntropyAnalyzer.compute_entropy on F resident frames (table regimes); per_k rows `per_k_stride` apart.
 int spatial_core(vet_handle* h, const void* packed_dev, int dtype, int64_t F, int64_t U, double* entropy_dev,
                  double* per_k_dev, int64_t per_k_stride, double* hist0_dev, uint16_t* assign0_dev, cudaStream_t st) {
@@ -363,7 +449,17 @@ extern "C" int vet_spatial(vet_handle* h, const void* packed_dev, int dtype, int
   h->call_frames = F;
   cudaStream_t st = (cudaStream_t)stream;
   if (h->direct_only) return spatial_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, hist0_dev, assign0_dev, st);
-  return spatial_core(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, F, hist0_dev, assign0_dev, st);
+  vet_handle::GraphSlot key;
+  key.api = 1;
+  key.dtype = dtype;
+  key.F = F;
+  key.U = U;
+  key.ptr[0] = packed_dev;
+  key.ptr[1] = entropy_dev;
+  key.ptr[2] = per_k_dev;
+  key.ptr[3] = hist0_dev;
+  key.ptr[4] = assign0_dev;
+  return run_graphed(h, key, st, [&] { return spatial_core(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, F, hist0_dev, assign0_dev, st); });
 }
 
 namespace {
@@ -427,7 +523,20 @@ extern "C" int vet_transition(vet_handle* h, const void* packed_dev, int dtype, 
   cudaStream_t st = (cudaStream_t)stream;
   if (h->direct_only)
     return transition_direct(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, prev_count0_dev, pairs0_dev, mode, st);
-  return transition_core(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, F - 1, prev_count0_dev, pairs0_dev, mode, st);
+  vet_handle::GraphSlot key;
+  key.api = 2;
+  key.dtype = dtype;
+  key.mode = mode;
+  key.F = F;
+  key.U = U;
+  key.ptr[0] = packed_dev;
+  key.ptr[1] = entropy_dev;
+  key.ptr[2] = per_k_dev;
+  key.ptr[3] = prev_count0_dev;
+  key.ptr[4] = pairs0_dev;
+  return run_graphed(h, key, st, [&] {
+    return transition_core(h, packed_dev, dtype, F, U, entropy_dev, per_k_dev, F - 1, prev_count0_dev, pairs0_dev, mode, st);
+  });
 }
 
 namespace {
@@ -525,6 +634,23 @@ extern "C" int vet_analyze(vet_handle* h, const void* packed_dev, int dtype, int
     if (int rc = vet_spatial(h, packed_dev, dtype, F, U, sp_entropy_dev, sp_per_k_dev, hist0_dev, assign0_dev, stream)) return rc;
     return vet_transition(h, packed_dev, dtype, F, U, tr_entropy_dev, tr_per_k_dev, prev_count0_dev, pairs0_dev, mode, stream);
   }
-  return analyze_core(h, packed_dev, dtype, F, U, sp_entropy_dev, sp_per_k_dev, F, hist0_dev, assign0_dev, tr_entropy_dev,
-                      tr_per_k_dev, F - 1, prev_count0_dev, pairs0_dev, mode, st);
+  vet_handle::GraphSlot key;
+  key.api = 3;
+  key.dtype = dtype;
+  key.mode = mode;
+  key.F = F;
+  key.U = U;
+  key.ptr[0] = packed_dev;
+  key.ptr[1] = sp_entropy_dev;
+  key.ptr[2] = sp_per_k_dev;
+  key.ptr[3] = hist0_dev;
+  key.ptr[4] = assign0_dev;
+  key.ptr[5] = tr_entropy_dev;
+  key.ptr[6] = tr_per_k_dev;
+  key.ptr[7] = prev_count0_dev;
+  key.ptr[8] = pairs0_dev;
+  return run_graphed(h, key, st, [&] {
+    return analyze_core(h, packed_dev, dtype, F, U, sp_entropy_dev, sp_per_k_dev, F, hist0_dev, assign0_dev, tr_entropy_dev,
+                        tr_per_k_dev, F - 1, prev_count0_dev, pairs0_dev, mode, st);
+  });
 }

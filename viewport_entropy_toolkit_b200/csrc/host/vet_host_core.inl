@@ -144,9 +144,23 @@ struct vet_handle {
     size_t smem;
     int n;
   };
+  // CUDA graphs of whole API calls (run_graphed): key = everything the launch sequence depends on
+  struct GraphSlot {
+    int api = 0, dtype = 0, mode = 0, seen = 0;
+    int64_t F = 0, U = 0;
+    const void* ptr[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    uint64_t epoch = 0;       // scratch allocations at capture time: a reallocation invalidates the graph
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;     // kernel launches of one replay
+    uint64_t used = 0;
+  };
+  std::vector<GraphSlot> graphs;
+  uint64_t graph_clock = 0;
+  int64_t graph_replays = 0;
   std::vector<T3cOcc> t3c_occ;  // co-resident clusters of k_transition3c per (LUT variant, cluster size, shared memory)
   int64_t launches = 0;
-  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1, 0, 0};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
+  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1, 0, 0, 1};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
   // optional per-kernel timing (vet_profile_*): CUDA events recorded around each launch
   bool profiling = false;
   struct Span {
@@ -227,8 +241,11 @@ int upload(T** dptr, const T* host, size_t count) {
   return VET_OK;
 }
 
+uint64_t g_scratch_epoch = 0;  // bumped by every scratch reallocation (captured graphs hold the old addresses)
+
 int grow(void** ptr, size_t* have, size_t want) {
   if (*have >= want) return VET_OK;
+  ++g_scratch_epoch;
   if (*ptr) VET_CUDA(cudaFree(*ptr));
   *ptr = nullptr;
   *have = 0;
@@ -267,6 +284,7 @@ struct LaunchTimer {  // records an event pair around one kernel launch when pro
 };
 
 int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64_t U, int Tmax, cudaStream_t st);
+void drop_graphs(vet_handle* h);
 int spatial_direct(vet_handle* h, const void* packed, int dtype, int64_t F, int64_t U, double* entropy, double* per_k,
                    double* hist0, uint16_t* assign0, cudaStream_t st);
 int transition_direct(vet_handle* h, const void* packed, int dtype, int64_t F, int64_t U, double* entropy, double* per_k,

@@ -325,6 +325,7 @@ int launch_whist(vet_handle* h, int k, int64_t F, const uint32_t* cnt, double* h
   const int64_t fblocks = (F + frames_per_cta - 1) / frames_per_cta;
   const int blocks = (int)std::min<int64_t>(fblocks * t.G, h->sm_count);
   if (t.sched_F != F || t.sched_blocks != blocks) {
+    ++g_scratch_epoch;                    // captured graphs of other frame counts read the schedule this one replaces
     VET_CUDA(cudaStreamSynchronize(st));  // the previous schedule may still be in use
     if (int rc = build_whist_schedule(t, fblocks, blocks)) return rc;
     t.sched_F = F;
@@ -478,6 +479,7 @@ int ensure_planes(vet_handle* h, int64_t F, cudaStream_t st) {
   const int64_t kp = i8_kp(h);
   const int64_t rows = (F + vet::kI8M - 1) / vet::kI8M * vet::kI8M;
   if (rows <= h->plane_rows) return VET_OK;
+  ++g_scratch_epoch;
   VET_CUDA(cudaStreamSynchronize(st));
   cudaFree(h->d_planes);
   cudaFree(h->d_dirty);

@@ -176,6 +176,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
   if (!in_smem) {
     const size_t words = (size_t)blocks * 4 * cap;
     if (h->tables_words < words || h->tables_cap != cap) {
+      ++g_scratch_epoch;  // new layout of the global pair tables: captured graphs were laid out for the old one
       if (h->tables_words < words) {
         if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
         h->d_tables = nullptr;
@@ -192,6 +193,7 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
       h->tables_cap = cap;
       h->tables_blocks = blocks;
     } else if (h->tables_blocks < blocks) {
+      ++g_scratch_epoch;
       for (int b = h->tables_blocks; b < blocks; ++b) {
         VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
         VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));

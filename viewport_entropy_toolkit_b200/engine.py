@@ -170,6 +170,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.vet_launch_count(self._h))
 
+    def graph_replays(self) -> int:
+        """API calls that ran as one CUDA graph launch (third identical call on, on a capturable stream)."""
+        return int(self._lib.vet_graph_replays(self._h))
+
     def profile(self, on: bool = True) -> None:
         """Starts (or stops) recording a CUDA-event pair around every kernel launch."""
         _check(self._lib.vet_profile_enable(self._h, int(on)))
