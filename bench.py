@@ -547,8 +547,12 @@ def main():
     # end to end: host buffers in, host results out, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((F, U, 3), dtype=torch.float32, pin_memory=True)
-        host.copy_(packed)
+        # the host tensor a caller hands over: (2dmu, 2dmv) per user and frame -- the frame times (time = 0.1 f, identical
+        # for all users of a frame) stay with the caller, the kernels never read them (VET_OPT_HOST_LAYOUT)
+        host3 = torch.empty((F, U, 3), dtype=torch.float32, pin_memory=True)
+        host3.copy_(packed)
+        host = torch.empty((F, U, 2), dtype=torch.float32, pin_memory=True)
+        host.copy_(packed[..., 1:])
         torch.cuda.synchronize()
         eng.spatial_host(host, want_per_k=False, reuse_buffers=True)  # warm-up (allocates the staging buffers)
         if world > 1:
@@ -564,7 +568,21 @@ def main():
         e2e = {"value": samples_per_step * args.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(host.numel() * 4),
                "d2h_bytes_per_step": int(res["entropy"].nbytes + res["hist0"].nbytes + res["assign0"].nbytes),
-               "steps": args.e2e_steps, "api": "Engine.spatial_host (vet_spatial_host), pinned host input"}
+               "steps": args.e2e_steps, "api": "Engine.spatial_host (vet_spatial_host), pinned host input [F,U,2] = (2dmu, 2dmv)"}
+        # the same with the time column uploaded as well ([F,U,3] records, 12 B per sample)
+        eng.spatial_host(host3, want_per_k=False, reuse_buffers=True)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.spatial_host(host3, want_per_k=False, reuse_buffers=True)
+        dt3 = time.perf_counter() - t0
+        t_e = torch.tensor([dt3], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e["packed3"] = {"value": samples_per_step * args.e2e_steps / float(t_e.item()), "unit": UNIT,
+                          "h2d_bytes_per_step": int(host3.numel() * 4), "api": "the same with [F,U,3] = (time, 2dmu, 2dmv) records"}
+        del host3
         # the same through vet_analyze_host: both analyzers, one upload (transition rows come back as well)
         eng.analyze_host(host, want_per_k=False, want_pairs0=False, reuse_buffers=True)
         if world > 1:

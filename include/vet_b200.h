@@ -124,7 +124,11 @@ enum {
   VET_OPT_CUDA_GRAPH = 9,        /* default 1: vet_spatial / vet_transition / vet_analyze replay their launch sequence as a CUDA
                                     graph from the third identical call on (same buffers, sizes, options, a capturable
                                     stream -- not the legacy default stream); 0: always launch kernel by kernel */
-  VET_OPT_COUNT = 10
+  VET_OPT_HOST_LAYOUT = 10,      /* the *_host entry points read `packed_host` as 0: [F,U,3] = (time, 2dmu, 2dmv) records
+                                    (default), 1: [F,U,2] = (2dmu, 2dmv) -- the kernels never read the time column, so a
+                                    caller that keeps the frame times itself uploads a third less; the records are widened
+                                    on the device */
+  VET_OPT_COUNT = 11
 };
 int vet_set_option(vet_handle* h, int option, int value);
 int vet_get_option(const vet_handle* h, int option, int* value);

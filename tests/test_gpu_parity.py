@@ -1147,6 +1147,30 @@ def test_global_table_regime_at_scale(vet):
         d.close()
 
 
+@pytest.mark.parametrize("dtype,use_w,tcs,batch", [(np.float32, True, [200], 7), (np.float64, False, [20, 50], 3), (np.float32, True, [200, 500], 0)])
+def test_two_column_host_layout_equals_packed_records(vet, dtype, use_w, tcs, batch):
+    """The host entry points on [F,U,2] = (2dmu, 2dmv) arrays (VET_OPT_HOST_LAYOUT: a third less to upload, records
+    widened on the device) return, bit for bit, what they return for the [F,U,3] records with the time column."""
+    p = synth(29, 3001, 1234, missing=0.05, dtype=dtype)
+    uv = np.ascontiguousarray(p[..., 1:])
+    e = engine(vet, tcs, 90.0, use_w)
+    e.set_option("weighted_kernel", "fp64")
+    e.set_option("host_batch_frames", batch)
+    a_s, a_t = e.analyze_host(p)
+    b_s, b_t = e.analyze_host(uv)
+    c_s = e.spatial_host(uv)
+    c_t = e.transition_host(uv)
+    d_s = e.spatial_host(p)          # and back to the three-column layout on the same handle
+    assert e.poll_flags() == 0
+    for got in (b_s, c_s, d_s):
+        for k in ("entropy", "per_k", "hist0", "assign0"):
+            assert np.array_equal(got[k], a_s[k], equal_nan=True), k
+    for got in (b_t, c_t):
+        for k in ("entropy", "per_k", "prev_count0", "pairs0"):
+            assert np.array_equal(got[k], a_t[k], equal_nan=True), k
+    e.close()
+
+
 def test_host_path_equals_device_path_at_scale(vet):
     """More frames than one host batch (512 for weighted handles) with a short last batch: the host-buffer path
     and the device path take the same weighted kernel for every batch of a call and return the same bits."""

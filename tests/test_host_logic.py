@@ -321,3 +321,24 @@ def test_tile_geometry_vs_reference_fixtures(pkg):
     for name in ("get_fb_tile_boundaries", "get_lat_lon_tiles", "normalize", "great_circle_intersection", "get_tile_corners",
                  "compute_spherical_polygon_area", "spherical_interpolation", "find_nearest_point", "angle_at_vertex"):
         assert getattr(pkg.utilities, name) is getattr(G, name)
+
+
+def test_lazy_row_dict_is_a_read_only_dict_view():
+    """LazyRowDict (the per-frame `tile_weights` / `tile_assignments` cells of the analyzers' DataFrames, SA:152-163):
+    built on first access, equal to the dict it stands for, usable like one."""
+    import pandas as pd
+    from viewport_entropy_toolkit_b200.analyzers import LazyRowDict
+    calls = []
+
+    def make():
+        calls.append(1)
+        return {"a": 1, "b": 2}
+
+    d = LazyRowDict(make)
+    df = pd.DataFrame({"time": [0.0], "tile_assignments": [d]})     # stays one object cell, not expanded
+    assert not calls and df["tile_assignments"][0] is d
+    assert d == {"a": 1, "b": 2} and {"a": 1, "b": 2} == d and len(calls) == 1
+    assert len(d) == 2 and "a" in d and d.get("c", 7) == 7 and sorted(d.items()) == [("a", 1), ("b", 2)] and dict(d) == {"a": 1, "b": 2}
+    assert len(calls) == 1 and repr(d) == repr({"a": 1, "b": 2})
+    with pytest.raises(TypeError):
+        d["c"] = 3

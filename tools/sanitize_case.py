@@ -18,11 +18,18 @@ def packed(F, U, dtype=np.float32):
 
 e = Engine(100, 200, [200, 20], EntropyConfig(fov_angle=90.0))
 r = e.spatial(packed(70, 2501))                     # k_stream_tma (odd U: unaligned tile heads) + k_whist + k_entropy_rows
-t = e.transition(packed(4, 9000))                   # k_stream_tma<cells> + k_transition3 (dense) per tile count + k_mean_rows
+t = e.transition(packed(4, 9000))                   # k_stream_tma<cells> + k_relabel_rows + k_transition4 (iid samples: lists overflow) +
+                                                    # k_transition3 (dense) over the flagged pairs, per tile count + k_mean_rows
+walk = packed(4, 16384)
+walk[1:, :, 1:] = (walk[:1, :, 1:] + 0.004 * torch.arange(1, 4, device="cuda")[:, None, None]).clamp_(0, 1)   # small steps
+tw = e.transition(walk)                             # k_transition4 on its tables (ranked tile deltas), list of a few users
 e.set_option("cluster_tail", "force")
+twc = e.transition(walk)                            # k_transition4<cluster>: tables merged into CTA 0 through DSMEM atomics
+e.set_option("transition_kernel", "v3")
 tc = e.transition(packed(3, 16384))                 # k_transition3c: a frame pair per cluster of 2 CTAs (tables merged through DSMEM)
 sa, ta = e.analyze(packed(3, 16384))                # the same with the spatial epilogue on the side stream beside it
 e.set_option("cluster_tail", "auto")
+e.set_option("transition_kernel", "auto")
 e.set_option("weighted_kernel", "i8")
 hot = packed(140, 2504)
 hot[:, :600, 1:] = 0.5                              # 600 users in one cell: second count plane

@@ -35,6 +35,7 @@ OPTIONS = {
     "host_batch_frames": (7, {"auto": 0}),
     "t4_list_cap": (8, {"auto": 0}),
     "cuda_graph": (9, {"off": 0, "on": 1}),
+    "host_layout": (10, {"tuv": 0, "uv": 1}),
 }
 
 

@@ -236,6 +236,8 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_i8flags);
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);
+  cudaFree(h->d_in2[0]);
+  cudaFree(h->d_in2[1]);
   for (void* p : h->d_hout) cudaFree(p);
   for (void* p : h->d_hout2) cudaFree(p);
   for (auto e : h->ev_pipe)

@@ -52,6 +52,48 @@ struct DeviceTemps {
   }
 };
 
+// Upload of `nf` frames of host records into `dst` (device, three columns) on the copy stream.  Two-column host layout
+// (VET_OPT_HOST_LAYOUT): the (2dmu, 2dmv) records go to the staging buffer `b` and are widened on the EXECUTE stream after
+// the copy; *widen is set so that the caller launches it behind its in_done wait.
+struct Upload {
+  const void* src = nullptr;  // staging buffer to widen from, or null
+  void* dst = nullptr;
+  int64_t n = 0;              // records
+};
+int grow_inputs2(vet_handle* h, size_t bytes) {
+  if (h->in2_bytes >= bytes) return VET_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (h->d_in2[i]) VET_CUDA(cudaFree(h->d_in2[i]));
+    h->d_in2[i] = nullptr;
+  }
+  h->in2_bytes = 0;
+  for (int i = 0; i < 2; ++i) VET_CUDA(cudaMalloc(&h->d_in2[i], bytes));
+  h->in2_bytes = bytes;
+  return VET_OK;
+}
+void upload_frames(vet_handle* h, PipeStatus& ps, const void* host, int rec, size_t esz, int64_t f0, int64_t nf, int64_t U, int b,
+                   void* dst, Upload* widen) {
+  *widen = Upload{};
+  const size_t rec_bytes = (size_t)rec * esz;
+  const char* src = (const char*)host + (size_t)f0 * U * rec_bytes;
+  if (rec == 3) {
+    VET_PIPE(ps, cudaMemcpyAsync(dst, src, (size_t)nf * U * rec_bytes, cudaMemcpyHostToDevice, h->s_copy));
+    return;
+  }
+  VET_PIPE(ps, cudaMemcpyAsync(h->d_in2[b], src, (size_t)nf * U * rec_bytes, cudaMemcpyHostToDevice, h->s_copy));
+  widen->src = h->d_in2[b];
+  widen->dst = dst;
+  widen->n = nf * U;
+}
+void widen_records(vet_handle* h, PipeStatus& ps, const Upload& w, int dtype, cudaStream_t st) {
+  if (!w.src || !ps.ok()) return;
+  const int blocks = (int)std::min<int64_t>((w.n + 255) / 256, (int64_t)h->sm_count * 16);
+  h->launches++;
+  if (dtype == VET_F32) vet::k_widen_records<float><<<blocks, 256, 0, st>>>((const float*)w.src, w.n, (float*)w.dst);
+  else vet::k_widen_records<double><<<blocks, 256, 0, st>>>((const double*)w.src, w.n, (double*)w.dst);
+  ps.cuda(cudaGetLastError(), "k_widen_records");
+}
+
 // Large-video (direct) regime: plain upload, direct kernels, download.  O(users x tiles) per frame on the device: the
 // copies are not what bounds it.
 int host_direct(vet_handle* h, const void* packed_host, int dtype, int64_t F, int64_t U, bool spatial, bool transition,
@@ -84,7 +126,18 @@ int host_direct(vet_handle* h, const void* packed_host, int dtype, int64_t F, in
   }
   PipeStatus ps;
   cudaStream_t st = h->s_exec;
-  VET_PIPE(ps, cudaMemcpyAsync(d_in, packed_host, (size_t)F * U * 3 * esz, cudaMemcpyHostToDevice, st));
+  if (h->opt[VET_OPT_HOST_LAYOUT]) {  // two-column host records: widened on the device
+    void* d_uv = nullptr;
+    if (int rc = t.alloc(&d_uv, (size_t)F * U * 2 * esz)) return rc;
+    VET_PIPE(ps, cudaMemcpyAsync(d_uv, packed_host, (size_t)F * U * 2 * esz, cudaMemcpyHostToDevice, st));
+    Upload w;
+    w.src = d_uv;
+    w.dst = d_in;
+    w.n = F * U;
+    widen_records(h, ps, w, dtype, st);
+  } else {
+    VET_PIPE(ps, cudaMemcpyAsync(d_in, packed_host, (size_t)F * U * 3 * esz, cudaMemcpyHostToDevice, st));
+  }
   if (ps.ok() && spatial)
     ps.call(spatial_direct(h, d_in, dtype, F, U, (double*)d_e, (double*)d_p, (double*)d_h, (uint16_t*)d_a, st));
   if (ps.ok() && transition && R > 0)
@@ -130,6 +183,9 @@ int host_pipeline_halo(vet_handle* h, const void* packed_host, int dtype, int64_
   const int64_t R = F - 1;
   const int64_t fb = host_batch_frames(h, F, U, esz);  // NEW frames per batch; the buffers hold one more (the halo)
   if (int rc = grow_inputs(h, (size_t)(fb + 1) * frame_bytes)) return rc;
+  const int rec = h->opt[VET_OPT_HOST_LAYOUT] ? 2 : 3;
+  if (rec == 2)
+    if (int rc = grow_inputs2(h, (size_t)fb * U * 2 * esz)) return rc;
   // device-side result rows are kept in the handle and only grown (cudaMalloc / cudaFree synchronise)
   if (spatial) {
     if (int rc = grow(&h->d_hout[0], &h->hout_bytes[0], (size_t)F * 8)) return rc;
@@ -166,11 +222,12 @@ int host_pipeline_halo(vet_handle* h, const void* packed_host, int dtype, int64_
     const bool halo = f0 > 0;
     char* buf = (char*)h->d_in[b];
     VET_PIPE(ps, cudaStreamWaitEvent(h->s_copy, exec_done[b], 0));  // buffer b was last read two batches ago
-    VET_PIPE(ps, cudaMemcpyAsync(buf + frame_bytes, (const char*)packed_host + (size_t)f0 * frame_bytes, (size_t)nf * frame_bytes,
-                                 cudaMemcpyHostToDevice, h->s_copy));
+    Upload widen;
+    upload_frames(h, ps, packed_host, rec, esz, f0, nf, U, b, buf + frame_bytes, &widen);
     VET_PIPE(ps, cudaEventRecord(in_done[b], h->s_copy));
     VET_PIPE(ps, cudaStreamWaitEvent(h->s_exec, in_done[b], 0));
     VET_PIPE(ps, cudaStreamWaitEvent(h->s_exec, out_done[b], 0));  // per-user result buffers b must have been downloaded
+    widen_records(h, ps, widen, dtype, h->s_exec);
     // frames on the device for this batch: [f0 - halo, f0 + nf) at buf + (halo ? 0 : 1 frame); the halo frame itself
     // was put into slot 0 of this buffer by the previous batch (below)
     const char* in = buf + (halo ? 0 : frame_bytes);
@@ -232,6 +289,9 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
                        nullptr, nullptr, nullptr, VET_TRANSITION_LITERAL);
   const int64_t fb = host_batch_frames(h, F, U, esz);
   if (int rc = grow_inputs(h, (size_t)fb * U * 3 * esz)) return rc;
+  const int rec = h->opt[VET_OPT_HOST_LAYOUT] ? 2 : 3;
+  if (rec == 2)
+    if (int rc = grow_inputs2(h, (size_t)fb * U * 2 * esz)) return rc;
   const int T0 = h->ts[0].T;
   // device-side result buffers are kept in the handle and only grown (cudaMalloc/cudaFree synchronise)
   if (int rc = grow(&h->d_hout[0], &h->hout_bytes[0], (size_t)F * 8)) return rc;
@@ -256,11 +316,12 @@ extern "C" int vet_spatial_host(vet_handle* h, const void* packed_host, int dtyp
   for (int64_t f0 = 0; f0 < F && ps.ok(); f0 += fb, b ^= 1) {
     const int64_t nf = std::min(fb, F - f0);
     VET_PIPE(ps, cudaStreamWaitEvent(h->s_copy, exec_done[b], 0));  // input buffer b was last read two batches ago
-    VET_PIPE(ps, cudaMemcpyAsync(h->d_in[b], (const char*)packed_host + (size_t)f0 * U * 3 * esz, (size_t)nf * U * 3 * esz,
-                                 cudaMemcpyHostToDevice, h->s_copy));
+    Upload widen;
+    upload_frames(h, ps, packed_host, rec, esz, f0, nf, U, b, h->d_in[b], &widen);
     VET_PIPE(ps, cudaEventRecord(in_done[b], h->s_copy));
     VET_PIPE(ps, cudaStreamWaitEvent(h->s_exec, in_done[b], 0));
     VET_PIPE(ps, cudaStreamWaitEvent(h->s_exec, out_done[b], 0));  // assignment buffer b must have been downloaded
+    widen_records(h, ps, widen, dtype, h->s_exec);
     if (ps.ok())
       ps.call(spatial_core(h, h->d_in[b], dtype, nf, U, d_ent + f0, d_perk ? d_perk + f0 : nullptr, F,
                            d_hist ? d_hist + f0 * T0 : nullptr, d_assign[b], h->s_exec));

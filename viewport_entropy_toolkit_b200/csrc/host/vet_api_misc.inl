@@ -39,7 +39,7 @@ extern "C" int vet_naive_points(vet_handle* h, const double* lonlat_dev, int64_t
 
 extern "C" int vet_set_option(vet_handle* h, int option, int value) {
   if (!h || option < 0 || option >= VET_OPT_COUNT) return fail(VET_ERR_INVALID_ARG, "bad option");
-  static const int max_value[VET_OPT_COUNT] = {2, 3, 3, 2, 1, 1, 1, 1 << 30, 1024, 1};
+  static const int max_value[VET_OPT_COUNT] = {2, 3, 3, 2, 1, 1, 1, 1 << 30, 1024, 1, 1};
   if (value < 0 || value > max_value[option]) return fail(VET_ERR_INVALID_ARG, "option %d: value %d out of range", option, value);
   h->opt[option] = value;
   drop_graphs(h);  // captured launch sequences were chosen under the old options

@@ -131,6 +131,8 @@ struct vet_handle {
   // host-buffer path
   void* d_in[2] = {nullptr, nullptr};
   size_t in_bytes = 0;
+  void* d_in2[2] = {nullptr, nullptr};  // staging of the two-column host layout (VET_OPT_HOST_LAYOUT), widened into d_in
+  size_t in2_bytes = 0;
   void* d_hout[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // entropy, per_k, hist0, assign x2
   size_t hout_bytes[5] = {0, 0, 0, 0, 0};
   void* d_hout2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // transition rows: entropy, per_k, prev_count0, pairs x2
@@ -160,7 +162,7 @@ struct vet_handle {
   int64_t graph_replays = 0;
   std::vector<T3cOcc> t3c_occ;  // co-resident clusters of k_transition3c per (LUT variant, cluster size, shared memory)
   int64_t launches = 0;
-  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1, 0, 0, 1};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
+  int opt[VET_OPT_COUNT] = {0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0};  // vet_set_option (defaults: cluster tail auto, analyze overlap on)
   // optional per-kernel timing (vet_profile_*): CUDA events recorded around each launch
   bool profiling = false;
   struct Span {

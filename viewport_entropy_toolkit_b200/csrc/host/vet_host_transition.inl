@@ -4,6 +4,38 @@ namespace {
 
 // Sizes the (prev,cur) pair tables, picks the shared- or global-memory variant and launches
 // k_transition for `rows` frame pairs.
+// Global (prev,cur) pair tables of k_transition2's global mode and of k_transition<false>: [blocks][4][cap] words, allocated
+// and laid out only when one of those kernels is about to run (620 MB at 201 tiles and two CTAs per SM, ~10 GB at 1001).
+int ensure_global_tables(vet_handle* h, int blocks, uint32_t cap, cudaStream_t st) {
+  const size_t words = (size_t)blocks * 4 * cap;
+  if (h->tables_words < words || h->tables_cap != cap) {
+    ++g_scratch_epoch;  // new layout of the global pair tables: captured graphs were laid out for the old one
+    if (h->tables_words < words) {
+      if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
+      h->d_tables = nullptr;
+      h->tables_words = 0;
+      VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
+      h->tables_words = words;
+    }
+    // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value).  Done once per layout:
+    // the kernels reset every slot they touch, so the tables stay clean between calls.
+    for (int b = 0; b < blocks; ++b) {
+      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+    }
+    h->tables_cap = cap;
+    h->tables_blocks = blocks;
+  } else if (h->tables_blocks < blocks) {
+    ++g_scratch_epoch;
+    for (int b = h->tables_blocks; b < blocks; ++b) {
+      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
+      VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
+    }
+    h->tables_blocks = blocks;
+  }
+  return VET_OK;
+}
+
 // k_transition2 over all tile counts of `a` (dense table / shared-memory hash / global table per tile count);
 // only_rows != null restricts it to the flagged rows.
 int launch_transition2(vet_handle* h, const vet::TransitionArgs& a, int64_t U, int Tmax, int blocks, size_t tile_bytes,
@@ -26,6 +58,12 @@ int launch_transition2(vet_handle* h, const vet::TransitionArgs& a, int64_t U, i
       } else {
         A2.mode[k] = vet::kTrGlobal;
       }
+    }
+    bool any_global = false;
+    for (int k = 0; k < a.K; ++k) any_global = any_global || A2.mode[k] != vet::kTrDense;  // the shared hash falls back to it
+    if (any_global) {
+      if (int rc = ensure_global_tables(h, blocks, a.cap, st)) return rc;
+      A2.t.g_tables = h->d_tables;
     }
     // LUT staging area after the table area, for the tile counts whose LUT still fits
     const size_t lut_off = (tile_bytes + table_words * 4 + 64 + 15) & ~(size_t)15;
@@ -173,36 +211,8 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
   const size_t smem_tab = tile_bytes + (size_t)cap * 16 + 64;
   const bool in_smem = smem_tab + kStaticSmemSlack <= h->smem_optin;
   const int blocks = (int)std::min<int64_t>(rows, (int64_t)h->sm_count * (in_smem ? 1 : 2));
-  if (!in_smem) {
-    const size_t words = (size_t)blocks * 4 * cap;
-    if (h->tables_words < words || h->tables_cap != cap) {
-      ++g_scratch_epoch;  // new layout of the global pair tables: captured graphs were laid out for the old one
-      if (h->tables_words < words) {
-        if (h->d_tables) VET_CUDA(cudaFree(h->d_tables));
-        h->d_tables = nullptr;
-        h->tables_words = 0;
-        VET_CUDA(cudaMalloc((void**)&h->d_tables, words * 4));
-        h->tables_words = words;
-      }
-      // keys/firsts = 0xFFFFFFFF, counts = 0 (list needs no initial value).  Done once per layout:
-      // the kernels reset every slot they touch, so the tables stay clean between calls.
-      for (int b = 0; b < blocks; ++b) {
-        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
-        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
-      }
-      h->tables_cap = cap;
-      h->tables_blocks = blocks;
-    } else if (h->tables_blocks < blocks) {
-      ++g_scratch_epoch;
-      for (int b = h->tables_blocks; b < blocks; ++b) {
-        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap, 0xFF, (size_t)cap * 8, st));
-        VET_CUDA(cudaMemsetAsync(h->d_tables + (size_t)b * 4 * cap + 2 * (size_t)cap, 0, (size_t)cap * 4, st));
-      }
-      h->tables_blocks = blocks;
-    }
-  }
   a.cap = cap;
-  a.g_tables = h->d_tables;
+  a.g_tables = nullptr;  // the global pair tables are only made for the kernels that use them (ensure_global_tables)
   // VET_OPT_TRANSITION_KERNEL pins k_transition (1) or k_transition2 (2): the parity suite runs them against the two-pass kernels
   const bool force_v1 = h->opt[VET_OPT_TRANSITION_KERNEL] == 1;
   const bool force_v2 = h->opt[VET_OPT_TRANSITION_KERNEL] == 2;
@@ -491,6 +501,8 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
     LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
     vet::k_transition<true><<<blocks, 512, smem_tab, st>>>(a, Tmax);
   } else {
+    if (int rc = ensure_global_tables(h, blocks, cap, st)) return rc;
+    a.g_tables = h->d_tables;
     VET_CUDA(cudaFuncSetAttribute(vet::k_transition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(tile_bytes + 64)));
     LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);

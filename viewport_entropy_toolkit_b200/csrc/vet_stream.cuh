@@ -304,4 +304,15 @@ __global__ void __launch_bounds__(512, 1) k_epilogue(EpilogueArgs a, int maxT) {
   }
 }
 
+// (2dmu, 2dmv) records of the two-column host layout -> the (time, 2dmu, 2dmv) records the streaming kernels read;
+// the time column is never read by any kernel and is set to zero.
+template <typename T>
+__global__ void k_widen_records(const T* __restrict__ uv, int64_t n, T* __restrict__ packed) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    packed[3 * i] = (T)0;
+    packed[3 * i + 1] = uv[2 * i];
+    packed[3 * i + 2] = uv[2 * i + 1];
+  }
+}
+
 }  // namespace vet

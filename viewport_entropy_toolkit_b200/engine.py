@@ -397,6 +397,7 @@ class Engine:
         reuse_buffers=True the same engine-owned arrays are returned by every call of
         the same shape (page-locking 0.7 GB costs more than copying it)."""
         arr, dt, F, U = _host_packed(packed)
+        self._host_layout(arr)
         K, T0 = len(self.tile_counts), self.num_tiles[0]
         key = (F, U, want_per_k, want_hist0, want_assign0)
         bufs = self._host_out.get(key) if reuse_buffers else None
@@ -412,6 +413,13 @@ class Engine:
                                           _np_ptr(hist0), _np_ptr(assign0)))
         return dict(entropy=ent, per_k=per_k, hist0=hist0, assign0=assign0)
 
+    def _host_layout(self, arr) -> None:
+        """[F,U,2] host arrays hold (2dmu, 2dmv) only: a third less to upload (the kernels never read the time column;
+        VET_OPT_HOST_LAYOUT).  The frame times stay with the caller."""
+        want = "uv" if int(arr.shape[-1]) == 2 else "tuv"
+        if self.get_option("host_layout") != want:
+            self.set_option("host_layout", want)
+
     def _host_buffers(self, key: tuple, make, reuse: bool) -> tuple:
         bufs = self._host_out.get(key) if reuse else None
         if bufs is None:
@@ -426,6 +434,7 @@ class Engine:
         """TransitionEntropyAnalyzer.compute_entropy on host memory (vet_transition_host): frame batches with a
         one-frame halo, upload | kernels | download on three streams; results in page-locked memory."""
         arr, dt, F, U = _host_packed(packed)
+        self._host_layout(arr)
         if mode not in ("literal", "textbook"):
             raise ValueError("mode must be 'literal' or 'textbook'")
         R = max(F - 1, 0)
@@ -446,6 +455,7 @@ class Engine:
         """Both analyzers on host memory with ONE upload of the input (vet_analyze_host) -> (spatial, transition)
         dicts of numpy arrays like spatial_host / transition_host."""
         arr, dt, F, U = _host_packed(packed)
+        self._host_layout(arr)
         if mode not in ("literal", "textbook"):
             raise ValueError("mode must be 'literal' or 'textbook'")
         R = max(F - 1, 0)
@@ -489,8 +499,8 @@ def _host_packed(packed):
         dtype = {np.dtype(np.float32): N.VET_F32, np.dtype(np.float64): N.VET_F64}.get(arr.dtype)
     if dtype is None:
         raise TypeError("packed must be float32 or float64")
-    if arr.ndim != 3 or arr.shape[-1] != 3:
-        raise ValueError("packed must be [F, U, 3]")
+    if arr.ndim != 3 or arr.shape[-1] not in (2, 3):
+        raise ValueError("packed must be [F, U, 3] = (time, 2dmu, 2dmv) or [F, U, 2] = (2dmu, 2dmv)")
     return arr, dtype, int(arr.shape[0]), int(arr.shape[1])
 
 
