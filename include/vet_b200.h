@@ -108,7 +108,8 @@ const char* vet_version(void);
  * so that the parity suite can run the kernel generations against each other bit for bit.  The library reads no
  * environment variable. */
 enum {
-  VET_OPT_WEIGHTED_KERNEL = 0,   /* 0 auto (tensor cores from 512 frames per call), 1 FP64 pipe, 2 tensor cores (int8 slices) */
+  VET_OPT_WEIGHTED_KERNEL = 0,   /* 0 auto (tensor cores from 512 frames per call on, where the bound on the entropy error of the
+                                    quantised weights holds: DESIGN 4.3), 1 FP64 pipe, 2 tensor cores (int8 slices) */
   VET_OPT_STREAM_KERNEL = 1,     /* 0 auto, 1 plain loads (k_stream_simple), 2 cell histograms only (no direct tile
                                     histograms), 3 global-table regime without the 16-bit privatised histogram */
   VET_OPT_TRANSITION_KERNEL = 2, /* 0 auto (one-pass kernel k_transition4 where its tables fit, the two-pass kernels behind it),
