@@ -227,7 +227,7 @@ TilesPlan plan_tiles(const vet_handle* h, const void* packed, int64_t U) {
   p.A.lut_packed = h->d_lut_packed;
   if (h->d_lut_packed) off = (int)(((size_t)h->C * 4 + 15) & ~(size_t)15);
   p.A.lut_bytes = off;
-  p.smem = (size_t)vet::kStages * vet::kStageBytes + (size_t)((soff + 3) & ~3) * 4 + off + 16;
+  p.smem = (size_t)vet::kStages * vet::kStageBytes + (size_t)2 * ((soff + 3) & ~3) * 4 + off + 16;  // two copies of the histograms
   p.ok = p.smem + kStaticSmemSlack <= h->smem_optin;
   return p;
 }
