@@ -288,6 +288,44 @@ int launch_stream_tiles(vet_handle* h, TilesPlan& p, const void* packed, int dty
   return VET_OK;
 }
 
+// Row schedule of k_entropy_rows (see EntropyRowsPlan): G frames per block, their G x K rows dealt longest-first to the
+// least loaded of the 8 warps; the G with the best balance wins (ties: fewer frames per block, more blocks).
+vet::EntropyRowsPlan plan_entropy_rows(const vet_handle* h, int64_t F) {
+  vet::EntropyRowsPlan best{};
+  double best_cost = 0.0;
+  for (int G : {1, 2, 4, 8}) {
+    if (G > 1 && (G * h->K > 8 * 16 || F < (int64_t)G * h->sm_count)) continue;
+    vet::EntropyRowsPlan pl{};
+    pl.G = G;
+    std::vector<std::pair<int, int>> rows;  // (cost, g * 16 + k)
+    for (int g = 0; g < G; ++g)
+      for (int k = 0; k < h->K; ++k) rows.push_back({(h->ts[k].T + 31) / 32 + 1, g * 16 + k});
+    std::stable_sort(rows.begin(), rows.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
+    int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool ok = true;
+    for (const auto& r : rows) {
+      int w = 0;
+      for (int j = 1; j < 8; ++j)
+        if (load[j] < load[w]) w = j;
+      if (pl.nrow[w] >= 16) {
+        ok = false;
+        break;
+      }
+      pl.row_g[w][pl.nrow[w]] = (unsigned char)(r.second / 16);
+      pl.row_k[w][pl.nrow[w]] = (unsigned char)(r.second % 16);
+      pl.nrow[w]++;
+      load[w] += r.first;
+    }
+    if (!ok) continue;
+    const double cost = (double)*std::max_element(load, load + 8) / G;  // block time per frame
+    if (best.G == 0 || cost < best_cost - 1e-9) {
+      best = pl;
+      best_cost = cost;
+    }
+  }
+  return best;
+}
+
 int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* entropy, double* per_k, int64_t per_k_stride,
                           double* hist0, cudaStream_t st) {
   vet::EntropyRowsArgs e{};
@@ -309,10 +347,9 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
   LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-  const int kw = h->K >= 8 ? 8 : (h->K >= 4 ? 4 : (h->K >= 2 ? 2 : 1));  // warps per frame
-  const int groups = 8 / kw;
-  const int blocks = (int)std::min<int64_t>((F + groups - 1) / groups, (int64_t)h->sm_count * 8);
-  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, kw);
+  const vet::EntropyRowsPlan pl = plan_entropy_rows(h, F);
+  const int blocks = (int)std::min<int64_t>((F + pl.G - 1) / pl.G, (int64_t)h->sm_count * 8);
+  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, pl);
   VET_CUDA(cudaGetLastError());
   return VET_OK;
 }
@@ -581,10 +618,9 @@ int launch_weighted_rows(vet_handle* h, int64_t F, double* const* hists, const u
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
   LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-  const int kw = h->K >= 8 ? 8 : (h->K >= 4 ? 4 : (h->K >= 2 ? 2 : 1));  // warps per frame
-  const int groups = 8 / kw;
-  const int blocks = (int)std::min<int64_t>((F + groups - 1) / groups, (int64_t)h->sm_count * 8);
-  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, kw);
+  const vet::EntropyRowsPlan pl = plan_entropy_rows(h, F);
+  const int blocks = (int)std::min<int64_t>((F + pl.G - 1) / pl.G, (int64_t)h->sm_count * 8);
+  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, pl);
   VET_CUDA(cudaGetLastError());
   return VET_OK;
 }

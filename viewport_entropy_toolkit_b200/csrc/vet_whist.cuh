@@ -273,51 +273,59 @@ struct EntropyRowsArgs {
   uint32_t* flags;
 };
 
-// kw = warps per frame (1, 2, 4 or 8, host-chosen from K): warp j of a frame's group computes tile counts
-// j, j+kw, ...; the group's first lane then averages them in tile-count order (SA:151-156).
-__global__ void __launch_bounds__(256) k_entropy_rows(EntropyRowsArgs a, int kw) {
+// Row schedule of k_entropy_rows: a block of 8 warps takes G consecutive frames; their G x K histogram rows are dealt
+// to the warps by the host (longest row first onto the least loaded warp), because a row costs one fp64 division and
+// one log2 per 32 tiles of latency -- with one warp per tile count the warp of the 201-tile row worked seven times
+// longer than the one of the 21-tile row and the block waited for it (ncu: barrier stalls 3.9 per issue).
+struct EntropyRowsPlan {
+  int G;                        // frames per block (1, 2, 4 or 8)
+  unsigned char nrow[8];        // rows of every warp
+  unsigned char row_g[8][16];   // frame of the row inside the block's group
+  unsigned char row_k[8][16];   // tile count of the row
+};
+
+__global__ void __launch_bounds__(256) k_entropy_rows(EntropyRowsArgs a, EntropyRowsPlan pl) {
   __shared__ double s_e[8][kMaxTileCounts];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;   // warp in block
-  const int groups = 8 / kw;                                    // frames per block and iteration
-  const int grp = wib / kw, sub = wib % kw;
-  for (int64_t f0 = (int64_t)blockIdx.x * groups; f0 < a.F; f0 += (int64_t)gridDim.x * groups) {
-    const int64_t f = f0 + grp;
-    if (f < a.F) {
+  for (int64_t f0 = (int64_t)blockIdx.x * pl.G; f0 < a.F; f0 += (int64_t)gridDim.x * pl.G) {
+    for (int i = 0; i < pl.nrow[wib]; ++i) {
+      const int g = pl.row_g[wib][i], k = pl.row_k[wib][i];
+      const int64_t f = f0 + g;
+      if (f >= a.F) continue;
       const uint32_t nv = a.nvalid[f];
-      if (nv == 0 && lane == 0 && sub == 0) atomicOr(a.flags, (uint32_t)VET_FLAG_EMPTY_FRAME);
-      for (int k = sub; k < a.K; k += kw) {
-        const int T = a.T[k];
-        const double* __restrict__ row = a.ihist ? nullptr : a.hist[k] + f * (int64_t)T;
-        const uint32_t* __restrict__ irow = a.ihist ? a.ihist + f * a.istride + a.ioff[k] : nullptr;
-        double part = 0.0;
-        for (int t = lane; t < T; t += 32) part += irow ? (double)irow[t] : row[t];
-        const double total = a.use_weight ? warp_sum(part) : (double)nv;
-        double acc = 0.0;
-        for (int t = lane; t < T; t += 32) {
-          const double w = irow ? (double)irow[t] : row[t];
-          if (irow && k == 0 && a.hist0_out) a.hist0_out[f * (int64_t)T + t] = w;
-          if (w > 0.0) {
-            const double p = w / total;
-            acc -= p * log2(p);
-          }
+      const int T = a.T[k];
+      const double* __restrict__ row = a.ihist ? nullptr : a.hist[k] + f * (int64_t)T;
+      const uint32_t* __restrict__ irow = a.ihist ? a.ihist + f * a.istride + a.ioff[k] : nullptr;
+      double part = 0.0;
+      for (int t = lane; t < T; t += 32) part += irow ? (double)irow[t] : row[t];
+      const double total = a.use_weight ? warp_sum(part) : (double)nv;
+      double acc = 0.0;
+      for (int t = lane; t < T; t += 32) {
+        const double w = irow ? (double)irow[t] : row[t];
+        if (irow && k == 0 && a.hist0_out) a.hist0_out[f * (int64_t)T + t] = w;
+        if (w > 0.0) {
+          const double p = w / total;
+          acc -= p * log2(p);
         }
-        const double Hs = warp_sum(acc);
-        const double nt = (double)((k == 0 && a.norm_T0 > 0) ? a.norm_T0 : T);
-        const double nn = (a.use_weight || a.norm_always || total > nt) ? nt : total;
-        const double mp = 1.0 / nn;
-        const double mx = -nn * mp * log2(mp);
-        double e = Hs / mx;
-        if (nv == 0) e = __longlong_as_double(0x7ff8000000000000LL);
-        if (lane == 0) {
-          if (a.per_k) a.per_k[k * a.per_k_stride + f] = e;
-          s_e[wib - sub][k] = e;
-        }
+      }
+      const double Hs = warp_sum(acc);
+      const double nt = (double)((k == 0 && a.norm_T0 > 0) ? a.norm_T0 : T);
+      const double nn = (a.use_weight || a.norm_always || total > nt) ? nt : total;
+      const double mp = 1.0 / nn;
+      const double mx = -nn * mp * log2(mp);
+      double e = Hs / mx;
+      if (nv == 0) e = __longlong_as_double(0x7ff8000000000000LL);
+      if (lane == 0) {
+        if (a.per_k) a.per_k[k * a.per_k_stride + f] = e;
+        s_e[g][k] = e;
       }
     }
     __syncthreads();
-    if (f < a.F && sub == 0 && lane == 0) {
+    if ((int)threadIdx.x < pl.G && f0 + threadIdx.x < a.F) {   // SA:151-156: the average in tile-count order
+      const int64_t f = f0 + threadIdx.x;
+      if (a.nvalid[f] == 0) atomicOr(a.flags, (uint32_t)VET_FLAG_EMPTY_FRAME);
       double esum = 0.0;
-      for (int k = 0; k < a.K; ++k) esum += s_e[wib][k];
+      for (int k = 0; k < a.K; ++k) esum += s_e[threadIdx.x][k];
       a.entropy[f] = esum / (double)a.K;
     }
     __syncthreads();
