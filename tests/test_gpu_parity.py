@@ -464,6 +464,11 @@ def test_large_video_direct_mode(vet, dims, regime):
     p = synth(4, 300, 4242, iid=True, missing=0.1, dtype=np.float64)
     for use_w, tcs in ((True, [20, 50]), (False, [200])):
         e = engine(vet, tcs, fov=100.0, use_w=use_w, W=W, H=H, regime="direct" if regime == "direct" else "auto")
+        if regime == "global":   # per-cell tables exist (also for the weighted 2.08 M-cell handle: its weight columns fit the budget)
+            assert e.cell_lut(0).shape == (H + 1, W + 1)
+        else:
+            with pytest.raises(vet.UnsupportedConfigurationError):
+                e.cell_lut(0)
         sp = e.spatial(dev(p))
         assert e.poll_flags() == 0
         ref = orc.spatial_analyzer(p, W, H, tcs, 100.0, use_w, 2.0)
@@ -478,6 +483,19 @@ def test_large_video_direct_mode(vet, dims, regime):
         h = e.spatial_host(p)
         assert np.array_equal(h["entropy"], sp.entropy.cpu().numpy())
         e.close()
+
+
+def test_weight_table_budget_decides_the_regime(vet):
+    """A weighted handle on a 1920x1080 video keeps per-cell tables while its weight columns stay under the budget
+    (201 tiles at fov = 120: ~105 M entries); the reference's default five tile counts (1424 tiles in all) exceed it and
+    run the direct per-sample regime."""
+    small = engine(vet, [200], fov=120.0, use_w=True, W=1920, H=1080)
+    assert small.cell_lut(0).shape == (1081, 1921)
+    small.close()
+    big = engine(vet, [20, 50, 100, 250, 1000], fov=120.0, use_w=True, W=1920, H=1080)
+    with pytest.raises(vet.UnsupportedConfigurationError):
+        big.cell_lut(0)
+    big.close()
 
 
 def test_analyzers_end_to_end_vs_reference(vet, tmp_path):

@@ -102,9 +102,18 @@ extern "C" int vet_create(vet_handle** out, const vet_config* cfg) {
   // weighted handles need per-cell weight tables (C x T): bounded; unweighted ones only the cell -> tile LUTs
   if (cfg->regime == VET_REGIME_DIRECT && !naive) {
     h->direct_only = true;  // pinned: per-sample evaluation without cell tables
-  } else if (h->direct_only && (h->C <= kGlobalTableCells || (!h->use_weight && h->C <= kGlobalLutCells))) {
-    h->direct_only = false;
-    h->global_tables = true;
+  } else if (h->direct_only) {
+    // Weighted handles keep per-cell weight columns: about C x sum(T_k) x (share of the sphere inside fov/2) entries of
+    // 12 bytes, plus the dense blocks / quantised slices made from them.  Up to 262,144 cells always; beyond that (a
+    // 1920x1080 video has 2.08 M cells) while the estimate stays under 2^27 entries (~1.6 GB of columns) -- e.g. 201
+    // tiles at fov = 120 on 1920x1080: 105 M; the reference's default five tile counts there: 741 M -> direct regime.
+    const double cap_share = 0.5 * (1.0 - std::cos(h->max_d));
+    const double est_entries = (double)h->C * (double)h->sumT * std::min(1.0, cap_share * 1.15 + 0.01);
+    const bool weights_fit = h->C <= kGlobalTableCells || (h->C <= kGlobalLutCells && est_entries <= (double)((int64_t)1 << 27));
+    if ((h->use_weight && weights_fit) || (!h->use_weight && h->C <= kGlobalLutCells)) {
+      h->direct_only = false;
+      h->global_tables = true;
+    }
   }
   if (h->C >= ((int64_t)1 << 31)) return fail(VET_ERR_UNSUPPORTED, "video %dx%d has too many cells", h->W, h->H);
   if (naive && h->direct_only) return fail(VET_ERR_UNSUPPORTED, "video %dx%d is too large for the grid-tiling tables", h->W, h->H);
