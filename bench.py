@@ -430,7 +430,8 @@ def main():
         for s_ in range(len(outs)):
             drain(s_)
 
-    for _ in range(3):   # set-up, not warm-up: the library captures a repeated call as a CUDA graph on its third occurrence
+    for _ in range(3 * len(outs)):   # set-up, not warm-up: the library captures a repeated call as a CUDA graph on its third
+        # occurrence (per set of output buffers)
         step()
     for _ in range(args.warmup):
         step()
