@@ -663,7 +663,7 @@ def main():
     # configs[4], frame-sharded over the ranks of this run: at EVERY N, all ranks
     if not args.no_c5 and args.workload == "c3":
         extra["c5_sharded"] = c5_sharded(torch, dist, device, rank, world, local_rank, peak_gbs,
-                                         steps=min(args.steps, 10), warmup=min(args.warmup, 3))
+                                         steps=min(args.steps, 10), warmup=3)
 
     cpu = None
     if cpu_sample is not None:
