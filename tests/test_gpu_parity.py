@@ -892,6 +892,47 @@ def test_transition_cluster_tail_equals_single_cta(vet, F, U, tcs):
     e.close()
 
 
+@pytest.mark.parametrize("n,alphabet,U,cap", [(200, 3, 2400, 0), (200, 40, 2400, 0), (20, 21, 999, 0), (200, 12, 640, 64), (100, 101, 5000, 0)])
+def test_one_pass_kernel_on_random_tile_patterns_vs_oracle(vet, n, alphabet, U, cap):
+    """Users that hop between a few tiles chosen at random (not lattice neighbours: ranked and unranked deltas mixed,
+    many users per (prev, cur) pair, skewed tile probabilities, missing users) -- the order-dependent bookkeeping of
+    EU:278-318 through k_transition4's first/second/count tables and its sorted list, against the literal oracle:
+    pairs and counts bit-exact, entropies to 1e-9; and bit for bit against the two-pass kernels."""
+    rng = np.random.default_rng(1000 * n + alphabet)
+    e = engine(vet, [n], use_w=False)
+    T = e.num_tiles[0]
+    rep = _tile_to_sample(e.cell_lut(0))
+    tiles = rng.choice(T, size=min(alphabet, T), replace=False)
+    prob = rng.dirichlet(np.full(len(tiles), 0.4))
+    F = 7
+    seq = rng.choice(tiles, size=(F, U), p=prob)
+    stay = rng.uniform(size=(F, U)) < 0.6                      # most users keep their tile, like real viewers
+    for f in range(1, F):
+        seq[f] = np.where(stay[f], seq[f - 1], seq[f])
+    packed = np.zeros((F, U, 3), dtype=np.float64)
+    lut_mu = np.array([rep[int(t)][0] if int(t) in rep else 0.5 for t in range(T)])
+    lut_mv = np.array([rep[int(t)][1] if int(t) in rep else 0.5 for t in range(T)])
+    packed[..., 1] = lut_mu[seq]
+    packed[..., 2] = lut_mv[seq]
+    miss = rng.uniform(size=(F, U)) < 0.03
+    miss[:, 0] = False
+    packed[miss, 1] = np.nan
+    e.set_option("t4_list_cap", cap)
+    res = {}
+    for impl in ("auto", "v3"):
+        e.set_option("transition_kernel", impl)
+        res[impl] = e.transition(dev(packed))
+        assert e.poll_flags() == 0
+    a, b = res["auto"], res["v3"]
+    assert torch.equal(a.pairs0, b.pairs0) and torch.equal(a.prev_count0, b.prev_count0)
+    assert np.array_equal(a.entropy.cpu().numpy(), b.entropy.cpu().numpy(), equal_nan=True)
+    ref = orc.transition_analyzer(packed, W0, H0, [n], mode="literal")
+    assert np.array_equal(a.pairs0.cpu().numpy(), ref["pairs0"])
+    assert np.array_equal(a.prev_count0.cpu().numpy(), ref["prev_count0"])
+    np.testing.assert_allclose(a.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL, equal_nan=True)
+    e.close()
+
+
 @pytest.mark.parametrize("cfg", [
     dict(F=40, U=100_000, tcs=[200], use_w=False),                                  # tile ids from the streaming kernel, 512-thread CTAs
     dict(F=24, U=100_000, tcs=[200, 500, 1000], use_w=False),                       # LUT staged / from global memory, 1024-thread CTAs for 1001 tiles
