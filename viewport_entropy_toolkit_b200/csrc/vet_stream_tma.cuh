@@ -109,6 +109,12 @@ __device__ __forceinline__ bool unit_range_fast(float v) { return __float_as_uin
 __device__ __forceinline__ bool unit_range_fast(double v) {
   return (unsigned long long)__double_as_longlong(v) <= 0x3FF0000000000000ull;
 }
+// NaN (= a missing sample) by its bit pattern: a frame with missing users then needs no branch into classify_slow --
+// with 20 % of the samples missing every warp step used to diverge into it (configs[2]: 1.12 ms against 0.86).
+__device__ __forceinline__ bool is_nan_bits(float v) { return (__float_as_uint(v) & 0x7FFFFFFFu) > 0x7F800000u; }
+__device__ __forceinline__ bool is_nan_bits(double v) {
+  return ((unsigned long long)__double_as_longlong(v) & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull;
+}
 
 // Cooperative 16-byte copy global -> shared of `bytes` (rounded up to 16; both buffers are
 // allocated with that padding).  Element-wise copies of the LUTs showed up as 30 % of the
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(kStreamThreads, VET_STREAM_MINBLOCKS) k_stream
         const int s = ctid + j * (kConsumerWarps * 32);
         if (full_tile || s < nsamp) {
           bool ok = unit_range_fast(mu[j]) && unit_range_fast(mv[j]);
-          if (!ok) {
+          if (!ok && !is_nan_bits(mu[j]) && !is_nan_bits(mv[j])) {  // not in [+0, 1] and not missing: -0.0 or out of range
             const int st = classify_slow(mu[j], mv[j]);
             ok = st == kOk;
             if (st == kOutOfRange) bad = 1;
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_tiles(StreamTilesA
         const int s = ctid + j * (kConsumerWarps * 32);
         if (full_tile || s < nsamp) {
           bool ok = unit_range_fast(mu[j]) && unit_range_fast(mv[j]);
-          if (!ok) {
+          if (!ok && !is_nan_bits(mu[j]) && !is_nan_bits(mv[j])) {  // not in [+0, 1] and not missing: -0.0 or out of range
             const int st = classify_slow(mu[j], mv[j]);
             ok = st == kOk;
             if (st == kOutOfRange) bad = 1;
