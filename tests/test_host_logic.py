@@ -342,3 +342,22 @@ def test_lazy_row_dict_is_a_read_only_dict_view():
     assert len(calls) == 1 and repr(d) == repr({"a": 1, "b": 2})
     with pytest.raises(TypeError):
         d["c"] = 3
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: the reference's own functions from /root/reference or baseline/_ref, else
+    the oracle port) prints ONE JSON line with the contract's keys; needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "samples/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("configs[2]") and d["gpu_launches"] == 0
