@@ -107,8 +107,9 @@ const char* vet_version(void);
  * are bit-reproducible across different frame batchings / shardings only when one mode is pinned.  The others exist
  * so that the parity suite can run the kernel generations against each other bit for bit.  The library reads no
  * environment variable. */
+#define VET_I8_MIN_FRAMES 384     /* frames per call from which the automatic dispatch takes the tensor-core histogram */
 enum {
-  VET_OPT_WEIGHTED_KERNEL = 0,   /* 0 auto (tensor cores from 512 frames per call on, where the bound on the entropy error of the
+  VET_OPT_WEIGHTED_KERNEL = 0,   /* 0 auto (tensor cores from VET_I8_MIN_FRAMES frames per call on, where the bound on the entropy error of the
                                     quantised weights holds: DESIGN 4.3), 1 FP64 pipe, 2 tensor cores (int8 slices) */
   VET_OPT_STREAM_KERNEL = 1,     /* 0 auto, 1 plain loads (k_stream_simple), 2 cell histograms only (no direct tile
                                     histograms), 3 global-table regime without the 16-bit privatised histogram */

@@ -751,10 +751,10 @@ def test_weighted_tensor_core_path_vs_oracle(vet, cfg):
 
 
 def test_weighted_default_dispatch_sparse_frames(vet):
-    """The DEFAULT dispatch (no kernel pinned) on 600 frames of 1-5 users each -- the tensor-core histogram from 512
+    """The DEFAULT dispatch (no kernel pinned) on 600 frames of 1-5 users each -- the tensor-core histogram from 384
     frames per call on -- against the oracle: the support of every hist0 row (tiles with d < fov/2, EU:133) is the
     oracle's, entries above the quantisation floor users * 2^-39 / 1e-9 agree to a pure relative 1e-9, all entries to
-    users * 2^-39 absolute, entropies to 1e-9; and the first 300 frames on their own (FP64 kernel: fewer than 512
+    users * 2^-39 absolute, entropies to 1e-9; and the first 300 frames on their own (FP64 kernel: fewer than 384
     frames) give the same support and the same values to 1e-9."""
     rng = np.random.default_rng(4242)
     F, U = 600, 5
@@ -778,7 +778,7 @@ def test_weighted_default_dispatch_sparse_frames(vet):
     assert np.all(np.abs(h - rh) <= present[:, None] * quantum)
     np.testing.assert_allclose(d.entropy.cpu().numpy(), ref["entropy"], rtol=RTOL, atol=ATOL)
     assert np.array_equal(d.assign0.cpu().numpy(), ref["assign0"])
-    short = e.spatial(dev(p[:300]))                           # fewer than 512 frames: the FP64 kernel
+    short = e.spatial(dev(p[:300]))                           # fewer than VET_I8_MIN_FRAMES = 384 frames: the FP64 kernel
     hs = short.hist0.cpu().numpy()
     assert np.array_equal(hs > 0, h[:300] > 0)
     np.testing.assert_allclose(hs[big[:300]], h[:300][big[:300]], rtol=1e-9, atol=0)
@@ -816,6 +816,34 @@ def test_weighted_tensor_core_count_planes(vet):
     # nothing special still sums to the same total weight in both kernels up to the quantisation
     tot64, tot8 = res["fp64"][0].hist0.sum(1), res["i8"][0].hist0.sum(1)
     np.testing.assert_allclose(tot8.cpu().numpy(), tot64.cpu().numpy(), rtol=1e-11)
+    e.close()
+
+
+def test_tensor_core_histogram_split_over_the_cells_equals_one_cta_per_tile(vet):
+    """k_whist_i8 with few output tiles splits the cells of a tile over several CTAs (int32 partial sums in
+    global memory, added and turned into the rows by k_whist_i8_finish): the rows of the first 200 / 450 frames
+    computed on their own (split) carry the bits of the same frames inside an 1800-frame call (one CTA per tile), call
+    after call, with large counts (second byte plane) in some frames, for two tile counts."""
+    import bench
+    F, U = 1800, 3000
+    p = bench.synth_on_device(torch, F, U, 777, torch.device("cuda"))
+    p[100:140, :400, 1] = 0.25          # 400 users in one cell: the second count plane in frame block 0
+    p[100:140, :400, 2] = 0.75
+    p[7, ::3, 1] = float("nan")
+    e = engine(vet, [200, 50], fov=90.0)
+    e.set_option("weighted_kernel", "i8")
+    full = e.spatial(p)
+    for n in (200, 450, 200):
+        part = e.spatial(p[:n].contiguous())
+        assert torch.equal(part.hist0, full.hist0[:n]), n
+        assert torch.equal(part.entropy, full.entropy[:n]) and torch.equal(part.per_k, full.per_k[:, :n]), n
+    sp, _ = e.analyze(p[:450].contiguous())
+    assert torch.equal(sp.hist0, full.hist0[:450]) and torch.equal(sp.entropy, full.entropy[:450])
+    e.set_option("weighted_kernel", "fp64")
+    ref = e.spatial(p[:450].contiguous())
+    np.testing.assert_allclose(sp.hist0.cpu().numpy(), ref.hist0.cpu().numpy(), rtol=RTOL, atol=U * I8_QUANT)
+    np.testing.assert_allclose(sp.entropy.cpu().numpy(), ref.entropy.cpu().numpy(), rtol=RTOL, atol=0)
+    assert e.poll_flags() == 0
     e.close()
 
 

@@ -77,7 +77,7 @@ CASES = [
     dict(world=2, F=9, U=3000, tcs=[200], fov=90.0, use_w=True, missing=0.0, seed=1),        # ragged 5 + 4, FP64 weighted histogram
     dict(world=3, F=7, U=2001, tcs=[20, 50], fov=120.0, use_w=False, missing=0.1, seed=2),   # missing users, two tile counts, odd U
     dict(world=4, F=3, U=500, tcs=[200], fov=90.0, use_w=True, missing=0.05, seed=3),        # rank 3 owns no frame
-    dict(world=2, F=600, U=300, tcs=[200], fov=90.0, use_w=True, missing=0.02, seed=4),      # >= 512 frames: tensor-core mode pinned on both shards
+    dict(world=2, F=600, U=300, tcs=[200], fov=90.0, use_w=True, missing=0.02, seed=4),      # >= VET_I8_MIN_FRAMES: tensor-core mode pinned on both shards
 ]
 
 

@@ -283,6 +283,15 @@ def test_integration_stub_matches_the_abi(pkg):
         assert name in body, name
 
 
+def test_tensor_core_dispatch_threshold_matches_the_header():
+    """distributed.py pins the weighted-histogram kernel per job with the library's own threshold."""
+    import re
+    from pathlib import Path
+    from viewport_entropy_toolkit_b200 import _native
+    header = (Path(__file__).resolve().parents[1] / "include" / "vet_b200.h").read_text()
+    assert int(re.search(r"#define VET_I8_MIN_FRAMES (\d+)", header).group(1)) == _native.I8_MIN_FRAMES
+
+
 def test_tile_geometry_vs_reference_fixtures(pkg):
     """Tile geometry for renders (DU:58-225, 412-743): boundary segments of the Fibonacci tiles, latitude/longitude
     tile boxes and tile areas, bit for bit against the live-reference fixtures."""

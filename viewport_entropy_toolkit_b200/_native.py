@@ -24,6 +24,10 @@ VET_MISSING = 0xFFFF
 VET_FLAG_OUT_OF_RANGE, VET_FLAG_EMPTY_FRAME, VET_FLAG_NO_COMMON_USER = 1, 2, 4
 VET_REGIME_AUTO, VET_REGIME_DIRECT = 0, 1
 # vet_set_option: name -> (option id, {value name -> value})
+# include/vet_b200.h VET_I8_MIN_FRAMES: frames per call from which the automatic dispatch of the weighted histogram
+# takes the tensor-core kernel (tests/test_host_logic.py checks the two against each other)
+I8_MIN_FRAMES = 384
+
 OPTIONS = {
     "weighted_kernel": (0, {"auto": 0, "fp64": 1, "i8": 2}),
     "stream_kernel": (1, {"auto": 0, "simple": 1, "cells": 2, "global": 3}),

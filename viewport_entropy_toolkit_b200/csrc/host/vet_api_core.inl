@@ -243,6 +243,7 @@ extern "C" int vet_destroy(vet_handle* h) {
   cudaFree(h->d_planes);
   cudaFree(h->d_dirty);
   cudaFree(h->d_i8flags);
+  cudaFree(h->d_i8acc);
   cudaFree(h->d_in[0]);
   cudaFree(h->d_in[1]);
   cudaFree(h->d_in2[0]);

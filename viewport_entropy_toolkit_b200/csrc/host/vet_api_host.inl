@@ -6,7 +6,7 @@ namespace {
 
 // frames per host batch: about 256 MiB of packed input per copy; weighted handles take 512 frames when that
 // stays under 1 GiB, so that the host path runs the same tensor-core weighted histogram as the device path
-// (use_whist_i8: from 512 frames per batch) and returns the same bits
+// (use_whist_i8: decided per call from VET_I8_MIN_FRAMES frames on) and returns the same bits
 int64_t host_batch_frames(const vet_handle* h, int64_t F, int64_t U, size_t esz) {
   if (h->opt[VET_OPT_HOST_BATCH_FRAMES] > 0) return std::min<int64_t>(F, std::max(2, h->opt[VET_OPT_HOST_BATCH_FRAMES]));
   const size_t per_frame = std::max<size_t>((size_t)U * 3 * esz, 1);

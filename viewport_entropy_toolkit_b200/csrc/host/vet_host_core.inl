@@ -114,6 +114,8 @@ struct vet_handle {
   int64_t plane_rows = 0;        // row capacity of the allocation (multiple of 128)
   uint8_t* d_dirty = nullptr;    // [plane_rows]
   uint32_t* d_i8flags = nullptr; // [2][plane_rows/128]
+  void* d_i8acc = nullptr;       // split-K slices of k_whist_i8's accumulators
+  size_t i8acc_bytes = 0;
   CUtensorMap tm_cnt;
   bool planes_from_stream = false;  // the last launch_stream wrote the planes of its batch itself
   bool i8_attr_set = false;
@@ -298,6 +300,7 @@ constexpr int64_t kGlobalTableCells = 262144;  // largest cell grid of the globa
 constexpr int64_t kGlobalLutCells = (int64_t)1 << 24;  // the same for unweighted handles (only LUTs: 2 B x C per tile count)
 
 // tensor-core weighted histogram (defined with launch_whist_i8 below)
+constexpr int64_t kI8MinFrames = VET_I8_MIN_FRAMES;
 bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U);
 int build_i8_tables(vet_handle* h, TileSet& t);
 int ensure_planes(vet_handle* h, int64_t F, cudaStream_t st);

@@ -429,11 +429,11 @@ bool use_whist_i8(const vet_handle* h, int64_t F, int64_t U) {
   if (U * 255 >= ((int64_t)1 << 31)) return false;  // int32 accumulators: D <= 255 * sum(count plane) <= 255 U
   if ((size_t)vet::kI8SmemBytes + kStaticSmemSlack > h->smem_optin) return false;
   if (impl == 2) return true;
-  // A CTA of the tensor-core kernel takes ~70 us whatever the batch (it walks all cells of 128 frames x 48
-  // tiles); the FP64 kernel costs ~0.14 us per frame at 201 tiles.  From a few hundred frames on the
-  // tensor cores win (measured: equal at 450 frames, 0.07 vs 0.50 ms at 3600).
+  // A CTA of the tensor-core kernel takes ~70 us over all cells of 128 frames x 48 tiles, split over up to 8 CTAs
+  // when the batch has few such tiles (launch_whist_i8); the FP64 kernel costs ~0.14 us per frame at 201 tiles.
+  // From a few hundred frames on the tensor cores win (0.07 vs 0.50 ms at 3600 frames).
   // decided per API call, not per internal batch, so that a short last batch does not switch kernels
-  if (std::max(F, h->call_frames) < 512) return false;
+  if (std::max(F, h->call_frames) < kI8MinFrames) return false;
   // and only where the weight quantisation keeps the entropies inside the stated tolerance (i8_ok, build_i8_tables)
   vet_handle* hm = const_cast<vet_handle*>(h);
   for (auto& t : hm->ts) {
@@ -575,7 +575,17 @@ int launch_whist_i8(vet_handle* h, int k, int64_t F, double* hist, cudaStream_t 
   a.n_blocks = t.i8_blocks;
   a.kb_range = t.d_kb_range;
   a.hist = hist;
-  const int grid = fblocks * t.i8_blocks;
+  // few output tiles (20 at 450 frames x 201 tiles, each ~70 us of TMA + MMA steps over every cell): split the cells
+  // over up to 8 CTAs per tile, at least 8 K blocks each
+  const int tiles = fblocks * t.i8_blocks;
+  const int kblocks = (int)(i8_kp(h) / vet::kI8BK);
+  const int ksplit = std::max(1, std::min({vet::kI8MaxSplit, h->sm_count / std::max(tiles, 1), kblocks / 8}));
+  if (ksplit > 1) {
+    if (int rc = grow((void**)&h->d_i8acc, &h->i8acc_bytes, (size_t)tiles * ksplit * (2 * vet::kI8N * vet::kI8M) * 4)) return rc;
+    a.part = (int*)h->d_i8acc;
+  }
+  a.ksplit = ksplit;
+  const int grid = tiles * ksplit;
   for (int pass = 0; pass < 2; ++pass) {
     a.row_a = pass == 0 ? 0 : (int)(2 * h->plane_rows);
     a.row_b = (int)h->plane_rows;
@@ -585,6 +595,7 @@ int launch_whist_i8(vet_handle* h, int k, int64_t F, double* hist, cudaStream_t 
     a.accumulate = pass;
     LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
     vet::k_whist_i8<<<grid, vet::kI8Threads, vet::kI8SmemBytes, st>>>(h->tm_cnt, t.tm_w, a);
+    if (ksplit > 1) vet::k_whist_i8_finish<<<dim3(vet::kI8TilesPerBlock, tiles), vet::kI8M, 0, st>>>(a);
   }
   VET_CUDA(cudaGetLastError());
   return VET_OK;

@@ -52,6 +52,7 @@ constexpr int kI8ABytes = kI8M * kI8BK;                    // 16 KB per count pl
 constexpr int kI8BBytes = kI8N * kI8BK;                    // 30 KB
 constexpr int kI8StageBytes = 2 * kI8ABytes + kI8BBytes;   // 62 KB, multiple of 1024
 constexpr int kI8Threads = 192;
+constexpr int kI8MaxSplit = 8;          // CTAs that may share one output tile (split over the cells)
 constexpr int kI8TmemCols = 512;
 constexpr int kI8SmemBytes = kI8Stages * kI8StageBytes + 1024;  // + slack to align the ring to 1024 B
 static_assert(kI8StageBytes % 1024 == 0 && (kI8ABytes + kI8BBytes) % 1024 == 0, "stages must keep the 1024 B swizzle alignment");
@@ -121,19 +122,31 @@ struct WhistI8Args {
   int accumulate;             // add to hist instead of storing (second pass, planes of higher bits)
   const int2* kb_range;       // [n_blocks] first / past-the-end 128-cell K block with a non-zero weight
   double* hist;               // [F, T]
+  // split-K (few frame blocks: 20 output tiles at 450 frames x 201 tiles, each walking every cell for ~70 us): ksplit
+  // CTAs share one output tile, each stores its int32 accumulators in its own slice of `part` and k_whist_i8_finish
+  // adds the slices (integers: exact whatever the split) and turns the sums into the histogram rows
+  int ksplit;                 // 1 = one CTA per output tile, rows straight from TMEM
+  int* part;                  // [frame blocks * n_blocks][ksplit][2 planes][240 columns][128 frames]
 };
 
 __global__ void __launch_bounds__(kI8Threads, 1)
 k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ CUtensorMap tm_w, WhistI8Args a) {
-  const int nb = blockIdx.x % a.n_blocks;
-  const int mb = blockIdx.x / a.n_blocks;
+  const int tile_id = blockIdx.x / a.ksplit;  // the CTAs of one output tile are neighbours: they read the same planes
+  const int sp = blockIdx.x % a.ksplit;
+  const int nb = tile_id % a.n_blocks;
+  const int mb = tile_id / a.n_blocks;
   if (a.run_if && a.run_if[mb] == 0u) return;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) unsigned long long s_full[kI8StagesOne], s_empty[kI8StagesOne], s_accum;
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const int2 kr = a.kb_range[nb];
+  int2 kr = a.kb_range[nb];
+  if (a.ksplit > 1) {  // this CTA's share of the K blocks (possibly none)
+    const int per = (kr.y - kr.x + a.ksplit - 1) / a.ksplit;
+    kr.x = min(kr.y, kr.x + sp * per);
+    kr.y = min(kr.y, kr.x + per);
+  }
   const bool two = a.flag_b && a.flag_b[mb] != 0u;
 
   // the ring holds 3 stages of {plane 0, plane 1, weights} or 4 stages of {plane 0, weights}
@@ -200,34 +213,60 @@ k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ C
     // ===== epilogue: warp w may read TMEM lanes [32 (w % 4), +32) =====
     const int q = warp & 3;
     const int64_t f = (int64_t)mb * kI8M + q * 32 + lane;
-    mbar_wait(smem_u32(&s_accum), 0u);
-    tc_fence_after();
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    if (a.ksplit > 1) {
+      // column-major slice: the 32 frames of a warp are one 128-byte store
+      int* __restrict__ part = a.part + ((int64_t)tile_id * a.ksplit + sp) * (2 * kI8N * kI8M) + q * 32 + lane;
+      const bool have = kr.y > kr.x;  // no K block for this CTA: its slice is zero
+      if (have) {
+        mbar_wait(smem_u32(&s_accum), 0u);
+        tc_fence_after();
+      }
 #pragma unroll 1
-    for (int j0 = 0; j0 < kI8TilesPerBlock; j0 += 16) {
-      double v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = 0.0;
-#pragma unroll
-      for (int s = kI8Slices - 1; s >= 0; --s) {  // most significant slice first
+      for (int c0 = 0; c0 < kI8N; c0 += 16) {
         uint32_t r0[16], r1[16];
-        tc_ld16(lane_base + s * kI8TilesPerBlock + j0, r0);
-        if (two) tc_ld16(lane_base + 256 + s * kI8TilesPerBlock + j0, r1);
-        tc_wait_ld();
-        const double scale = __longlong_as_double((long long)(1023 + 8 * s - kI8FracBits + a.shift) << 52);  // 2^(8s-39+shift)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r0[j] = r1[j] = 0u;
+        if (have) {
+          tc_ld16(lane_base + c0, r0);
+          if (two) tc_ld16(lane_base + 256 + c0, r1);
+          tc_wait_ld();
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          long long x = (long long)(int)r0[j];
-          if (two) x += (long long)(int)r1[j] << 8;
-          v[j] = fma((double)x, scale, v[j]);
+          __stcg(part + (c0 + j) * kI8M, (int)r0[j]);
+          if (two) __stcg(part + (kI8N + c0 + j) * kI8M, (int)r1[j]);
         }
       }
-      if (f < a.F) {
-        double* __restrict__ row = a.hist + f * (int64_t)a.T;
+    } else {
+      mbar_wait(smem_u32(&s_accum), 0u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j0 = 0; j0 < kI8TilesPerBlock; j0 += 16) {
+        double v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int tile = nb * kI8TilesPerBlock + j0 + j;
-          if (tile < a.T) row[tile] = a.accumulate ? row[tile] + v[j] : v[j];
+        for (int j = 0; j < 16; ++j) v[j] = 0.0;
+#pragma unroll
+        for (int s = kI8Slices - 1; s >= 0; --s) {  // most significant slice first
+          uint32_t r0[16], r1[16];
+          tc_ld16(lane_base + s * kI8TilesPerBlock + j0, r0);
+          if (two) tc_ld16(lane_base + 256 + s * kI8TilesPerBlock + j0, r1);
+          tc_wait_ld();
+          const double scale = __longlong_as_double((long long)(1023 + 8 * s - kI8FracBits + a.shift) << 52);  // 2^(8s-39+shift)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            long long x = (long long)(int)r0[j];
+            if (two) x += (long long)(int)r1[j] << 8;
+            v[j] = fma((double)x, scale, v[j]);
+          }
+        }
+        if (f < a.F) {
+          double* __restrict__ row = a.hist + f * (int64_t)a.T;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int tile = nb * kI8TilesPerBlock + j0 + j;
+            if (tile < a.T) row[tile] = a.accumulate ? row[tile] + v[j] : v[j];
+          }
         }
       }
     }
@@ -235,6 +274,47 @@ k_whist_i8(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tc_dealloc(tmem, kI8TmemCols);
+}
+
+// Second half of the split-K launch: thread (frame, tile) adds the ksplit slices of its 5 (10) accumulators and runs
+// the same fma chain as the one-CTA epilogue above, so the rows carry the same bits however the cells were split.
+// Grid: (48 tile columns, output tiles), 128 threads = the frames of the block.
+__global__ void __launch_bounds__(kI8M) k_whist_i8_finish(WhistI8Args a) {
+  const int tile_id = blockIdx.y;
+  const int nb = tile_id % a.n_blocks;
+  const int mb = tile_id / a.n_blocks;
+  if (a.run_if && a.run_if[mb] == 0u) return;
+  const int j = blockIdx.x;
+  const int tile = nb * kI8TilesPerBlock + j;
+  const int64_t f = (int64_t)mb * kI8M + threadIdx.x;
+  if (tile >= a.T || f >= a.F) return;
+  const bool two = a.flag_b && a.flag_b[mb] != 0u;
+  const int* __restrict__ part = a.part + (int64_t)tile_id * a.ksplit * (2 * kI8N * kI8M) + threadIdx.x;
+  // every load of the thread in flight at once: 5 slices x up to kI8MaxSplit parts (x 2 planes)
+  int x0[kI8Slices], x1[kI8Slices];
+#pragma unroll
+  for (int s = 0; s < kI8Slices; ++s) x0[s] = x1[s] = 0;
+#pragma unroll
+  for (int sp = 0; sp < kI8MaxSplit; ++sp) {
+    if (sp < a.ksplit) {
+#pragma unroll
+      for (int s = 0; s < kI8Slices; ++s) {
+        const int* p = part + (int64_t)sp * (2 * kI8N * kI8M) + (s * kI8TilesPerBlock + j) * kI8M;
+        x0[s] += __ldcg(p);
+        if (two) x1[s] += __ldcg(p + kI8N * kI8M);
+      }
+    }
+  }
+  double v = 0.0;
+#pragma unroll
+  for (int s = kI8Slices - 1; s >= 0; --s) {
+    long long x = (long long)x0[s];
+    if (two) x += (long long)x1[s] << 8;
+    const double scale = __longlong_as_double((long long)(1023 + 8 * s - kI8FracBits + a.shift) << 52);
+    v = fma((double)x, scale, v);
+  }
+  double* __restrict__ row = a.hist + f * (int64_t)a.T;
+  row[tile] = a.accumulate ? row[tile] + v : v;
 }
 
 // Cell histogram rows (uint32) -> the byte planes of the tensor-core kernel, for frames that the
@@ -284,8 +364,9 @@ __global__ void __launch_bounds__(256) k_cnt_planes(CntPlanesArgs a) {
         p0[o] = pack_bytes(v[i], 0);
         p1[o] = w1;
         p2[o] = w2;
-        if (w1) atomicOr(&a.hi1[f >> 7], 1u);
-        if (w2) atomicOr(&a.hi2[f >> 7], 1u);
+        // a few flags for millions of words: look before the atomic (a stale zero only costs one more atomic)
+        if (w1 && *reinterpret_cast<volatile uint32_t*>(&a.hi1[f >> 7]) == 0u) atomicOr(&a.hi1[f >> 7], 1u);
+        if (w2 && *reinterpret_cast<volatile uint32_t*>(&a.hi2[f >> 7]) == 0u) atomicOr(&a.hi2[f >> 7], 1u);
         if (u % upr == 0 && lane == 0) a.dirty[f] = 3;
       }
     }

@@ -21,6 +21,8 @@ from typing import Callable, List, Optional, Tuple, Union
 import torch
 import torch.distributed as dist
 
+from . import _native
+
 
 def frame_range(num_frames: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous frame range [begin, end) of `rank`; the first F % world ranks get one extra frame."""
@@ -168,7 +170,7 @@ class ShardedAnalyzer:
         if n_own:
             pinned = eng.get_option("weighted_kernel") == "auto"
             if pinned:
-                eng.set_option("weighted_kernel", "i8" if self.num_frames >= 512 else "fp64")
+                eng.set_option("weighted_kernel", "i8" if self.num_frames >= _native.I8_MIN_FRAMES else "fp64")
             try:
                 sp, tr = eng.analyze(packed_local, mode=self.mode, want_per_k=False, want_hist0=self.want_hist0,
                                      want_assign0=self.want_assign0, want_pairs0=False)
