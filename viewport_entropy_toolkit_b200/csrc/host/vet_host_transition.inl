@@ -299,6 +299,43 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         per_k = h->d_trk;
         stride = rows;
       }
+      // one-pass kernel plans of every tile count, and the tile-id rows they read where the rows hold cell ids (several
+      // tile counts): relabelled here, up to kRelabelGroup tile counts per pass over the cell ids
+      Plan4 plan4[vet::kMaxTileCounts];
+      const uint16_t* rows_of[vet::kMaxTileCounts] = {};
+      {
+        int need[vet::kMaxTileCounts], nneed = 0;
+        for (int k = 0; k < a.K; ++k) {
+          const TileSet& tsk = h->ts[std::min(k, h->K - 1)];
+          plan4[k] = (use_t4 && plan[k].mode >= 0 && k < h->K && tsk.T == a.T[k]) ? plan_transition4(h, tsk, rows) : Plan4{};
+          if (plan4[k].ok && plan[k].lw != vet::kLutIdentity && a.cell16) need[nneed++] = k;
+        }
+        const int64_t n = a.F * U;
+        const size_t slot = ((size_t)n * 2 + 16 + 15) & ~(size_t)15;
+        const int cp = (int)((h->C + 1 + 7) & ~(int64_t)7);
+        const int group = (int)std::min<size_t>(vet::kRelabelGroup, (h->smem_optin - kStaticSmemSlack) / ((size_t)cp * 2));
+        if (nneed)
+          if (int rc = grow((void**)&h->d_rows, &h->rows_bytes, slot * (group >= 2 ? nneed : 1))) return rc;
+        for (int i0 = 0; group >= 2 && i0 < nneed; i0 += group) {
+          vet::RelabelArgs R{};
+          R.cells = a.cell16;
+          R.G = std::min(group, nneed - i0);
+          R.C = (int)h->C;
+          R.cp = cp;
+          R.n = n;
+          for (int g = 0; g < R.G; ++g) {
+            R.lut[g] = a.lut[need[i0 + g]];
+            R.tiles[g] = (uint16_t*)((char*)h->d_rows + slot * (i0 + g));
+            rows_of[need[i0 + g]] = R.tiles[g];
+          }
+          const size_t smem = (size_t)R.G * cp * 2;
+          VET_CUDA(cudaFuncSetAttribute(vet::k_relabel_rows_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+          vet::k_relabel_rows_group<<<(unsigned)std::min<int64_t>((n / 8 + vet::kRelabelThreads - 1) / vet::kRelabelThreads + 1, h->sm_count),
+                                      vet::kRelabelThreads, smem, st>>>(R);
+          VET_CUDA(cudaGetLastError());
+        }
+      }
       bool any_hash = false;
       for (int k = 0; k < a.K; ++k) {
         Plan pl = plan[k];
@@ -337,18 +374,20 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
         bool t4_done = false;
         // the k-th tile set of the handle (cell LUT or, with tile ids in the rows, the identity table over it)
         const TileSet& tsk = h->ts[std::min(k, h->K - 1)];
-        const Plan4 p4 = (use_t4 && k < h->K && tsk.T == a.T[k]) ? plan_transition4(h, tsk, rows) : Plan4{};
+        const Plan4 p4 = plan4[k];
         if (p4.ok) {
           if (pl.lw != vet::kLutIdentity) {
             // several tile counts: the rows hold cell ids -> tile ids of this tile count first (one lookup per sample
             // instead of two per user and pair inside the kernels)
-            if (int rc = grow((void**)&h->d_rows, &h->rows_bytes, (size_t)a.F * U * 2 + 16)) return rc;
-            const int64_t n = a.F * U;
-            LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
-            vet::k_relabel_rows<<<(unsigned)std::min<int64_t>((n / 8 + 255) / 256 + 1, (int64_t)h->sm_count * 16), 256, 0, st>>>(
-                a.cell16, a.lut[k], n, h->d_rows);
-            VET_CUDA(cudaGetLastError());
-            A3.cell16 = h->d_rows;
+            if (!rows_of[k]) {  // tables of two tile counts do not fit shared memory together: one pass per tile count
+              const int64_t n = a.F * U;
+              LaunchTimer lt(h, VET_KERNEL_TRANSITION, st);
+              vet::k_relabel_rows<<<(unsigned)std::min<int64_t>((n / 8 + 255) / 256 + 1, (int64_t)h->sm_count * 16), 256, 0, st>>>(
+                  a.cell16, a.lut[k], n, h->d_rows);
+              VET_CUDA(cudaGetLastError());
+              rows_of[k] = h->d_rows;
+            }
+            A3.cell16 = rows_of[k];
             A3.lut_src = nullptr;
             A3.pair_scratch = keep_scratch ? h->d_pairs : nullptr;
             pl.lw = vet::kLutIdentity;
