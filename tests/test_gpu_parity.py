@@ -970,6 +970,7 @@ def test_one_pass_kernel_on_random_tile_patterns_vs_oracle(vet, n, alphabet, U, 
     dict(F=5, U=3000, tcs=[50], use_w=True, iid=True),                              # iid: lists overflow -> pairs redone by the two-pass kernels
     dict(F=9, U=4000, tcs=[200, 500], use_w=False, cap=8),                          # tiny list: a mix of pairs kept and pairs handed on
     dict(F=2, U=9, tcs=[200], use_w=False),
+    dict(F=6, U=4003, tcs=[700, 800, 900, 1000], use_w=False, missing=0.05),        # relabelling: four lookup tables in shared memory for one pass over the cell ids; odd U
     dict(F=4, U=66_000, tcs=[200], use_w=False, cluster="force"),                  # 3 pairs on clusters of 8 CTAs (tables merged through DSMEM)
     dict(F=152, U=16_384, tcs=[200, 500], use_w=False, cluster="force"),           # one full round + 3 pairs on clusters of 4
     dict(F=10, U=600_000, tcs=[200], use_w=True),                                   # 9 pairs of 600k users: clusters picked by the host itself

@@ -478,8 +478,10 @@ __global__ void k_relabel_rows(const uint16_t* __restrict__ cells, const uint16_
 
 // The same for up to kRelabelGroup tile counts in one pass over the cell ids: the lookup tables sit in shared memory
 // (entry C = 0xFFFF for a missing sample, so no branch), every cell id is read once and one row per tile count written.
-// Three separate passes with lookups through L1 took 3 x 0.43 ms on 100k users x 3600 frames (configs[3]); this one is
-// bound by its 4 x 0.72 GB of traffic.
+// Three separate passes with lookups through L1 took 3 x 0.43 ms on 100k users x 3600 frames (configs[3]); this one
+// takes 0.55 ms for its 0.72 GB in + 3 x 0.72 GB out (5.1 TB/s on a stream that is three quarters writes).  Measured and
+// not kept: the tile ids of the three tile counts packed into one 32-bit entry (one lookup per sample instead of three:
+// 0.58 ms) and four 16-byte loads in flight per thread (0.57 ms) -- neither the lookups nor the latency bound it.
 constexpr int kRelabelGroup = 4;
 constexpr int kRelabelThreads = 1024;
 struct RelabelArgs {
