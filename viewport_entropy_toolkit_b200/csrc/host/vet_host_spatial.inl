@@ -326,6 +326,29 @@ vet::EntropyRowsPlan plan_entropy_rows(const vet_handle* h, int64_t F) {
   return best;
 }
 
+// Entropies of F frames from their histogram rows: k_entropy_frames (one frame per block and step, see vet_whist.cuh);
+// k_entropy_rows only when the rows of a frame do not fit 48 KB of shared memory.
+int launch_entropy_kernel(vet_handle* h, vet::EntropyRowsArgs& e, int64_t F, cudaStream_t st) {
+  vet::EntropyFramesPlan fp{};
+  for (int k = 0; k < e.K; ++k) {
+    const int units = (e.T[k] + 31) / 32;
+    fp.uoff[k + 1] = fp.uoff[k] + units;
+    fp.soff[k + 1] = fp.soff[k] + units * 32;
+  }
+  fp.nunits = fp.uoff[e.K];
+  const size_t smem = (size_t)fp.soff[e.K] * 16;
+  if (smem <= 48 * 1024) {
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(F, (int64_t)h->sm_count * 8));
+    vet::k_entropy_frames<<<blocks, 256, smem, st>>>(e, fp);
+  } else {
+    const vet::EntropyRowsPlan pl = plan_entropy_rows(h, F);
+    const int blocks = (int)std::min<int64_t>((F + pl.G - 1) / pl.G, (int64_t)h->sm_count * 8);
+    vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, pl);
+  }
+  VET_CUDA(cudaGetLastError());
+  return VET_OK;
+}
+
 int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* entropy, double* per_k, int64_t per_k_stride,
                           double* hist0, cudaStream_t st) {
   vet::EntropyRowsArgs e{};
@@ -347,11 +370,7 @@ int launch_tiles_epilogue(vet_handle* h, const TilesPlan& p, int64_t F, double* 
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
   LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-  const vet::EntropyRowsPlan pl = plan_entropy_rows(h, F);
-  const int blocks = (int)std::min<int64_t>((F + pl.G - 1) / pl.G, (int64_t)h->sm_count * 8);
-  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, pl);
-  VET_CUDA(cudaGetLastError());
-  return VET_OK;
+  return launch_entropy_kernel(h, e, F, st);
 }
 
 // k_whist for tile count k over F frames of the cell histogram `cnt` -> hist[F,T_k]
@@ -629,11 +648,7 @@ int launch_weighted_rows(vet_handle* h, int64_t F, double* const* hists, const u
   e.per_k_stride = per_k_stride;
   e.flags = h->d_flags;
   LaunchTimer lt(h, VET_KERNEL_EPILOGUE, st);
-  const vet::EntropyRowsPlan pl = plan_entropy_rows(h, F);
-  const int blocks = (int)std::min<int64_t>((F + pl.G - 1) / pl.G, (int64_t)h->sm_count * 8);
-  vet::k_entropy_rows<<<blocks, 256, 0, st>>>(e, pl);
-  VET_CUDA(cudaGetLastError());
-  return VET_OK;
+  return launch_entropy_kernel(h, e, F, st);
 }
 
 int launch_weighted_epilogue(vet_handle* h, int64_t F, int64_t U, double* entropy, double* per_k, int64_t per_k_stride,

@@ -133,7 +133,7 @@ __device__ __forceinline__ double normalized_entropy(const double* hist, int T, 
       const double w = hist[t];
       if (w > 0.0) {
         const double p = w / total;
-        acc -= p * log2(p);
+        acc = fma(-p, log2(p), acc);  // spelled out: k_entropy_frames adds the same products from shared memory
       }
     }
     acc = warp_sum(acc);

@@ -292,20 +292,21 @@ __global__ void __launch_bounds__(256) k_entropy_rows(EntropyRowsArgs a, Entropy
       const int g = pl.row_g[wib][i], k = pl.row_k[wib][i];
       const int64_t f = f0 + g;
       if (f >= a.F) continue;
-      const uint32_t nv = a.nvalid[f];
+      const uint32_t nv = __ldcg(a.nvalid + f);
       const int T = a.T[k];
       const double* __restrict__ row = a.ihist ? nullptr : a.hist[k] + f * (int64_t)T;
       const uint32_t* __restrict__ irow = a.ihist ? a.ihist + f * a.istride + a.ioff[k] : nullptr;
       double part = 0.0;
-      for (int t = lane; t < T; t += 32) part += irow ? (double)irow[t] : row[t];
+      if (a.use_weight)
+        for (int t = lane; t < T; t += 32) part += irow ? (double)__ldcg(irow + t) : row[t];
       const double total = a.use_weight ? warp_sum(part) : (double)nv;
       double acc = 0.0;
       for (int t = lane; t < T; t += 32) {
-        const double w = irow ? (double)irow[t] : row[t];
+        const double w = irow ? (double)__ldcg(irow + t) : row[t];
         if (irow && k == 0 && a.hist0_out) a.hist0_out[f * (int64_t)T + t] = w;
         if (w > 0.0) {
           const double p = w / total;
-          acc -= p * log2(p);
+          acc = fma(-p, log2(p), acc);
         }
       }
       const double Hs = warp_sum(acc);
@@ -323,12 +324,92 @@ __global__ void __launch_bounds__(256) k_entropy_rows(EntropyRowsArgs a, Entropy
     __syncthreads();
     if ((int)threadIdx.x < pl.G && f0 + threadIdx.x < a.F) {   // SA:151-156: the average in tile-count order
       const int64_t f = f0 + threadIdx.x;
-      if (a.nvalid[f] == 0) atomicOr(a.flags, (uint32_t)VET_FLAG_EMPTY_FRAME);
+      if (__ldcg(a.nvalid + f) == 0) atomicOr(a.flags, (uint32_t)VET_FLAG_EMPTY_FRAME);
       double esum = 0.0;
       for (int k = 0; k < a.K; ++k) esum += s_e[threadIdx.x][k];
       a.entropy[f] = esum / (double)a.K;
     }
     __syncthreads();
+  }
+}
+
+// One frame per block and step, the div + log2 of a frame spread over all 8 warps.  k_entropy_rows gives a warp whole
+// rows: a 201-tile row is seven dependent div + log2 rounds of one warp (~3.5 us), a group of 8 frames x 4 tile counts
+// takes a block 14 us however many blocks run -- 15 us behind a 60 us streaming kernel on configs[1].  Here unit (k, j)
+// = tiles 32 j .. 32 j + 31 of tile count k goes to warp u mod 8, which leaves p and log2 p in shared memory; then the
+// warp of row k adds the products in k_entropy_rows' order (lane l: tiles l, l + 32, ...; butterfly), so the bits are
+// the same.  Dynamic shared memory: 2 x soff[K] doubles.  configs[1]: 15 -> 10 us, the step 0.077 -> 0.072 ms.
+// Measured and dropped: this kernel launched as a programmatic dependent of k_stream_tiles (griddepcontrol), waiting
+// per frame on completion counters and working beside the streaming CTAs -- one or two blocks fit next to a streaming
+// CTA, a frame takes such a block ~4 us, and the step grew to 0.094 ms.
+struct EntropyFramesPlan {
+  int nunits;
+  int uoff[kMaxTileCounts + 1];  // first unit of every tile count
+  int soff[kMaxTileCounts + 1];  // first shared-memory slot of every tile count (32 per unit)
+};
+
+__global__ void __launch_bounds__(256) k_entropy_frames(EntropyRowsArgs a, EntropyFramesPlan pl) {
+  extern __shared__ __align__(16) double s_pl[];
+  double* s_p = s_pl;
+  double* s_l = s_pl + pl.soff[a.K];
+  __shared__ double s_tot[kMaxTileCounts], s_e[kMaxTileCounts];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int64_t f = blockIdx.x; f < a.F; f += gridDim.x) {
+    const uint32_t nv = __ldcg(a.nvalid + f);
+    if (a.use_weight) {  // totals of the weighted rows (the unweighted total is the number of present users)
+      for (int k = wib; k < a.K; k += 8) {
+        const int T = a.T[k];
+        const double* __restrict__ row = a.hist[k] + f * (int64_t)T;
+        double part = 0.0;
+        for (int t = lane; t < T; t += 32) part += row[t];
+        part = warp_sum(part);
+        if (lane == 0) s_tot[k] = part;
+      }
+      __syncthreads();
+    }
+    for (int u = wib; u < pl.nunits; u += 8) {
+      int k = 0;
+      while (u >= pl.uoff[k + 1]) ++k;
+      const int j = u - pl.uoff[k], t = 32 * j + lane, T = a.T[k];
+      const double total = a.use_weight ? s_tot[k] : (double)nv;
+      double w = 0.0;
+      if (t < T) {
+        w = a.ihist ? (double)__ldcg(a.ihist + f * a.istride + a.ioff[k] + t) : a.hist[k][f * (int64_t)T + t];
+        if (a.ihist && k == 0 && a.hist0_out) a.hist0_out[f * (int64_t)T + t] = w;
+      }
+      double p = 0.0, l = 0.0;
+      if (w > 0.0) {
+        p = w / total;
+        l = log2(p);
+      }
+      s_p[pl.soff[k] + t] = p;
+      s_l[pl.soff[k] + t] = l;
+    }
+    __syncthreads();
+    for (int k = wib; k < a.K; k += 8) {
+      const int T = a.T[k], nj = pl.uoff[k + 1] - pl.uoff[k];
+      const double total = a.use_weight ? s_tot[k] : (double)nv;
+      double acc = 0.0;
+      for (int j = 0; j < nj; ++j) acc = fma(-s_p[pl.soff[k] + 32 * j + lane], s_l[pl.soff[k] + 32 * j + lane], acc);
+      const double Hs = warp_sum(acc);
+      const double nt = (double)((k == 0 && a.norm_T0 > 0) ? a.norm_T0 : T);
+      const double nn = (a.use_weight || a.norm_always || total > nt) ? nt : total;
+      const double mp = 1.0 / nn;
+      const double mx = -nn * mp * log2(mp);
+      double e = Hs / mx;
+      if (nv == 0) e = __longlong_as_double(0x7ff8000000000000LL);
+      if (lane == 0) {
+        if (a.per_k) a.per_k[k * a.per_k_stride + f] = e;
+        s_e[k] = e;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // SA:151-156: the average in tile-count order
+      if (nv == 0) atomicOr(a.flags, (uint32_t)VET_FLAG_EMPTY_FRAME);
+      double esum = 0.0;
+      for (int k = 0; k < a.K; ++k) esum += s_e[k];
+      a.entropy[f] = esum / (double)a.K;
+    }
   }
 }
 
