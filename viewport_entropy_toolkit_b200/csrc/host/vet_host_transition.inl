@@ -430,7 +430,11 @@ int launch_transition(vet_handle* h, vet::TransitionArgs& a, int64_t rows, int64
           VET_CUDA(cudaFuncSetAttribute(vet::k_transition4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p4.smem));
           if (cluster_tail) {
             const int64_t rem = rows % h->sm_count;
-            for (int S = 8; S >= 2 && rem > 0 && !S4; S >>= 1)
+            // clusters of 16 (non-portable size, where the occupancy query grants them) when 16 shares of a frame still
+            // hold 32k users: 5 pairs of 1M users 77 -> 70 us
+            const int Smax = U >= (int64_t)16 * 32768 ? 16 : 8;
+            if (Smax == 16) VET_CUDA(cudaFuncSetAttribute(vet::k_transition4<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            for (int S = Smax; S >= 2 && rem > 0 && !S4; S >>= 1)
               if (U >= (int64_t)S * p4.threads * 8 && (cluster_tail == 2 || U * (S - 1) >= (int64_t)131072 * S) &&
                   rem <= t4c_max_clusters(h, S, p4.threads, p4.smem))
                 S4 = S;
