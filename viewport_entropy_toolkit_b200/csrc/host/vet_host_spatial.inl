@@ -329,7 +329,7 @@ vet::EntropyRowsPlan plan_entropy_rows(const vet_handle* h, int64_t F) {
 // Entropies of F frames from their histogram rows.  Several tile counts: k_entropy_frames (one frame per block and step,
 // its rows spread over the 8 warps: vet_whist.cuh).  One tile count: k_entropy_rows, whose 8 warps take one row each of 8
 // frames -- nothing to balance there, and one round of blocks instead of three at 3600 frames (headline step: 0.862 ms
-// against 0.868 with k_entropy_frames); also when the rows of a frame do not fit 48 KB of shared memory.
+// against 0.868 with k_entropy_frames); also when the rows of a frame do not fit 40 KB of shared memory.
 int launch_entropy_kernel(vet_handle* h, vet::EntropyRowsArgs& e, int64_t F, cudaStream_t st) {
   vet::EntropyFramesPlan fp{};
   for (int k = 0; k < e.K; ++k) {
@@ -339,7 +339,7 @@ int launch_entropy_kernel(vet_handle* h, vet::EntropyRowsArgs& e, int64_t F, cud
   }
   fp.nunits = fp.uoff[e.K];
   const size_t smem = (size_t)fp.soff[e.K] * 16;
-  if (e.K >= 2 && smem <= 48 * 1024) {
+  if (e.K >= 2 && smem <= 40 * 1024) {  // 48 KB without opt-in, static shared memory included
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(F, (int64_t)h->sm_count * 8));
     vet::k_entropy_frames<<<blocks, 256, smem, st>>>(e, fp);
   } else {
