@@ -283,6 +283,29 @@ def test_integration_stub_matches_the_abi(pkg):
         assert name in body, name
 
 
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The bench lines kept under profiles/ (one per GPU count) have every key of the bench contract, the roofline /
+    cpu_baseline / e2e objects included, and the strong-scaling block of configs[4]."""
+    import json
+    from pathlib import Path
+    prof = Path(__file__).resolve().parents[1] / "profiles"
+    for n in (1, 2, 4, 8):
+        d = json.loads((prof / f"bench_r02_n{n}.json").read_text())
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "clocks", "gpu_launches"):
+            assert k in d, (n, k)
+        assert d["n_gpus"] == n and d["gpu_launches"] > 0 and "workload" in d["config"]
+        for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert k in d["roofline"], (n, k)
+        for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+            assert k in d["e2e"], (n, k)
+        c5 = d["extra"]["c5_sharded"]
+        assert c5["n_gpus"] == n and c5["scaling"] == "strong" and c5["checks_ok"] is True
+        if n == 1:
+            for k in ("value", "unit", "cores", "kind", "sample"):
+                assert k in d["cpu_baseline"], k
+
+
 def test_tensor_core_dispatch_threshold_matches_the_header():
     """distributed.py pins the weighted-histogram kernel per job with the library's own threshold."""
     import re
